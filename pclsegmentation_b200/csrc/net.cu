@@ -1,0 +1,471 @@
+// pcls_net: op-list executor for the SqueezeSegV2 / Darknet forward (sm_100a).
+//
+// The Python model builders describe the graph (pcls_net_tensor / _conv / _maxpool3x3_s2 / _cam); this file
+// folds BatchNorm into the convolutions, packs weights, plans the activation arena by liveness and runs the ops
+// on a stream (optionally as a replayed CUDA graph).  Replaces model([lidar, mask]) == SqueezeSegV2.call
+// (pcl_segmentation/nets/SqueezeSegV2.py:285-325) / Darknet.call (nets/Darknet.py:279-314) + segmentation_head
+// (nets/SegmentationNetwork.py:58-69).
+#include "net.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace pcls {
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <typename T>
+static void pack_to(std::vector<uint16_t>& dst, const std::vector<float>& src) {
+  dst.resize(src.size());
+  for (size_t i = 0; i < src.size(); ++i) {
+    if (sizeof(T) == 2 && std::is_same<T, __half>::value) {
+      __half h = __float2half_rn(src[i]);
+      memcpy(&dst[i], &h, 2);
+    } else {
+      __nv_bfloat16 h = __float2bfloat16_rn(src[i]);
+      memcpy(&dst[i], &h, 2);
+    }
+  }
+}
+
+// y = gamma * (conv + b - mean) / sqrt(var + eps) + beta  ==  conv * scale + bias'
+static void fold_bn(int cout, const float* b, const float* gamma, const float* beta, const float* mean,
+                    const float* var, float eps, std::vector<double>& scale, std::vector<double>& bias) {
+  scale.assign(cout, 1.0);
+  bias.assign(cout, 0.0);
+  for (int c = 0; c < cout; ++c) {
+    const double b0 = b ? (double)b[c] : 0.0;
+    if (gamma) {
+      const double sc = (double)gamma[c] / std::sqrt((double)var[c] + (double)eps);
+      scale[c] = sc;
+      bias[c] = (b0 - (double)mean[c]) * sc + (double)beta[c];
+    } else {
+      bias[c] = b0;
+    }
+  }
+}
+
+int Net::add_tensor(int width, int channels, bool logits) {
+  TensorInfo t;
+  t.width = width;
+  t.channels = channels;
+  t.logits = logits;
+  tensors.push_back(t);
+  return (int)tensors.size() - 1;
+}
+
+size_t Net::tensor_frame_bytes(const TensorInfo& t) const {
+  return (size_t)H * t.width * t.channels * (t.logits ? 4 : 2);
+}
+
+int Net::add_conv(const pcls_conv_desc& d) {
+  PCLS_REQUIRE(!finalized, "pcls_net_conv: net already finalized");
+  ConvLayer L;
+  if (d.kind == PCLS_CONV) {
+    if (d.kh == 1 && d.kw == 1 && d.stride_w == 1) L.p.mode = MODE_1x1;
+    else if (d.kh == 3 && d.kw == 3 && d.stride_w == 1) L.p.mode = MODE_3x3_S1;
+    else if (d.kh == 3 && d.kw == 3 && d.stride_w == 2) L.p.mode = MODE_3x3_S2;
+    else PCLS_REQUIRE(false, "pcls_net_conv: unsupported Conv2D %dx%d stride_w %d", d.kh, d.kw, d.stride_w);
+  } else if (d.kind == PCLS_DECONV_1x4_S2) {
+    PCLS_REQUIRE(d.kh == 1 && d.kw == 4 && d.stride_w == 2, "pcls_net_conv: transposed conv must be [1,4] stride [1,2]");
+    L.p.mode = MODE_DECONV;
+  } else {
+    PCLS_REQUIRE(false, "pcls_net_conv: unknown kind %d", d.kind);
+  }
+  PCLS_REQUIRE(d.in_tensor >= 0 && d.in_tensor < (int)tensors.size() && d.out_tensor > 0 &&
+                   d.out_tensor < (int)tensors.size() && d.in_tensor != d.out_tensor,
+               "pcls_net_conv: bad tensor ids in=%d out=%d", d.in_tensor, d.out_tensor);
+  const TensorInfo& ti = tensors[d.in_tensor];
+  const TensorInfo& to = tensors[d.out_tensor];
+  PCLS_REQUIRE(!ti.logits, "pcls_net_conv: cannot read a logits tensor");
+  PCLS_REQUIRE(d.cin >= 1 && d.cin <= ti.channels && d.cout >= 1, "pcls_net_conv: cin %d exceeds input tensor channels %d",
+               d.cin, ti.channels);
+  PCLS_REQUIRE(d.out_channel_offset >= 0 && d.out_channel_offset + d.cout <= to.channels,
+               "pcls_net_conv: output slice [%d,%d) exceeds tensor channels %d", d.out_channel_offset,
+               d.out_channel_offset + d.cout, to.channels);
+  PCLS_REQUIRE((d.out_is_logits != 0) == to.logits, "pcls_net_conv: out_is_logits does not match the output tensor");
+  PCLS_REQUIRE(to.logits || d.out_channel_offset % 8 == 0, "pcls_net_conv: channel offset must be a multiple of 8");
+  int wout = ti.width;
+  if (L.p.mode == MODE_3x3_S2) wout = (ti.width + 1) / 2;
+  if (L.p.mode == MODE_DECONV) wout = ti.width * 2;
+  PCLS_REQUIRE(to.width == wout, "pcls_net_conv: output width %d, expected %d", to.width, wout);
+  PCLS_REQUIRE(d.h_kernel != nullptr, "pcls_net_conv: kernel is NULL");
+  const bool bn = d.h_bn_gamma != nullptr;
+  PCLS_REQUIRE(!bn || (d.h_bn_beta && d.h_bn_mean && d.h_bn_var), "pcls_net_conv: incomplete BatchNorm parameters");
+  PCLS_REQUIRE(d.act >= 0 && d.act <= 2, "pcls_net_conv: bad activation %d", d.act);
+  const int res[2] = {d.residual0, d.residual1};
+  for (int r = 0; r < 2; ++r) {
+    if (res[r] < 0) continue;
+    PCLS_REQUIRE(res[r] < (int)tensors.size() && !tensors[res[r]].logits && tensors[res[r]].width == to.width &&
+                     d.out_channel_offset + d.cout <= tensors[res[r]].channels && res[r] != d.out_tensor,
+                 "pcls_net_conv: residual tensor %d does not match the output", res[r]);
+  }
+
+  ConvParams& p = L.p;
+  p.H = H; p.Win = ti.width; p.Wout = wout;
+  p.cin = d.cin; p.cin_pad = (d.cin + 15) / 16 * 16;
+  p.in_channels = ti.channels;
+  p.cout = d.cout; p.cout_pad = (d.cout + 15) / 16 * 16;
+  p.out_channels = to.channels; p.out_coff = d.out_channel_offset;
+  p.act = d.act;
+  p.ntaps = (p.mode == MODE_1x1) ? 1 : (p.mode == MODE_DECONV ? 4 : 9);
+  p.pad_left = 0;
+  if (p.mode == MODE_3x3_S2) {
+    const int total = std::max((wout - 1) * 2 + 3 - ti.width, 0);
+    p.pad_left = total / 2;
+  }
+  p.out_f32 = d.out_is_logits ? 1 : 0;
+  p.res0_channels = d.residual0 >= 0 ? tensors[d.residual0].channels : 0;
+  p.res1_channels = d.residual1 >= 0 ? tensors[d.residual1].channels : 0;
+  L.in = d.in_tensor; L.out = d.out_tensor; L.res0 = d.residual0; L.res1 = d.residual1;
+
+  // fold BN, pack [tap][cout_pad][cin_pad]
+  std::vector<double> scale, bias;
+  fold_bn(d.cout, d.h_bias, d.h_bn_gamma, d.h_bn_beta, d.h_bn_mean, d.h_bn_var, d.bn_eps, scale, bias);
+  L.w_f32.assign((size_t)p.ntaps * p.cout_pad * p.cin_pad, 0.0f);
+  for (int t = 0; t < p.ntaps; ++t)
+    for (int co = 0; co < d.cout; ++co)
+      for (int ci = 0; ci < d.cin; ++ci) {
+        const size_t src = (d.kind == PCLS_CONV) ? ((size_t)t * d.cin + ci) * d.cout + co   // [kh,kw,Cin,Cout]
+                                                 : ((size_t)t * d.cout + co) * d.cin + ci;  // [1,4,Cout,Cin]
+        L.w_f32[((size_t)t * p.cout_pad + co) * p.cin_pad + ci] = (float)((double)d.h_kernel[src] * scale[co]);
+      }
+  L.bias_f32.assign(p.cout_pad, 0.0f);
+  for (int co = 0; co < d.cout; ++co) L.bias_f32[co] = (float)bias[co];
+
+  convs.push_back(std::move(L));
+  ops.push_back({OP_CONV, (int)convs.size() - 1});
+  return PCLS_OK;
+}
+
+int Net::add_pool(int in, int out) {
+  PCLS_REQUIRE(!finalized, "pcls_net_maxpool3x3_s2: net already finalized");
+  PCLS_REQUIRE(in >= 0 && in < (int)tensors.size() && out > 0 && out < (int)tensors.size() && in != out,
+               "pcls_net_maxpool3x3_s2: bad tensor ids");
+  const TensorInfo &ti = tensors[in], &to = tensors[out];
+  PCLS_REQUIRE(!ti.logits && !to.logits && ti.channels == to.channels && to.width == (ti.width + 1) / 2,
+               "pcls_net_maxpool3x3_s2: shape mismatch");
+  PoolLayer L;
+  L.in = in; L.out = out;
+  L.pad_left = std::max((to.width - 1) * 2 + 3 - ti.width, 0) / 2;
+  pools.push_back(L);
+  ops.push_back({OP_POOL, (int)pools.size() - 1});
+  return PCLS_OK;
+}
+
+int Net::add_cam(const pcls_cam_desc& d) {
+  PCLS_REQUIRE(!finalized, "pcls_net_cam: net already finalized");
+  PCLS_REQUIRE(d.in_tensor >= 0 && d.in_tensor < (int)tensors.size() && d.out_tensor > 0 &&
+                   d.out_tensor < (int)tensors.size() && d.in_tensor != d.out_tensor,
+               "pcls_net_cam: bad tensor ids");
+  const TensorInfo &ti = tensors[d.in_tensor], &to = tensors[d.out_tensor];
+  PCLS_REQUIRE(ti.channels == d.channels && to.channels == d.channels && ti.width == to.width && !ti.logits && !to.logits,
+               "pcls_net_cam: shape mismatch");
+  PCLS_REQUIRE((d.channels == 64 || d.channels == 128) && d.reduced == d.channels / 16,
+               "pcls_net_cam: supported channels 64/128 with reduction 16 (got %d -> %d)", d.channels, d.reduced);
+  PCLS_REQUIRE(d.h_sq_kernel && d.h_ex_kernel, "pcls_net_cam: kernels must not be NULL");
+  CamLayer L;
+  L.in = d.in_tensor; L.out = d.out_tensor; L.C = d.channels; L.R = d.reduced;
+  std::vector<double> s1, bb1, s2, bb2;
+  fold_bn(L.R, d.h_sq_bias, d.h_sq_gamma, d.h_sq_beta, d.h_sq_mean, d.h_sq_var, d.bn_eps, s1, bb1);
+  fold_bn(L.C, d.h_ex_bias, d.h_ex_gamma, d.h_ex_beta, d.h_ex_mean, d.h_ex_var, d.bn_eps, s2, bb2);
+  L.h.resize((size_t)2 * L.C * L.R + L.R + L.C);
+  float* w1 = L.h.data();           // [C][R]  Keras [1,1,C,R]
+  float* w2 = w1 + L.C * L.R;       // [R][C]  Keras [1,1,R,C]
+  float* b1 = w2 + L.R * L.C;
+  float* b2 = b1 + L.R;
+  for (int c = 0; c < L.C; ++c)
+    for (int j = 0; j < L.R; ++j) w1[c * L.R + j] = (float)((double)d.h_sq_kernel[c * L.R + j] * s1[j]);
+  for (int j = 0; j < L.R; ++j)
+    for (int c = 0; c < L.C; ++c) w2[j * L.C + c] = (float)((double)d.h_ex_kernel[j * L.C + c] * s2[c]);
+  for (int j = 0; j < L.R; ++j) b1[j] = (float)bb1[j];
+  for (int c = 0; c < L.C; ++c) b2[c] = (float)bb2[c];
+  cams.push_back(std::move(L));
+  ops.push_back({OP_CAM, (int)cams.size() - 1});
+  return PCLS_OK;
+}
+
+void Net::op_tensors(const OpRef& op, std::vector<int>& reads, std::vector<int>& writes) const {
+  reads.clear(); writes.clear();
+  if (op.type == OP_CONV) {
+    const ConvLayer& L = convs[op.index];
+    reads.push_back(L.in);
+    if (L.res0 >= 0) reads.push_back(L.res0);
+    if (L.res1 >= 0) reads.push_back(L.res1);
+    writes.push_back(L.out);
+  } else if (op.type == OP_POOL) {
+    reads.push_back(pools[op.index].in); writes.push_back(pools[op.index].out);
+  } else {
+    reads.push_back(cams[op.index].in); writes.push_back(cams[op.index].out);
+  }
+}
+
+int Net::finalize(int logits_tensor_, int num_classes_, int none_index_) {
+  PCLS_REQUIRE(!finalized, "pcls_net_finalize: already finalized");
+  PCLS_REQUIRE(logits_tensor_ > 0 && logits_tensor_ < (int)tensors.size() && tensors[logits_tensor_].logits,
+               "pcls_net_finalize: logits tensor id %d is not a logits tensor", logits_tensor_);
+  PCLS_REQUIRE(num_classes_ >= 1 && num_classes_ <= 32 && tensors[logits_tensor_].channels == num_classes_ &&
+                   tensors[logits_tensor_].width == W,
+               "pcls_net_finalize: logits tensor must be [B,H,W,num_classes] with num_classes <= 32");
+  PCLS_REQUIRE(none_index_ >= 0 && none_index_ < num_classes_, "pcls_net_finalize: none_index out of range");
+  logits_tensor = logits_tensor_; num_classes = num_classes_; none_index = none_index_;
+
+  // liveness: first write .. last read (op order); the logits tensor lives to the end (head reads it)
+  const int n_ops = (int)ops.size();
+  std::vector<int> reads, writes;
+  for (auto& t : tensors) { t.first = -1; t.last = -1; }
+  tensors[0].first = -1; tensors[0].last = -1;  // input: written by the input kernel before op 0
+  for (int i = 0; i < n_ops; ++i) {
+    op_tensors(ops[i], reads, writes);
+    for (int r : reads) {
+      PCLS_REQUIRE(r == 0 || tensors[r].first >= 0, "pcls_net_finalize: op %d reads tensor %d before it is written", i, r);
+      tensors[r].last = std::max(tensors[r].last, i);
+    }
+    for (int w : writes) {
+      if (tensors[w].first < 0) tensors[w].first = i;
+      tensors[w].last = std::max(tensors[w].last, i);
+    }
+  }
+  tensors[logits_tensor].last = n_ops;
+
+  // greedy first-fit arena planning (per-frame offsets; scaled by the frames per pass)
+  struct Block { size_t off, size; };
+  std::vector<Block> free_list;
+  size_t top = 0;
+  auto alloc = [&](size_t size) -> size_t {
+    size = align_up(size, 1024);
+    for (size_t i = 0; i < free_list.size(); ++i) {
+      if (free_list[i].size >= size) {
+        size_t off = free_list[i].off;
+        free_list[i].off += size; free_list[i].size -= size;
+        if (free_list[i].size == 0) free_list.erase(free_list.begin() + i);
+        return off;
+      }
+    }
+    size_t off = top; top += size; return off;
+  };
+  auto release = [&](size_t off, size_t size) {
+    size = align_up(size, 1024);
+    free_list.push_back({off, size});
+    std::sort(free_list.begin(), free_list.end(), [](const Block& a, const Block& b) { return a.off < b.off; });
+    for (size_t i = 0; i + 1 < free_list.size();) {
+      if (free_list[i].off + free_list[i].size == free_list[i + 1].off) {
+        free_list[i].size += free_list[i + 1].size; free_list.erase(free_list.begin() + i + 1);
+      } else ++i;
+    }
+    if (!free_list.empty() && free_list.back().off + free_list.back().size == top) { top = free_list.back().off; free_list.pop_back(); }
+  };
+  tensors[0].offset = alloc(tensor_frame_bytes(tensors[0]));
+  mask_offset = alloc((size_t)H * W);  // u8 mask lives for the whole pass
+  size_t peak = top;
+  for (int i = 0; i < n_ops; ++i) {
+    op_tensors(ops[i], reads, writes);
+    for (int w : writes)
+      if (tensors[w].first == i) { tensors[w].offset = alloc(tensor_frame_bytes(tensors[w])); peak = std::max(peak, top); }
+    // release after the op: tensors whose last use is this op (never the input's slot before its last read)
+    for (size_t t = 0; t < tensors.size(); ++t)
+      if (tensors[t].last == i && (int)t != logits_tensor && !(t == 0 && tensors[0].last < 0))
+        release(tensors[t].offset, tensor_frame_bytes(tensors[t]));
+  }
+  frame_bytes = align_up(peak, 1024);
+  for (size_t t = 0; t < tensors.size(); ++t)
+    PCLS_REQUIRE(t == 0 || tensors[t].first >= 0, "pcls_net_finalize: tensor %d is never written", (int)t);
+
+  frames_per_pass = (micro_batch > 0 && micro_batch < max_batch) ? micro_batch : max_batch;
+  PCLS_CHECK_CUDA(cudaMalloc(&arena, frame_bytes * (size_t)frames_per_pass));
+  arena_bytes = frame_bytes * (size_t)frames_per_pass;
+
+  // upload weights
+  size_t wbytes = 0;
+  for (auto& L : convs) wbytes += align_up(L.w_f32.size() * 2, 256) + align_up(L.bias_f32.size() * 4, 256);
+  for (auto& L : cams) wbytes += align_up(L.h.size() * 4, 256);
+  PCLS_CHECK_CUDA(cudaMalloc(&weights, std::max<size_t>(wbytes, 256)));
+  weight_bytes = wbytes;
+  size_t off = 0;
+  std::vector<uint16_t> packed;
+  for (auto& L : convs) {
+    if (precision == PCLS_F16) pack_to<__half>(packed, L.w_f32); else pack_to<__nv_bfloat16>(packed, L.w_f32);
+    PCLS_CHECK_CUDA(cudaMemcpy((char*)weights + off, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
+    L.p.w = (char*)weights + off; off += align_up(packed.size() * 2, 256);
+    PCLS_CHECK_CUDA(cudaMemcpy((char*)weights + off, L.bias_f32.data(), L.bias_f32.size() * 4, cudaMemcpyHostToDevice));
+    L.p.bias = (const float*)((char*)weights + off); off += align_up(L.bias_f32.size() * 4, 256);
+  }
+  for (auto& L : cams) {
+    PCLS_CHECK_CUDA(cudaMemcpy((char*)weights + off, L.h.data(), L.h.size() * 4, cudaMemcpyHostToDevice));
+    const float* base = (const float*)((char*)weights + off);
+    L.p.C = L.C; L.p.R = L.R;
+    L.p.w1 = base; L.p.w2 = base + L.C * L.R; L.p.b1 = L.p.w2 + L.R * L.C; L.p.b2 = L.p.b1 + L.R;
+    off += align_up(L.h.size() * 4, 256);
+  }
+  int rc = tc_prepare();
+  if (rc != PCLS_OK) return rc;
+  finalized = true;
+  return PCLS_OK;
+}
+
+void* Net::tensor_ptr(int t, int frames) const {
+  // per-pass layout: every tensor is contiguous over the frames of the pass
+  (void)frames;
+  return (char*)arena + tensors[t].offset * (size_t)frames_per_pass;
+}
+
+template <typename T>
+int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool raw, const double* mean5,
+                  const double* std5, int nb, float* logits, float* probs, int32_t* preds, cudaStream_t s) {
+  const int64_t n_pixels = (int64_t)nb * H * W;
+  uint8_t* mask_buf = (uint8_t*)arena + mask_offset * (size_t)frames_per_pass;
+  int rc = launch_net_input<T>(lidar, channels, mask, raw, mean5, std5, n_pixels, (T*)tensor_ptr(0, nb), mask_buf, s);
+  if (rc) return rc;
+  float* logits_buf = logits ? logits : (float*)tensor_ptr(logits_tensor, nb);
+  for (const OpRef& op : ops) {
+    if (op.type == OP_CONV) {
+      ConvLayer& L = convs[op.index];
+      ConvParams p = L.p;
+      p.in = tensor_ptr(L.in, nb);
+      p.out = (L.out == logits_tensor) ? (void*)logits_buf : tensor_ptr(L.out, nb);
+      p.res0 = L.res0 >= 0 ? tensor_ptr(L.res0, nb) : nullptr;
+      p.res1 = L.res1 >= 0 ? tensor_ptr(L.res1, nb) : nullptr;
+      if (conv_impl == 0 && L.tc_ok) rc = tc_launch(L, p, nb, s);
+      else rc = launch_conv_direct<T>(p, nb, s);
+    } else if (op.type == OP_POOL) {
+      const PoolLayer& L = pools[op.index];
+      rc = launch_maxpool3x3_s2<T>((const T*)tensor_ptr(L.in, nb), (T*)tensor_ptr(L.out, nb), nb, H, tensors[L.in].width,
+                                   tensors[L.out].width, tensors[L.in].channels, L.pad_left, s);
+    } else {
+      const CamLayer& L = cams[op.index];
+      rc = launch_cam<T>((const T*)tensor_ptr(L.in, nb), (T*)tensor_ptr(L.out, nb), L.p, nb, H, tensors[L.in].width, s);
+    }
+    if (rc) return rc;
+  }
+  return launch_head(logits_buf, mask_buf, n_pixels, num_classes, none_index, probs, preds, s);
+}
+
+int Net::forward(const float* lidar, int channels, const uint8_t* mask, const double* mean5, const double* std5, int B,
+                 float* logits, float* probs, int32_t* preds, cudaStream_t s) {
+  PCLS_REQUIRE(finalized, "pcls_net_forward: call pcls_net_finalize first");
+  PCLS_REQUIRE(B >= 0 && B <= max_batch, "pcls_net_forward: batch %d exceeds max_batch %d", B, max_batch);
+  const bool raw = mean5 != nullptr;
+  PCLS_REQUIRE(raw ? (channels == 5 || channels == 6) : channels == 6,
+               "pcls_net_forward: channels must be 6 (normalised input) or 5/6 with mean/std (raw input), got %d", channels);
+  PCLS_REQUIRE(!raw || std5 != nullptr, "pcls_net_forward: std is NULL");
+  PCLS_REQUIRE(B == 0 || (lidar != nullptr && preds != nullptr), "pcls_net_forward: lidar/preds must not be NULL");
+  const size_t px = (size_t)H * W;
+  for (int b0 = 0; b0 < B; b0 += frames_per_pass) {
+    const int nb = std::min(frames_per_pass, B - b0);
+    const float* l = lidar + (size_t)b0 * px * channels;
+    const uint8_t* m = mask ? mask + (size_t)b0 * px : nullptr;
+    float* lg = logits ? logits + (size_t)b0 * px * num_classes : nullptr;
+    float* pr = probs ? probs + (size_t)b0 * px * num_classes : nullptr;
+    int32_t* pd = preds + (size_t)b0 * px;
+    int rc = (precision == PCLS_F16) ? run_pass<__half>(l, channels, m, raw, mean5, std5, nb, lg, pr, pd, s)
+                                     : run_pass<__nv_bfloat16>(l, channels, m, raw, mean5, std5, nb, lg, pr, pd, s);
+    if (rc) return rc;
+  }
+  last_B = B;
+  return PCLS_OK;
+}
+
+int Net::read_tensor(int t, int B, float* out, cudaStream_t s) {
+  PCLS_REQUIRE(finalized && t >= 0 && t < (int)tensors.size(), "pcls_net_read_tensor: bad tensor id %d", t);
+  PCLS_REQUIRE(B >= 0 && B <= frames_per_pass, "pcls_net_read_tensor: B exceeds the frames of one pass");
+  const TensorInfo& ti = tensors[t];
+  const int64_t n = (int64_t)B * H * ti.width * ti.channels;
+  if (ti.logits) { PCLS_CHECK_CUDA(cudaMemcpyAsync(out, tensor_ptr(t, B), n * 4, cudaMemcpyDeviceToDevice, s)); return PCLS_OK; }
+  return precision == PCLS_F16 ? launch_tensor_to_f32<__half>((const __half*)tensor_ptr(t, B), out, n, s)
+                               : launch_tensor_to_f32<__nv_bfloat16>((const __nv_bfloat16*)tensor_ptr(t, B), out, n, s);
+}
+
+Net::~Net() {
+  if (arena) cudaFree(arena);
+  if (weights) cudaFree(weights);
+  tc_release();
+}
+
+}  // namespace pcls
+
+using namespace pcls;
+
+extern "C" int pcls_net_create(pcls_net** out, int H, int W, int precision, int max_batch) {
+  PCLS_REQUIRE(out != nullptr, "pcls_net_create: out is NULL");
+  PCLS_REQUIRE(H > 0 && W > 0 && max_batch > 0, "pcls_net_create: bad shape H=%d W=%d max_batch=%d", H, W, max_batch);
+  PCLS_REQUIRE(precision == PCLS_F16 || precision == PCLS_BF16, "pcls_net_create: bad precision %d", precision);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("pcls_net_create: no CUDA device (libpclseg has no CPU fallback)");
+    return PCLS_ERR_CUDA;
+  }
+  Net* n = new Net();
+  n->H = H; n->W = W; n->precision = precision; n->max_batch = max_batch;
+  n->add_tensor(W, 8, false);  // tensor 0: network input, 6 channels + 2 zero pad
+  *out = reinterpret_cast<pcls_net*>(n);
+  return PCLS_OK;
+}
+
+extern "C" void pcls_net_destroy(pcls_net* net) { delete reinterpret_cast<Net*>(net); }
+
+extern "C" int pcls_net_tensor(pcls_net* net, int width, int channels, int is_logits) {
+  Net* n = reinterpret_cast<Net*>(net);
+  PCLS_REQUIRE(n != nullptr && !n->finalized, "pcls_net_tensor: bad or finalized net");
+  PCLS_REQUIRE(width > 0 && channels > 0 && (is_logits || channels % 8 == 0),
+               "pcls_net_tensor: width %d channels %d (activation channels must be a multiple of 8)", width, channels);
+  return n->add_tensor(width, channels, is_logits != 0);
+}
+
+extern "C" int pcls_net_conv(pcls_net* net, const pcls_conv_desc* desc) {
+  PCLS_REQUIRE(net != nullptr && desc != nullptr, "pcls_net_conv: NULL argument");
+  return reinterpret_cast<Net*>(net)->add_conv(*desc);
+}
+
+extern "C" int pcls_net_maxpool3x3_s2(pcls_net* net, int in_tensor, int out_tensor) {
+  PCLS_REQUIRE(net != nullptr, "pcls_net_maxpool3x3_s2: NULL net");
+  return reinterpret_cast<Net*>(net)->add_pool(in_tensor, out_tensor);
+}
+
+extern "C" int pcls_net_cam(pcls_net* net, const pcls_cam_desc* desc) {
+  PCLS_REQUIRE(net != nullptr && desc != nullptr, "pcls_net_cam: NULL argument");
+  return reinterpret_cast<Net*>(net)->add_cam(*desc);
+}
+
+extern "C" int pcls_net_finalize(pcls_net* net, int logits_tensor, int num_classes, int none_index) {
+  PCLS_REQUIRE(net != nullptr, "pcls_net_finalize: NULL net");
+  return reinterpret_cast<Net*>(net)->finalize(logits_tensor, num_classes, none_index);
+}
+
+extern "C" int pcls_net_forward(pcls_net* net, const float* lidar, int channels, const uint8_t* mask,
+                                const double* h_mean5, const double* h_std5, int B, float* logits, float* probs,
+                                int32_t* preds, pcls_stream stream) {
+  PCLS_REQUIRE(net != nullptr, "pcls_net_forward: NULL net");
+  return reinterpret_cast<Net*>(net)->forward(lidar, channels, mask, h_mean5, h_std5, B, logits, probs, preds,
+                                              (cudaStream_t)stream);
+}
+
+extern "C" int pcls_net_read_tensor(pcls_net* net, int tensor, int B, float* out, pcls_stream stream) {
+  PCLS_REQUIRE(net != nullptr && out != nullptr, "pcls_net_read_tensor: NULL argument");
+  return reinterpret_cast<Net*>(net)->read_tensor(tensor, B, out, (cudaStream_t)stream);
+}
+
+extern "C" int pcls_net_launches_per_forward(const pcls_net* net) {
+  const Net* n = reinterpret_cast<const Net*>(net);
+  if (!n) return 0;
+  return (int)n->ops.size() + 2;  // + input kernel + head kernel (per pass)
+}
+
+extern "C" int64_t pcls_net_workspace_bytes(const pcls_net* net) {
+  const Net* n = reinterpret_cast<const Net*>(net);
+  return n ? (int64_t)(n->arena_bytes + n->weight_bytes) : 0;
+}
+
+extern "C" int pcls_net_set_option(pcls_net* net, const char* name, int value) {
+  Net* n = reinterpret_cast<Net*>(net);
+  PCLS_REQUIRE(n != nullptr && name != nullptr, "pcls_net_set_option: NULL argument");
+  if (!strcmp(name, "conv_impl")) { PCLS_REQUIRE(value == 0 || value == 1, "conv_impl must be 0 or 1"); n->conv_impl = value; return PCLS_OK; }
+  if (!strcmp(name, "use_graph")) { n->use_graph = value != 0; return PCLS_OK; }
+  if (!strcmp(name, "micro_batch")) {
+    PCLS_REQUIRE(!n->finalized, "micro_batch must be set before pcls_net_finalize");
+    PCLS_REQUIRE(value >= 0, "micro_batch must be >= 0");
+    n->micro_batch = value; return PCLS_OK;
+  }
+  set_error("pcls_net_set_option: unknown option '%s'", name);
+  return PCLS_ERR_INVALID;
+}

@@ -1,0 +1,82 @@
+// Internal definition of pcls_net (the op-list executor).
+#pragma once
+#include <vector>
+
+#include "nn_kernels.cuh"
+
+namespace pcls {
+
+struct TensorInfo {
+  int width = 0, channels = 0;
+  bool logits = false;
+  int first = -1, last = -1;  // op indices of first write / last use
+  size_t offset = 0;          // per-frame byte offset inside the arena (scaled by frames_per_pass)
+};
+
+struct TcPlan;  // tcgen05 launch plan of one conv layer (conv_tc.cu)
+
+struct ConvLayer {
+  ConvParams p;
+  int in = -1, out = -1, res0 = -1, res1 = -1;
+  std::vector<float> w_f32;     // folded, packed [tap][cout_pad][cin_pad]
+  std::vector<float> bias_f32;  // folded [cout_pad]
+  bool tc_ok = false;
+  TcPlan* tc = nullptr;
+};
+
+struct PoolLayer { int in, out, pad_left; };
+
+struct CamLayer {
+  int in, out, C, R;
+  std::vector<float> h;  // w1 [C][R], w2 [R][C], b1 [R], b2 [C]
+  CamParams p;
+};
+
+enum OpType { OP_CONV = 0, OP_POOL = 1, OP_CAM = 2 };
+struct OpRef { int type, index; };
+
+struct Net {
+  int H = 0, W = 0, precision = PCLS_F16, max_batch = 0;
+  std::vector<TensorInfo> tensors;
+  std::vector<ConvLayer> convs;
+  std::vector<PoolLayer> pools;
+  std::vector<CamLayer> cams;
+  std::vector<OpRef> ops;
+  bool finalized = false;
+  int logits_tensor = -1, num_classes = 0, none_index = 0;
+  // execution knobs
+  int conv_impl = 0;
+  bool use_graph = true;
+  int micro_batch = 0;
+  // device state
+  int frames_per_pass = 0;
+  size_t frame_bytes = 0, mask_offset = 0;
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  void* weights = nullptr;
+  size_t weight_bytes = 0;
+  int last_B = 0;
+
+  ~Net();
+  int add_tensor(int width, int channels, bool logits);
+  size_t tensor_frame_bytes(const TensorInfo& t) const;
+  int add_conv(const pcls_conv_desc& d);
+  int add_pool(int in, int out);
+  int add_cam(const pcls_cam_desc& d);
+  void op_tensors(const OpRef& op, std::vector<int>& reads, std::vector<int>& writes) const;
+  int finalize(int logits_tensor, int num_classes, int none_index);
+  void* tensor_ptr(int t, int frames) const;
+  template <typename T>
+  int run_pass(const float* lidar, int channels, const uint8_t* mask, bool raw, const double* mean5, const double* std5,
+               int nb, float* logits, float* probs, int32_t* preds, cudaStream_t s);
+  int forward(const float* lidar, int channels, const uint8_t* mask, const double* mean5, const double* std5, int B,
+              float* logits, float* probs, int32_t* preds, cudaStream_t s);
+  int read_tensor(int t, int B, float* out, cudaStream_t s);
+
+  // tcgen05 implicit-GEMM path (conv_tc.cu)
+  int tc_prepare();
+  int tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s);
+  void tc_release();
+};
+
+}  // namespace pcls

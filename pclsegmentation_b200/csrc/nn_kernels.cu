@@ -1,0 +1,398 @@
+// CUDA-core network kernels (sm_100a): generic direct convolution (every conv flavour of the two nets),
+// network input conversion with the fused input stage, 3x3/s2 max-pool, the fused CAM gate.
+//
+// The direct convolution is the always-available CUDA path and the on-GPU cross-check for the tcgen05
+// implicit-GEMM kernel (conv_tc.cu), which takes over every layer whose channel counts fit UMMA tiles.
+#include "nn_kernels.cuh"
+
+namespace pcls {
+
+// --------------------------------------------------------------------------------------------------
+// tap geometry shared by all conv implementations
+// --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool tap_source(const ConvParams& p, int tap, int h, int wo, int& hi, int& wi) {
+  switch (p.mode) {
+    case MODE_1x1:
+      hi = h; wi = wo; return true;
+    case MODE_3x3_S1:
+      hi = h + tap / 3 - 1; wi = wo + tap % 3 - 1; break;
+    case MODE_3x3_S2:  // TF SAME: total pad 1 for even Win -> 0 left / 1 right
+      hi = h + tap / 3 - 1; wi = 2 * wo + tap % 3 - p.pad_left; break;
+    default: {         // MODE_DECONV: out[m] += in[j] * w[k] with m = 2j + k - 1
+      const int t = wo + 1 - tap;
+      if (t < 0 || (t & 1)) return false;
+      hi = h; wi = t >> 1; break;
+    }
+  }
+  return hi >= 0 && hi < p.H && wi >= 0 && wi < p.Win;
+}
+
+// --------------------------------------------------------------------------------------------------
+// direct convolution: 64 output pixels x 64 output channels per CTA, fp32 accumulate
+// --------------------------------------------------------------------------------------------------
+constexpr int DC_PX = 64, DC_CO = 64, DC_K = 16, DC_LD = 68;
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+conv_direct_kernel(const ConvParams p, const int64_t n_out) {
+  __shared__ __align__(16) float As[DC_K][DC_LD];
+  __shared__ __align__(16) float Ws[DC_K][DC_LD];
+  const int tid = threadIdx.x;
+  const int pxg = tid & 15, cg = tid >> 4;
+  const int64_t pix0 = (int64_t)blockIdx.x * DC_PX;
+  const int co0 = blockIdx.y * DC_CO;
+
+  // the pixel / weight row this thread stages
+  const int lpx = tid >> 1, lj = tid & 1;
+  const int64_t lpix = pix0 + lpx;
+  const bool lvalid = lpix < n_out;
+  int lb = 0, lh = 0, lwo = 0;
+  if (lvalid) {
+    lwo = (int)(lpix % p.Wout);
+    const int64_t r = lpix / p.Wout;
+    lh = (int)(r % p.H);
+    lb = (int)(r / p.H);
+  }
+  const int lco = co0 + lpx;  // weight row staged by this thread
+  const T* in = reinterpret_cast<const T*>(p.in);
+  const T* wt = reinterpret_cast<const T*>(p.w);
+
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+
+  for (int tap = 0; tap < p.ntaps; ++tap) {
+    int hi = 0, wi = 0;
+    const bool src_ok = lvalid && tap_source(p, tap, lh, lwo, hi, wi);
+    const T* src = in + (((int64_t)lb * p.H + hi) * p.Win + wi) * p.in_channels;
+    const T* wrow = wt + ((int64_t)tap * p.cout_pad + lco) * p.cin_pad;
+    for (int ck = 0; ck < p.cin_pad; ck += DC_K) {
+      const int c = ck + 8 * lj;
+      float f[8];
+      if (src_ok && c < p.in_channels) {
+        unpack8<T>(__ldg(reinterpret_cast<const int4*>(src + c)), f);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = 0.0f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) As[8 * lj + i][lpx] = f[i];
+      if (lco < p.cout_pad) {
+        unpack8<T>(__ldg(reinterpret_cast<const int4*>(wrow + c)), f);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = 0.0f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) Ws[8 * lj + i][lpx] = f[i];
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < DC_K; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[k][pxg * 4]);
+        const float4 w0 = *reinterpret_cast<const float4*>(&Ws[k][cg * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&Ws[k][cg * 8 + 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+  // epilogue: bias (BN folded), activation, residual adds (after the activation), store
+  const T* res0 = reinterpret_cast<const T*>(p.res0);
+  const T* res1 = reinterpret_cast<const T*>(p.res1);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t pix = pix0 + pxg * 4 + i;
+    if (pix >= n_out) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int co = co0 + cg * 8 + j;
+      if (co >= p.cout) continue;
+      float v = apply_act(acc[i][j] + __ldg(p.bias + co), p.act);
+      if (res0) v += to_f32<T>(res0[pix * p.res0_channels + p.out_coff + co]);
+      if (res1) v += to_f32<T>(res1[pix * p.res1_channels + p.out_coff + co]);
+      if (p.out_f32) reinterpret_cast<float*>(p.out)[pix * p.out_channels + p.out_coff + co] = v;
+      else reinterpret_cast<T*>(p.out)[pix * p.out_channels + p.out_coff + co] = from_f32<T>(v);
+    }
+  }
+}
+
+template <typename T>
+int launch_conv_direct(const ConvParams& p, int B, cudaStream_t s) {
+  const int64_t n_out = (int64_t)B * p.H * p.Wout;
+  if (n_out == 0) return PCLS_OK;
+  dim3 grid((unsigned)ceil_div(n_out, DC_PX), (unsigned)ceil_div(p.cout, DC_CO));
+  conv_direct_kernel<T><<<grid, 128, 0, s>>>(p, n_out);
+  return check_launch("conv_direct_kernel");
+}
+template int launch_conv_direct<__half>(const ConvParams&, int, cudaStream_t);
+template int launch_conv_direct<__nv_bfloat16>(const ConvParams&, int, cudaStream_t);
+
+// --------------------------------------------------------------------------------------------------
+// network input: float32 [n,ch] -> 16-bit [n,8] (6 channels + 2 zero pad) + u8 mask, optional fused input stage
+// --------------------------------------------------------------------------------------------------
+struct Norm5f { double mean[5]; double std[5]; };
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+net_input_kernel(const float* __restrict__ lidar, int channels, const uint8_t* __restrict__ mask_in, int raw, Norm5f nrm,
+                 int64_t n_pixels, T* __restrict__ out8, uint8_t* __restrict__ mask_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pixels; p += stride) {
+    const float* s = lidar + p * channels;
+    float f[8];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) f[c] = __ldg(s + c);
+    bool m;
+    if (raw) {  // inference.py:50-62 fused: mask = depth > 0, float64 normalise, zero where empty, append mask
+      m = f[4] > 0.0f;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) f[c] = m ? (float)(((double)f[c] - nrm.mean[c]) / nrm.std[c]) : 0.0f;
+      f[5] = m ? 1.0f : 0.0f;
+      if (mask_in) m = mask_in[p] != 0;
+    } else {    // already normalised 6-channel reference input; channel 5 is the mask
+      f[5] = __ldg(s + 5);
+      m = mask_in ? (mask_in[p] != 0) : (f[5] != 0.0f);
+    }
+    f[6] = 0.0f; f[7] = 0.0f;
+    reinterpret_cast<int4*>(out8)[p] = pack8<T>(f);
+    mask_out[p] = m ? 1 : 0;
+  }
+}
+
+template <typename T>
+int launch_net_input(const float* lidar, int channels, const uint8_t* mask_in, bool raw, const double* mean5,
+                     const double* std5, int64_t n_pixels, T* out8, uint8_t* mask_out, cudaStream_t s) {
+  if (n_pixels == 0) return PCLS_OK;
+  Norm5f nrm;
+  for (int c = 0; c < 5; ++c) { nrm.mean[c] = raw ? mean5[c] : 0.0; nrm.std[c] = raw ? std5[c] : 1.0; }
+  int64_t blocks = ceil_div(n_pixels, 256);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  net_input_kernel<T><<<(int)blocks, 256, 0, s>>>(lidar, channels, mask_in, raw ? 1 : 0, nrm, n_pixels, out8, mask_out);
+  return check_launch("net_input_kernel");
+}
+template int launch_net_input<__half>(const float*, int, const uint8_t*, bool, const double*, const double*, int64_t,
+                                      __half*, uint8_t*, cudaStream_t);
+template int launch_net_input<__nv_bfloat16>(const float*, int, const uint8_t*, bool, const double*, const double*,
+                                             int64_t, __nv_bfloat16*, uint8_t*, cudaStream_t);
+
+// --------------------------------------------------------------------------------------------------
+// tf.nn.max_pool2d(ksize=3, strides=[1,2], padding='SAME'): rows h-1..h+1, cols 2wo-pl .. 2wo-pl+2
+// one thread = one output pixel x 8 channels (128-bit loads/stores); padding never wins the max
+// --------------------------------------------------------------------------------------------------
+template <typename T> struct Vec2;
+template <> struct Vec2<__half> { using type = __half2; };
+template <> struct Vec2<__nv_bfloat16> { using type = __nv_bfloat162; };
+
+template <typename T>
+__device__ __forceinline__ int4 max8(const int4& a, const int4& b) {
+  using V = typename Vec2<T>::type;
+  int4 r;
+  const V* x = reinterpret_cast<const V*>(&a);
+  const V* y = reinterpret_cast<const V*>(&b);
+  V* o = reinterpret_cast<V*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = __hmax2(x[i], y[i]);
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool3x3_s2_kernel(const int4* __restrict__ in, int4* __restrict__ out, int64_t n_vec, int H, int Win, int Wout,
+                     int CV, int pad_left) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+    const int cv = (int)(i % CV);
+    int64_t r = i / CV;
+    const int wo = (int)(r % Wout); r /= Wout;
+    const int h = (int)(r % H);
+    const int64_t b = r / H;
+    bool have = false;
+    int4 m = make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int hi = h + dy;
+      if (hi < 0 || hi >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int wi = 2 * wo + dx - pad_left;
+        if (wi < 0 || wi >= Win) continue;
+        const int4 v = __ldg(in + ((b * H + hi) * Win + wi) * CV + cv);
+        m = have ? max8<T>(m, v) : v;
+        have = true;
+      }
+    }
+    out[i] = m;
+  }
+}
+
+template <typename T>
+int launch_maxpool3x3_s2(const T* in, T* out, int B, int H, int Win, int Wout, int C, int pad_left, cudaStream_t s) {
+  const int CV = C / 8;
+  const int64_t n_vec = (int64_t)B * H * Wout * CV;
+  if (n_vec == 0) return PCLS_OK;
+  int64_t blocks = ceil_div(n_vec, 256);
+  const int64_t cap = (int64_t)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  maxpool3x3_s2_kernel<T><<<(int)blocks, 256, 0, s>>>(reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out),
+                                                     n_vec, H, Win, Wout, CV, pad_left);
+  return check_launch("maxpool3x3_s2_kernel");
+}
+template int launch_maxpool3x3_s2<__half>(const __half*, __half*, int, int, int, int, int, int, cudaStream_t);
+template int launch_maxpool3x3_s2<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, int, int, int,
+                                                 cudaStream_t);
+
+// --------------------------------------------------------------------------------------------------
+// CAM (nets/SqueezeSegV2.py:66-70), one kernel:
+//   pool = maxpool7x7_SAME(x); s = relu(W1^T pool + b1); e = sigmoid(W2^T s + b2); out = x * e
+// CTA tile = CAM_TH rows x CAM_TW cols x C channels.  Pass 1: horizontal 7-max from global (L1-resident
+// re-reads) into shared memory for CAM_TH+6 rows.  Pass 2: vertical 7-max from shared memory, then the two
+// tiny 1x1 convolutions: a thread owns 8 channels of a pixel, partial dot products are reduced across the
+// C/8 lanes of the pixel with xor-shuffles.
+// --------------------------------------------------------------------------------------------------
+constexpr int CAM_TH = 8;
+
+template <typename T, int C>
+__global__ void __launch_bounds__(256)
+cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int H, int W, int TW) {
+  constexpr int CV = C / 8;        // 16-byte vectors per pixel (8 or 16)
+  constexpr int R = C / 16;        // reduced channels (4 or 8)
+  extern __shared__ __align__(16) unsigned char cam_smem[];
+  int4* hmax = reinterpret_cast<int4*>(cam_smem);                        // [(TH+6)][TW][CV]
+  float* w1s = reinterpret_cast<float*>(hmax + (CAM_TH + 6) * TW * CV);  // [C][R]
+  float* w2s = w1s + C * R;                                              // [R][C]
+  float* b1s = w2s + R * C;                                              // [R]
+  float* b2s = b1s + R;                                                  // [C]
+  for (int i = threadIdx.x; i < C * R; i += blockDim.x) { w1s[i] = p.w1[i]; w2s[i] = p.w2[i]; }
+  for (int i = threadIdx.x; i < R; i += blockDim.x) b1s[i] = p.b1[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) b2s[i] = p.b2[i];
+
+  const int w0 = blockIdx.x * TW, h0 = blockIdx.y * CAM_TH;
+  const int64_t b = blockIdx.z;
+  const int4* img = in + b * H * W * CV;
+
+  // pass 1: horizontal max over cols w-3..w+3 (clipped), rows h0-3 .. h0+TH+2
+  const int n1 = (CAM_TH + 6) * TW * CV;
+  for (int i = threadIdx.x; i < n1; i += blockDim.x) {
+    const int cv = i % CV;
+    const int c = (i / CV) % TW;
+    const int r = i / (CV * TW);
+    const int h = h0 + r - 3, w = w0 + c;
+    int4 m = make_int4(0, 0, 0, 0);
+    if (h >= 0 && h < H && w < W) {
+      const int4* row = img + (int64_t)h * W * CV + cv;
+      m = __ldg(row + (int64_t)w * CV);
+#pragma unroll
+      for (int d = -3; d <= 3; ++d) {
+        const int ww = w + d;
+        if (d != 0 && ww >= 0 && ww < W) m = max8<T>(m, __ldg(row + (int64_t)ww * CV));
+      }
+    }
+    hmax[i] = m;
+  }
+  __syncthreads();
+
+  // pass 2: CV lanes per pixel
+  const int n2 = CAM_TH * TW * CV;
+  for (int i0 = 0; i0 < n2; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    const bool in_tile = i < n2;
+    const int cv = i % CV;
+    const int c = (i / CV) % TW;
+    const int r = i / (CV * TW);
+    const int h = h0 + r, w = w0 + c;
+    const bool valid = in_tile && h < H && w < W;
+    float pooled[8];
+    if (valid) {
+      int4 m = hmax[((r + 3) * TW + c) * CV + cv];
+#pragma unroll
+      for (int d = -3; d <= 3; ++d) {
+        const int hh = h + d;
+        if (d != 0 && hh >= 0 && hh < H) m = max8<T>(m, hmax[((r + 3 + d) * TW + c) * CV + cv]);
+      }
+      unpack8<T>(m, pooled);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pooled[k] = 0.0f;
+    }
+    float sq[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      float a = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a = fmaf(pooled[k], w1s[(cv * 8 + k) * R + j], a);
+      sq[j] = a;
+    }
+    // reduce over the CV lanes of this pixel (CV = 8 or 16 consecutive lanes, aligned)
+#pragma unroll
+    for (int off = CV / 2; off >= 1; off >>= 1)
+#pragma unroll
+      for (int j = 0; j < R; ++j) sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], off);
+#pragma unroll
+    for (int j = 0; j < R; ++j) sq[j] = fmaxf(sq[j] + b1s[j], 0.0f);
+    if (valid) {
+      const int64_t off = ((int64_t)h * W + w) * CV + cv;
+      float x[8];
+      unpack8<T>(__ldg(img + off), x);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float e = b2s[cv * 8 + k];
+#pragma unroll
+        for (int j = 0; j < R; ++j) e = fmaf(sq[j], w2s[j * C + cv * 8 + k], e);
+        e = 1.0f / (1.0f + expf(-e));
+        x[k] *= e;
+      }
+      out[b * H * W * CV + off] = pack8<T>(x);
+    }
+  }
+}
+
+template <typename T>
+int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, cudaStream_t s) {
+  if (B == 0) return PCLS_OK;
+  PCLS_REQUIRE(p.C == 64 || p.C == 128, "CAM: channels must be 64 or 128, got %d", p.C);
+  PCLS_REQUIRE(p.R == p.C / 16, "CAM: reduced channels must be C/16");
+  const int TW = 32;  // TW * CV is a multiple of the warp size, so the CV lanes of a pixel share a warp
+  const int CV = p.C / 8;
+  const size_t smem = (size_t)(CAM_TH + 6) * TW * CV * 16 + (size_t)(2 * p.C * p.R + p.R + p.C) * sizeof(float);
+  dim3 grid((unsigned)ceil_div(W, TW), (unsigned)ceil_div(H, CAM_TH), (unsigned)B);
+  if (p.C == 64) {
+    static bool attr64 = false;
+    if (!attr64) { PCLS_CHECK_CUDA(cudaFuncSetAttribute(cam_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr64 = true; }
+    cam_kernel<T, 64><<<grid, 256, smem, s>>>(reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), p, H, W, TW);
+  } else {
+    static bool attr128 = false;
+    if (!attr128) { PCLS_CHECK_CUDA(cudaFuncSetAttribute(cam_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr128 = true; }
+    cam_kernel<T, 128><<<grid, 256, smem, s>>>(reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), p, H, W, TW);
+  }
+  return check_launch("cam_kernel");
+}
+template int launch_cam<__half>(const __half*, __half*, const CamParams&, int, int, int, cudaStream_t);
+template int launch_cam<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, const CamParams&, int, int, int, cudaStream_t);
+
+// --------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void tensor_to_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = to_f32<T>(in[i]);
+}
+template <typename T>
+int launch_tensor_to_f32(const T* in, float* out, int64_t n, cudaStream_t s) {
+  if (n == 0) return PCLS_OK;
+  int64_t blocks = ceil_div(n, 256);
+  if (blocks > 65535) blocks = 65535;
+  tensor_to_f32_kernel<T><<<(int)blocks, 256, 0, s>>>(in, out, n);
+  return check_launch("tensor_to_f32_kernel");
+}
+template int launch_tensor_to_f32<__half>(const __half*, float*, int64_t, cudaStream_t);
+template int launch_tensor_to_f32<__nv_bfloat16>(const __nv_bfloat16*, float*, int64_t, cudaStream_t);
+
+}  // namespace pcls

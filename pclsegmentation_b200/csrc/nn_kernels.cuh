@@ -1,0 +1,83 @@
+// Launchers of the network kernels (internal to libpclseg).
+#pragma once
+#include "common.cuh"
+
+namespace pcls {
+
+// Geometry of one convolution-like op as "taps": output pixel (h, wo) reads, for tap t, the input pixel
+// (h + dh[t], wo * w_mul + dw[t]) when parity[t] < 0 or parity[t] == (wo & 1); transposed convs use
+// w_shift: input column = (wo + dw[t]) >> 1.
+enum ConvMode { MODE_1x1 = 0, MODE_3x3_S1 = 1, MODE_3x3_S2 = 2, MODE_DECONV = 3 };
+
+struct ConvParams {
+  int mode;
+  int H, Win, Wout;
+  int cin;            // logical input channels actually contracted (weights are zero beyond)
+  int cin_pad;        // packed weight inner dim (multiple of 16)
+  int in_channels;    // channel count (pixel stride) of the input tensor
+  int cout;           // logical output channels
+  int cout_pad;       // packed weight rows (multiple of 16)
+  int out_channels;   // pixel stride of the output tensor
+  int out_coff;       // channel offset of the write (tf.concat)
+  int pad_left;       // MODE_3x3_S2: TF SAME left padding (0 for even Win)
+  int act;
+  int ntaps;          // 1, 9, 9, 4
+  const void* in;     // T [B,H,Win,in_channels]
+  void* out;          // T [B,H,Wout,out_channels]  or float [B,H,Wout,out_channels] when out_f32
+  int out_f32;
+  const void* res0;   // T, same geometry as out (pixel stride res0_channels), read at out_coff
+  const void* res1;
+  int res0_channels, res1_channels;
+  const void* w;      // T packed [ntaps][cout_pad][cin_pad]
+  const float* bias;  // [cout_pad]
+};
+
+template <typename T> int launch_conv_direct(const ConvParams& p, int B, cudaStream_t s);
+template <typename T> int launch_net_input(const float* lidar, int channels, const uint8_t* mask_in, bool raw,
+                                           const double* mean5, const double* std5, int64_t n_pixels, T* out8,
+                                           uint8_t* mask_out, cudaStream_t s);
+template <typename T> int launch_maxpool3x3_s2(const T* in, T* out, int B, int H, int Win, int Wout, int C,
+                                               int pad_left, cudaStream_t s);
+
+struct CamParams {
+  int C, R;            // channels, reduced channels (C / 16)
+  const float* w1;     // [C][R]   folded squeeze weights
+  const float* b1;     // [R]
+  const float* w2;     // [R][C]   folded excitation weights
+  const float* b2;     // [C]
+};
+template <typename T> int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, cudaStream_t s);
+template <typename T> int launch_tensor_to_f32(const T* in, float* out, int64_t n, cudaStream_t s);
+
+int launch_head(const float* logits, const uint8_t* mask, int64_t n_pixels, int nc, int none_index, float* probs,
+                int32_t* preds, cudaStream_t s);
+
+// 16-bit <-> float helpers
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == PCLS_ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == PCLS_ACT_LEAKY) return v > 0.0f ? v : 0.1f * v;
+  return v;
+}
+
+// unpack / pack 8 x 16-bit values held in an int4
+template <typename T> __device__ __forceinline__ void unpack8(const int4& q, float (&f)[8]) {
+  const T* h = reinterpret_cast<const T*>(&q);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = to_f32<T>(h[i]);
+}
+template <typename T> __device__ __forceinline__ int4 pack8(const float (&f)[8]) {
+  int4 q;
+  T* h = reinterpret_cast<T*>(&q);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) h[i] = from_f32<T>(f[i]);
+  return q;
+}
+
+}  // namespace pcls

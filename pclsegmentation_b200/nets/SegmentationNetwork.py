@@ -1,0 +1,209 @@
+"""``PCLSegmentationNetwork`` - base class of the segmentation networks.
+
+Mirrors pcl_segmentation/nets/SegmentationNetwork.py: the constructor fields (:31-53), the ``call`` contract
+``model([lidar_input, lidar_mask]) -> (probabilities, predictions)`` (:55-69), ``predict_step`` (:133-136), the
+``miou_tracker`` and ``get_config`` (:144-151).  The forward itself - the traced layer graph plus ``segmentation_head``
+(softmax -> argmax -> depth-zero mask, :58-69) - runs in libpclseg (pcls_net_forward).  Training members
+(``train_step``, losses, optimizer) are out of scope of this inference path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..device import DeviceTensor, ptr, require_cuda, stream_handle, to_device, wrap
+from ..metrics import MeanIoU
+from .layers import Graph
+
+
+class PCLSegmentationNetwork:
+  """Base Class for segmentation networks (inference path)."""
+
+  def __init__(self, mc):
+    self.mc = mc
+    self.NUM_CLASS = mc.NUM_CLASS
+    self.BATCH_SIZE = mc.BATCH_SIZE
+    self.ZENITH_LEVEL = mc.ZENITH_LEVEL
+    self.AZIMUTH_LEVEL = mc.AZIMUTH_LEVEL
+    self.NUM_FEATURES = mc.NUM_FEATURES
+    self.CLASSES = mc.CLASSES
+    self.CLS_COLOR_MAP = mc.CLS_COLOR_MAP
+    assert self.NUM_FEATURES == 6, "the path implements the reference's 6-channel input (5 lidar channels + mask)"
+
+    self.miou_tracker = MeanIoU(num_classes=self.NUM_CLASS, name="MeanIoU")
+
+    self.precision = _lib.PCLS_F16
+    self.net_options = {}
+    self._graph = Graph(self.ZENITH_LEVEL, self.AZIMUTH_LEVEL)
+    self._logits_sym = None
+    self._net = None
+    self._net_batch = 0
+    self._pinned = {}
+
+  # ---- the subclass provides call(); tracing it builds the op program and creates the variables ----
+  def call(self, inputs, training=False, mask=None):
+    raise NotImplementedError("Method should be called in child class!")
+
+  def _trace(self):
+    self._logits_sym = self.call([self._graph.input, None])
+
+  def segmentation_head(self, logits, lidar_mask):
+    """Symbolic marker: the head (softmax, argmax, mask fill with CLASSES.index("None")) is executed by
+    pcls_net_forward on the tensor returned here."""
+    return logits
+
+  # ---- variables (Keras attribute paths) -----------------------------------------------------------
+  @property
+  def variables(self):
+    return self._graph.variables
+
+  def get_weights_dict(self):
+    return {k: v.copy() for k, v in self._graph.variables.items()}
+
+  def set_weights_dict(self, weights, strict=True):
+    """weights: {keras attribute path: array}; also accepts TF checkpoint style keys ending in
+    '/.ATTRIBUTES/VARIABLE_VALUE'."""
+    seen = set()
+    for k, v in weights.items():
+      k = k.replace("/.ATTRIBUTES/VARIABLE_VALUE", "")
+      if k not in self._graph.variables:
+        if strict and not k.startswith(("miou_tracker", "loss_tracker", "optimizer")):
+          raise KeyError("unknown variable %r" % k)
+        continue
+      v = np.asarray(v, dtype=np.float32)
+      if v.shape != self._graph.variables[k].shape:
+        raise ValueError("variable %r has shape %s, expected %s" % (k, v.shape, self._graph.variables[k].shape))
+      self._graph.variables[k] = v.copy()
+      seen.add(k)
+    if strict and len(seen) != len(self._graph.variables):
+      raise KeyError("missing variables: %s" % sorted(set(self._graph.variables) - seen)[:5])
+    self._release()
+
+  def save_weights_npz(self, path):
+    np.savez(path, **self._graph.variables)
+
+  def load_weights_npz(self, path):
+    with np.load(path) as f:
+      self.set_weights_dict({k: f[k] for k in f.files})
+
+  def randomize_batch_norm(self, seed=0):
+    """Random BN statistics / affine (mu ~ N(0,0.1), var ~ U(0.5,1.5), gamma ~ U(0.8,1.2), beta ~ N(0,0.1)) so that
+    the BN folding is exercised; random biases ~ N(0, 0.05) likewise."""
+    rng = np.random.default_rng(seed)
+    for k in sorted(self._graph.variables):
+      shape = self._graph.variables[k].shape
+      if k.endswith("/moving_mean") or k.endswith("/beta"):
+        self._graph.variables[k] = rng.normal(0, 0.1, shape).astype(np.float32)
+      elif k.endswith("/moving_variance"):
+        self._graph.variables[k] = rng.uniform(0.5, 1.5, shape).astype(np.float32)
+      elif k.endswith("/gamma"):
+        self._graph.variables[k] = rng.uniform(0.8, 1.2, shape).astype(np.float32)
+      elif k.endswith("/bias"):
+        self._graph.variables[k] = rng.normal(0, 0.05, shape).astype(np.float32)
+    self._release()
+
+  # ---- device execution ------------------------------------------------------------------------------
+  def _release(self):
+    if self._net is not None:
+      _lib.load().pcls_net_destroy(self._net)
+      self._net, self._net_batch = None, 0
+
+  def __del__(self):
+    try:
+      self._release()
+    except Exception:
+      pass
+
+  def set_option(self, name, value):
+    """Execution knobs of the C library ('conv_impl', 'use_graph', 'micro_batch'); rebuilds the device net."""
+    self.net_options[name] = int(value)
+    self._release()
+
+  def _ensure_net(self, batch):
+    if self._net is None or batch > self._net_batch:
+      self._release()
+      require_cuda()
+      cap = max(batch, 1)
+      self._net = self._graph.build_net(self._logits_sym, self.NUM_CLASS, self.CLASSES.index("None"), self.precision,
+                                        cap, self.net_options)
+      self._net_batch = cap
+    return self._net
+
+  def forward_device(self, lidar, mask=None, mean=None, std=None, want_probabilities=True, want_logits=False,
+                     out=None):
+    """Runs pcls_net_forward on device tensors.  lidar: float32 CUDA tensor [B,H,W,6] (normalised, mask in channel 5)
+    or, with mean/std, RAW [B,H,W,5|6] (input stage fused).  mask: uint8/bool CUDA tensor [B,H,W] or None.
+    Returns dict(predictions, probabilities?, logits?) of CUDA tensors."""
+    lib = _lib.load()
+    B, H, W, C = lidar.shape
+    if (H, W) != (self.ZENITH_LEVEL, self.AZIMUTH_LEVEL):
+      raise ValueError("input is %dx%d but the model was built for %dx%d" % (H, W, self.ZENITH_LEVEL, self.AZIMUTH_LEVEL))
+    net = self._ensure_net(B)
+    dev = lidar.device
+    out = out or {}
+    preds = out.get("predictions")
+    if preds is None:
+      preds = torch.empty((B, H, W), dtype=torch.int32, device=dev)
+    probs = logits = None
+    if want_probabilities:
+      probs = out.get("probabilities")
+      if probs is None:
+        probs = torch.empty((B, H, W, self.NUM_CLASS), dtype=torch.float32, device=dev)
+    if want_logits:
+      logits = out.get("logits")
+      if logits is None:
+        logits = torch.empty((B, H, W, self.NUM_CLASS), dtype=torch.float32, device=dev)
+    mean_p = std_p = None
+    if mean is not None:
+      mean_p = (ctypes.c_double * 5)(*[float(v) for v in np.asarray(mean).reshape(-1)[:5]])
+      std_p = (ctypes.c_double * 5)(*[float(v) for v in np.asarray(std).reshape(-1)[:5]])
+    if mask is not None and mask.dtype == torch.bool:
+      mask = mask.view(torch.uint8)
+    _lib.check(lib.pcls_net_forward(net, ptr(lidar), C, ptr(mask), mean_p, std_p, B, ptr(logits), ptr(probs),
+                                    ptr(preds), stream_handle()), "pcls_net_forward")
+    res = {"predictions": preds}
+    if probs is not None:
+      res["probabilities"] = probs
+    if logits is not None:
+      res["logits"] = logits
+    return res
+
+  def __call__(self, inputs, training=False, mask=None):
+    """``probabilities, predictions = model([lidar, mask])`` (inference.py:75, eval.py:47).
+    lidar [B,H,W,6] (numpy or torch, any float dtype), mask [B,H,W] bool.  Returns CUDA tensors whose ``.numpy()``
+    copies to the host."""
+    if training:
+      raise NotImplementedError("training is outside the scope of this inference path")
+    lidar_input, lidar_mask = inputs[0], inputs[1]
+    lidar = to_device(lidar_input, torch.float32, self._pinned, "lidar")
+    m = None
+    if lidar_mask is not None:
+      m = to_device(lidar_mask, torch.uint8 if not (torch.is_tensor(lidar_mask) and lidar_mask.dtype == torch.bool)
+                    else torch.bool, self._pinned, "mask")
+      m = m.reshape(lidar.shape[0], lidar.shape[1], lidar.shape[2])  # tf.squeeze(lidar_mask) semantics
+    res = self.forward_device(lidar, m)
+    return wrap(res["probabilities"]), wrap(res["predictions"])
+
+  def predict_step(self, data):
+    (lidar_input, lidar_mask), _, _ = data
+    return self([lidar_input, lidar_mask], training=False)
+
+  def test_step(self, data):
+    """Forward + weighted MeanIoU update (nets/SegmentationNetwork.py:118-131); the loss is training-side and not
+    computed here."""
+    (lidar_input, lidar_mask), label, weight = data
+    probabilities, predictions = self([lidar_input, lidar_mask], training=False)
+    self.miou_tracker.update_state(label, predictions)
+    return {'miou': self.miou_tracker.result()}
+
+  @property
+  def metrics(self):
+    return [self.miou_tracker]
+
+  def get_config(self):
+    return {"mc": self.mc}
+
+  @classmethod
+  def from_config(cls, config):
+    return cls(**config)
