@@ -218,6 +218,19 @@ int pcls_net_forward(pcls_net* net, const float* lidar, int channels, const uint
  * `out` ([B,H,width,channels] f32, device). */
 int pcls_net_read_tensor(pcls_net* net, int tensor, int B, float* out, pcls_stream stream);
 
+/* Per-op measurement for the roofline tables (bench.py): runs ONE forward like pcls_net_forward but
+ * brackets every op with CUDA events on `stream` and returns the device time of each in h_ms (host, length
+ * pcls_net_num_ops()).  Op 0 is the input kernel, the last op is the head.  Synchronises the stream. */
+int pcls_net_num_ops(const pcls_net* net);
+int pcls_net_profile_ops(pcls_net* net, const float* lidar, int channels, const uint8_t* mask,
+                         const double* h_mean5, const double* h_std5, int B, float* logits, float* probs,
+                         int32_t* preds, float* h_ms, pcls_stream stream);
+/* Static description of op `i` for a batch of one frame: a short name (h_name, >= 64 bytes), which kernel
+ * family runs it (0 = CUDA-core elementwise/direct, 1 = tcgen05 implicit GEMM), its algorithmic FLOPs and
+ * its algorithmic bytes (external inputs + outputs at the storage width + weights), per frame. */
+int pcls_net_op_info(const pcls_net* net, int i, char* h_name, int* family, int64_t* flops_per_frame,
+                     int64_t* bytes_per_frame);
+
 /* Introspection used by bench.py: number of kernel launches one forward enqueues, and workspace bytes. */
 int pcls_net_launches_per_forward(const pcls_net* net);
 int64_t pcls_net_workspace_bytes(const pcls_net* net);

@@ -56,6 +56,10 @@ SIGNATURES = {
   "pcls_net_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, POINTER(c_double), POINTER(c_double), c_int,
                                c_void_p, c_void_p, c_void_p, c_void_p]),
   "pcls_net_read_tensor": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+  "pcls_net_num_ops": (c_int, [c_void_p]),
+  "pcls_net_profile_ops": (c_int, [c_void_p, c_void_p, c_int, c_void_p, POINTER(c_double), POINTER(c_double), c_int,
+                                   c_void_p, c_void_p, c_void_p, POINTER(c_float), c_void_p]),
+  "pcls_net_op_info": (c_int, [c_void_p, c_int, c_char_p, POINTER(c_int), POINTER(c_int64), POINTER(c_int64)]),
   "pcls_net_launches_per_forward": (c_int, [c_void_p]),
   "pcls_net_workspace_bytes": (c_int64, [c_void_p]),
   "pcls_net_set_option": (c_int, [c_void_p, c_char_p, c_int]),

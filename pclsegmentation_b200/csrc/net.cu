@@ -312,13 +312,17 @@ void* Net::tensor_ptr(int t, int frames) const {
 
 template <typename T>
 int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool raw, const double* mean5,
-                  const double* std5, int nb, float* logits, float* probs, int32_t* preds, cudaStream_t s) {
+                  const double* std5, int nb, float* logits, float* probs, int32_t* preds, cudaStream_t s,
+                  cudaEvent_t* ev) {
   const int64_t n_pixels = (int64_t)nb * H * W;
   uint8_t* mask_buf = (uint8_t*)arena + mask_offset * (size_t)frames_per_pass;
+  int evi = 0;
+  if (ev) cudaEventRecord(ev[evi++], s);
   int rc = launch_net_input<T>(lidar, channels, mask, raw, mean5, std5, n_pixels, (T*)tensor_ptr(0, nb), mask_buf, s);
   if (rc) return rc;
   float* logits_buf = logits ? logits : (float*)tensor_ptr(logits_tensor, nb);
   for (const OpRef& op : ops) {
+    if (ev) cudaEventRecord(ev[evi++], s);
     if (op.type == OP_CONV) {
       ConvLayer& L = convs[op.index];
       ConvParams p = L.p;
@@ -338,18 +342,15 @@ int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool ra
     }
     if (rc) return rc;
   }
-  return launch_head(logits_buf, mask_buf, n_pixels, num_classes, none_index, probs, preds, s);
+  if (ev) cudaEventRecord(ev[evi++], s);
+  rc = launch_head(logits_buf, mask_buf, n_pixels, num_classes, none_index, probs, preds, s);
+  if (ev) cudaEventRecord(ev[evi++], s);
+  return rc;
 }
 
-int Net::forward(const float* lidar, int channels, const uint8_t* mask, const double* mean5, const double* std5, int B,
-                 float* logits, float* probs, int32_t* preds, cudaStream_t s) {
-  PCLS_REQUIRE(finalized, "pcls_net_forward: call pcls_net_finalize first");
-  PCLS_REQUIRE(B >= 0 && B <= max_batch, "pcls_net_forward: batch %d exceeds max_batch %d", B, max_batch);
-  const bool raw = mean5 != nullptr;
-  PCLS_REQUIRE(raw ? (channels == 5 || channels == 6) : channels == 6,
-               "pcls_net_forward: channels must be 6 (normalised input) or 5/6 with mean/std (raw input), got %d", channels);
-  PCLS_REQUIRE(!raw || std5 != nullptr, "pcls_net_forward: std is NULL");
-  PCLS_REQUIRE(B == 0 || (lidar != nullptr && preds != nullptr), "pcls_net_forward: lidar/preds must not be NULL");
+int Net::run_all(const float* lidar, int channels, const uint8_t* mask, bool raw, const double* mean5,
+                 const double* std5, int B, float* logits, float* probs, int32_t* preds, cudaStream_t s,
+                 cudaEvent_t* ev) {
   const size_t px = (size_t)H * W;
   for (int b0 = 0; b0 < B; b0 += frames_per_pass) {
     const int nb = std::min(frames_per_pass, B - b0);
@@ -358,11 +359,139 @@ int Net::forward(const float* lidar, int channels, const uint8_t* mask, const do
     float* lg = logits ? logits + (size_t)b0 * px * num_classes : nullptr;
     float* pr = probs ? probs + (size_t)b0 * px * num_classes : nullptr;
     int32_t* pd = preds + (size_t)b0 * px;
-    int rc = (precision == PCLS_F16) ? run_pass<__half>(l, channels, m, raw, mean5, std5, nb, lg, pr, pd, s)
-                                     : run_pass<__nv_bfloat16>(l, channels, m, raw, mean5, std5, nb, lg, pr, pd, s);
+    int rc = (precision == PCLS_F16) ? run_pass<__half>(l, channels, m, raw, mean5, std5, nb, lg, pr, pd, s, ev)
+                                     : run_pass<__nv_bfloat16>(l, channels, m, raw, mean5, std5, nb, lg, pr, pd, s, ev);
     if (rc) return rc;
   }
+  return PCLS_OK;
+}
+
+static int check_forward_args(const Net& n, const float* lidar, int channels, const double* mean5, const double* std5,
+                              int B, const int32_t* preds) {
+  PCLS_REQUIRE(n.finalized, "pcls_net_forward: call pcls_net_finalize first");
+  PCLS_REQUIRE(B >= 0 && B <= n.max_batch, "pcls_net_forward: batch %d exceeds max_batch %d", B, n.max_batch);
+  const bool raw = mean5 != nullptr;
+  PCLS_REQUIRE(raw ? (channels == 5 || channels == 6) : channels == 6,
+               "pcls_net_forward: channels must be 6 (normalised input) or 5/6 with mean/std (raw input), got %d", channels);
+  PCLS_REQUIRE(!raw || std5 != nullptr, "pcls_net_forward: std is NULL");
+  PCLS_REQUIRE(B == 0 || (lidar != nullptr && preds != nullptr), "pcls_net_forward: lidar/preds must not be NULL");
+  return PCLS_OK;
+}
+
+int Net::forward(const float* lidar, int channels, const uint8_t* mask, const double* mean5, const double* std5, int B,
+                 float* logits, float* probs, int32_t* preds, cudaStream_t s) {
+  int rc = check_forward_args(*this, lidar, channels, mean5, std5, B, preds);
+  if (rc) return rc;
   last_B = B;
+  if (B == 0) return PCLS_OK;
+  const bool raw = mean5 != nullptr;
+  if (!use_graph) return run_all(lidar, channels, mask, raw, mean5, std5, B, logits, probs, preds, s, nullptr);
+
+  // CUDA-graph replay: the whole forward (all passes) is captured once per distinct argument set on an internal
+  // stream and replayed on the caller's stream; ~60-70 launches collapse into one graph launch.
+  GraphKey key;
+  memset(&key, 0, sizeof(key));
+  key.lidar = lidar; key.mask = mask; key.logits = logits; key.probs = probs; key.preds = preds;
+  key.channels = channels; key.B = B; key.raw = raw ? 1 : 0; key.conv_impl = conv_impl;
+  for (int c = 0; c < 5; ++c) { key.norm[c] = raw ? mean5[c] : 0.0; key.norm[5 + c] = raw ? std5[c] : 0.0; }
+  for (auto& g : graphs) {
+    if (!memcmp(&g.key, &key, sizeof(key))) {
+      g.stamp = ++graph_clock;
+      PCLS_CHECK_CUDA(cudaGraphLaunch(g.exec, s));
+      return PCLS_OK;
+    }
+  }
+  if (!cap_stream) PCLS_CHECK_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+  PCLS_CHECK_CUDA(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeRelaxed));
+  rc = run_all(lidar, channels, mask, raw, mean5, std5, B, logits, probs, preds, cap_stream, nullptr);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(cap_stream, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (e != cudaSuccess) { set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e)); return PCLS_ERR_CUDA; }
+  CachedGraph cg;
+  cg.key = key;
+  e = cudaGraphInstantiate(&cg.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return PCLS_ERR_CUDA; }
+  cg.stamp = ++graph_clock;
+  if (graphs.size() >= 16) {  // evict the least recently used
+    size_t victim = 0;
+    for (size_t i = 1; i < graphs.size(); ++i) if (graphs[i].stamp < graphs[victim].stamp) victim = i;
+    cudaGraphExecDestroy(graphs[victim].exec);
+    graphs.erase(graphs.begin() + victim);
+  }
+  graphs.push_back(cg);
+  PCLS_CHECK_CUDA(cudaGraphLaunch(cg.exec, s));
+  return PCLS_OK;
+}
+
+void Net::drop_graphs() {
+  for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+  graphs.clear();
+}
+
+int Net::profile_ops(const float* lidar, int channels, const uint8_t* mask, const double* mean5, const double* std5,
+                     int B, float* logits, float* probs, int32_t* preds, float* h_ms, cudaStream_t s) {
+  int rc = check_forward_args(*this, lidar, channels, mean5, std5, B, preds);
+  if (rc) return rc;
+  PCLS_REQUIRE(B >= 1 && B <= frames_per_pass, "pcls_net_profile_ops: B must fit one pass (<= %d)", frames_per_pass);
+  PCLS_REQUIRE(h_ms != nullptr, "pcls_net_profile_ops: h_ms is NULL");
+  const int n = (int)ops.size() + 2;
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) PCLS_CHECK_CUDA(cudaEventCreate(&e));
+  rc = run_all(lidar, channels, mask, mean5 != nullptr, mean5, std5, B, logits, probs, preds, s, ev.data());
+  if (rc == PCLS_OK) {
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { set_error("profile: %s", cudaGetErrorString(e)); rc = PCLS_ERR_CUDA; }
+  }
+  if (rc == PCLS_OK)
+    for (int i = 0; i < n; ++i) cudaEventElapsedTime(&h_ms[i], ev[i], ev[i + 1]);
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
+}
+
+int Net::op_info(int i, char* name, int* family, int64_t* flops, int64_t* bytes) const {
+  const int n = (int)ops.size() + 2;
+  PCLS_REQUIRE(i >= 0 && i < n, "pcls_net_op_info: op index %d out of range", i);
+  const int64_t HW = (int64_t)H * W;
+  int fam = 0;
+  int64_t fl = 0, by = 0;
+  char buf[64];
+  if (i == 0) {
+    snprintf(buf, sizeof(buf), "input_stage");
+    by = HW * (5 * 4 + 16 + 1);
+  } else if (i == n - 1) {
+    snprintf(buf, sizeof(buf), "head_softmax_argmax");
+    by = HW * ((int64_t)num_classes * 4 * 2 + 4 + 1);
+  } else {
+    const OpRef& op = ops[i - 1];
+    if (op.type == OP_CONV) {
+      const ConvLayer& L = convs[op.index];
+      const ConvParams& p = L.p;
+      const char* mode = p.mode == MODE_1x1 ? "conv1x1" : p.mode == MODE_3x3_S1 ? "conv3x3" : p.mode == MODE_3x3_S2 ? "conv3x3s2" : "deconv1x4s2";
+      snprintf(buf, sizeof(buf), "%s_%dx%d_w%d", mode, p.cin, p.cout, p.Wout);
+      const int64_t taps = p.mode == MODE_DECONV ? 2 : p.ntaps;  // 2 of the 4 taps hit each output column
+      fl = 2 * (int64_t)H * p.Wout * p.cin * p.cout * taps;
+      by = (int64_t)H * p.Win * p.cin * 2 + (int64_t)H * p.Wout * p.cout * (p.out_f32 ? 4 : 2) +
+           (int64_t)p.ntaps * p.cin * p.cout * 2;
+      if (L.res0 >= 0) by += (int64_t)H * p.Wout * p.cout * 2;
+      if (L.res1 >= 0) by += (int64_t)H * p.Wout * p.cout * 2;
+      fam = (conv_impl == 0 && L.tc_ok) ? 1 : 0;
+    } else if (op.type == OP_POOL) {
+      const PoolLayer& L = pools[op.index];
+      snprintf(buf, sizeof(buf), "maxpool3x3s2_c%d_w%d", tensors[L.in].channels, tensors[L.out].width);
+      by = (int64_t)H * (tensors[L.in].width + tensors[L.out].width) * tensors[L.in].channels * 2;
+    } else {
+      const CamLayer& L = cams[op.index];
+      snprintf(buf, sizeof(buf), "cam_c%d_w%d", L.C, tensors[L.in].width);
+      fl = 2 * (int64_t)H * tensors[L.in].width * L.C * L.R * 2;
+      by = (int64_t)H * tensors[L.in].width * L.C * 2 * 2;
+    }
+  }
+  if (name) { strncpy(name, buf, 63); name[63] = 0; }
+  if (family) *family = fam;
+  if (flops) *flops = fl;
+  if (bytes) *bytes = by;
   return PCLS_OK;
 }
 
@@ -377,6 +506,8 @@ int Net::read_tensor(int t, int B, float* out, cudaStream_t s) {
 }
 
 Net::~Net() {
+  drop_graphs();
+  if (cap_stream) cudaStreamDestroy(cap_stream);
   if (arena) cudaFree(arena);
   if (weights) cudaFree(weights);
   tc_release();
@@ -445,6 +576,25 @@ extern "C" int pcls_net_read_tensor(pcls_net* net, int tensor, int B, float* out
   return reinterpret_cast<Net*>(net)->read_tensor(tensor, B, out, (cudaStream_t)stream);
 }
 
+extern "C" int pcls_net_num_ops(const pcls_net* net) {
+  const Net* n = reinterpret_cast<const Net*>(net);
+  return n ? (int)n->ops.size() + 2 : 0;
+}
+
+extern "C" int pcls_net_profile_ops(pcls_net* net, const float* lidar, int channels, const uint8_t* mask,
+                                    const double* h_mean5, const double* h_std5, int B, float* logits, float* probs,
+                                    int32_t* preds, float* h_ms, pcls_stream stream) {
+  PCLS_REQUIRE(net != nullptr, "pcls_net_profile_ops: NULL net");
+  return reinterpret_cast<Net*>(net)->profile_ops(lidar, channels, mask, h_mean5, h_std5, B, logits, probs, preds, h_ms,
+                                                  (cudaStream_t)stream);
+}
+
+extern "C" int pcls_net_op_info(const pcls_net* net, int i, char* h_name, int* family, int64_t* flops_per_frame,
+                                int64_t* bytes_per_frame) {
+  PCLS_REQUIRE(net != nullptr, "pcls_net_op_info: NULL net");
+  return reinterpret_cast<const Net*>(net)->op_info(i, h_name, family, flops_per_frame, bytes_per_frame);
+}
+
 extern "C" int pcls_net_launches_per_forward(const pcls_net* net) {
   const Net* n = reinterpret_cast<const Net*>(net);
   if (!n) return 0;
@@ -460,7 +610,7 @@ extern "C" int pcls_net_set_option(pcls_net* net, const char* name, int value) {
   Net* n = reinterpret_cast<Net*>(net);
   PCLS_REQUIRE(n != nullptr && name != nullptr, "pcls_net_set_option: NULL argument");
   if (!strcmp(name, "conv_impl")) { PCLS_REQUIRE(value == 0 || value == 1, "conv_impl must be 0 or 1"); n->conv_impl = value; return PCLS_OK; }
-  if (!strcmp(name, "use_graph")) { n->use_graph = value != 0; return PCLS_OK; }
+  if (!strcmp(name, "use_graph")) { n->use_graph = value != 0; if (!n->use_graph) n->drop_graphs(); return PCLS_OK; }
   if (!strcmp(name, "micro_batch")) {
     PCLS_REQUIRE(!n->finalized, "micro_batch must be set before pcls_net_finalize");
     PCLS_REQUIRE(value >= 0, "micro_batch must be >= 0");

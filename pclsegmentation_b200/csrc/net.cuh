@@ -35,6 +35,13 @@ struct CamLayer {
 enum OpType { OP_CONV = 0, OP_POOL = 1, OP_CAM = 2 };
 struct OpRef { int type, index; };
 
+struct GraphKey {
+  const void *lidar, *mask, *logits, *probs, *preds;
+  int channels, B, raw, conv_impl;
+  double norm[10];
+};
+struct CachedGraph { GraphKey key; cudaGraphExec_t exec = nullptr; uint64_t stamp = 0; };
+
 struct Net {
   int H = 0, W = 0, precision = PCLS_F16, max_batch = 0;
   std::vector<TensorInfo> tensors;
@@ -56,6 +63,9 @@ struct Net {
   void* weights = nullptr;
   size_t weight_bytes = 0;
   int last_B = 0;
+  std::vector<CachedGraph> graphs;
+  uint64_t graph_clock = 0;
+  cudaStream_t cap_stream = nullptr;
 
   ~Net();
   int add_tensor(int width, int channels, bool logits);
@@ -68,7 +78,13 @@ struct Net {
   void* tensor_ptr(int t, int frames) const;
   template <typename T>
   int run_pass(const float* lidar, int channels, const uint8_t* mask, bool raw, const double* mean5, const double* std5,
-               int nb, float* logits, float* probs, int32_t* preds, cudaStream_t s);
+               int nb, float* logits, float* probs, int32_t* preds, cudaStream_t s, cudaEvent_t* ev);
+  int run_all(const float* lidar, int channels, const uint8_t* mask, bool raw, const double* mean5, const double* std5,
+              int B, float* logits, float* probs, int32_t* preds, cudaStream_t s, cudaEvent_t* ev);
+  void drop_graphs();
+  int profile_ops(const float* lidar, int channels, const uint8_t* mask, const double* mean5, const double* std5, int B,
+                  float* logits, float* probs, int32_t* preds, float* h_ms, cudaStream_t s);
+  int op_info(int i, char* name, int* family, int64_t* flops, int64_t* bytes) const;
   int forward(const float* lidar, int channels, const uint8_t* mask, const double* mean5, const double* std5, int B,
               float* logits, float* probs, int32_t* preds, cudaStream_t s);
   int read_tensor(int t, int B, float* out, cudaStream_t s);

@@ -1,0 +1,100 @@
+"""Head, input stage and confusion matrix through the C ABI vs the oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import confusion as C
+from oracle import nn as O
+from pclsegmentation_b200 import _lib
+from tests.util import synth_range_images
+
+pytestmark = pytest.mark.gpu
+
+
+def _s():
+  return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize("n,nc,none", [(64 * 2048 * 2, 20, 0), (32 * 240 * 3 + 7, 11, 10), (5, 3, 1), (33, 32, 31)])
+def test_head_matches_oracle(n, nc, none):
+  lib = _lib.load()
+  rng = np.random.default_rng(n)
+  logits = (rng.normal(size=(n, nc)) * 4).astype(np.float32)
+  logits[::7] = np.round(logits[::7])            # exact ties -> lowest index must win
+  logits[1::11, :] = 3.0
+  mask = rng.random(n) < 0.7
+  lg, m = torch.from_numpy(logits).cuda(), torch.from_numpy(mask).cuda()
+  probs = torch.empty_like(lg)
+  preds = torch.empty(n, dtype=torch.int32, device="cuda")
+  _lib.check(lib.pcls_head(lg.data_ptr(), m.view(torch.uint8).data_ptr(), n, nc, none, probs.data_ptr(),
+                           preds.data_ptr(), _s()))
+  p_ref, pred_ref = O.segmentation_head(torch.from_numpy(logits), torch.from_numpy(mask), none)
+  assert np.allclose(probs.cpu().numpy(), p_ref.numpy(), rtol=0, atol=2e-7)
+  got = preds.cpu().numpy()
+  # argmax is taken over OUR rounded probabilities: it must equal the reference wherever the oracle's top-2
+  # probabilities are not within float rounding of each other, and always be a maximiser of our own probabilities
+  top2 = np.sort(p_ref.numpy(), axis=1)[:, -2:]
+  clear = (top2[:, 1] - top2[:, 0]) > 1e-6
+  assert np.array_equal(got[clear | ~mask], pred_ref.numpy()[clear | ~mask])
+  own = probs.cpu().numpy()
+  assert np.array_equal(got[mask], own.argmax(1)[mask])
+  assert (got == pred_ref.numpy()).mean() > 0.9999
+  # probs = NULL variant gives the same predictions
+  preds2 = torch.empty_like(preds)
+  _lib.check(lib.pcls_head(lg.data_ptr(), m.view(torch.uint8).data_ptr(), n, nc, none, None, preds2.data_ptr(), _s()))
+  assert torch.equal(preds, preds2)
+
+
+def test_input_stage_matches_oracle():
+  from pclsegmentation_b200.configs import SqueezeSegV2KittiConfig
+  lib = _lib.load()
+  mc = SqueezeSegV2KittiConfig()
+  rng = np.random.default_rng(1)
+  raw = synth_range_images(rng, 2, 64, 512)
+  n = 2 * 64 * 512
+  d = torch.from_numpy(raw).cuda()
+  lidar = torch.empty((n, 6), dtype=torch.float32, device="cuda")
+  mask = torch.empty(n, dtype=torch.uint8, device="cuda")
+  label = torch.empty(n, dtype=torch.int32, device="cuda")
+  mean = (ctypes.c_double * 5)(*mc.INPUT_MEAN.reshape(-1))
+  std = (ctypes.c_double * 5)(*mc.INPUT_STD.reshape(-1))
+  _lib.check(lib.pcls_input_stage(d.data_ptr(), 6, n, mean, std, 0, lidar.data_ptr(), mask.data_ptr(),
+                                  label.data_ptr(), _s()))
+  for b in range(2):
+    l_ref, m_ref, lab_ref = O.input_stage(raw[b], mc.INPUT_MEAN, mc.INPUT_STD, 0)
+    sl = slice(b * 64 * 512, (b + 1) * 64 * 512)
+    assert np.array_equal(lidar[sl].cpu().numpy().reshape(64, 512, 6), l_ref)     # bit-exact (float64 normalise)
+    assert np.array_equal(mask[sl].cpu().numpy().reshape(64, 512).astype(bool), m_ref)
+    assert np.array_equal(label[sl].cpu().numpy().reshape(64, 512), lab_ref)
+
+
+@pytest.mark.parametrize("n,nc", [(32 * 64 * 2048, 20), (3 * 32 * 240 + 3, 11), (1, 2), (0, 11)])
+def test_confusion_bit_exact(n, nc):
+  from pclsegmentation_b200.metrics import MeanIoU
+  from pclsegmentation_b200.utils.util import confusion_matrix_to_iou_recall_precision
+  rng = np.random.default_rng(n + nc)
+  p = np.full(nc, 0.5 / max(nc - 1, 1))
+  p[nc - 1] = 0.5                                 # heavily skewed, like the None class
+  p /= p.sum()
+  label = rng.choice(nc, n, p=p).astype(np.int32)
+  pred = np.where(rng.random(n) < 0.8, label, rng.integers(0, nc, n)).astype(np.int32)
+  m = MeanIoU(nc)
+  half = (n // 2) // 4 * 4
+  m.update_state(label[:half], pred[:half])       # accumulates across calls like update_state
+  m.update_state(label[half:], pred[half:])
+  ref = C.confusion_matrix(label, pred, nc)
+  assert np.array_equal(m.total_cm.cpu().numpy(), ref) and m.dropped == 0
+  assert abs(float(m.result()) - C.mean_iou(ref)) < 1e-6
+  got = confusion_matrix_to_iou_recall_precision(m.total_cm)
+  assert all(np.allclose(a, b) for a, b in zip(got, C.iou_recall_precision(ref)))
+  m.reset_states()
+  assert int(m.total_cm.sum()) == 0
+
+
+def test_confusion_out_of_range_pairs_are_dropped_and_counted():
+  from pclsegmentation_b200.metrics import MeanIoU
+  m = MeanIoU(4)
+  m.update_state(np.array([0, 1, 7, -1, 2], np.int32), np.array([0, 9, 1, 1, 2], np.int32))
+  assert int(m.total_cm.sum()) == 2 and m.dropped == 3

@@ -1,0 +1,234 @@
+"""Network forward through the C ABI vs the fp32 CPU oracle: every op flavour in isolation (odd widths, asymmetric
+SAME padding, concat offsets, residuals) and the three whole nets.
+
+Tolerances (BASELINE.json north_star): logits max-abs error <= 1e-2 against the fp32 oracle for the 16-bit path,
+argmax agreement >= 99.9 % of valid pixels."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nn as O
+from pclsegmentation_b200 import _lib
+from pclsegmentation_b200.nets import layers as L
+from tests.util import synth_range_images
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-2
+IMPLS = [0, 1]  # conv_impl: 0 = tcgen05 implicit GEMM where the shape allows, 1 = CUDA-core direct kernel
+
+
+def _f16(a):
+  return np.asarray(a, np.float32).astype(np.float16).astype(np.float32)
+
+
+class TinyNet:
+  """One-op graphs built with the same Graph the model builders use."""
+
+  def __init__(self, H, W):
+    self.g = L.Graph(H, W)
+    self.g.rng = np.random.default_rng(7)
+    # the net needs a [B,H,W,NC] logits tensor: a throw-away 1x1 conv from the input, emitted FIRST so that the
+    # tensor under test is the last thing written into the arena
+    self.logits = L.Conv2D("zz_logits", 2, 1)(self.g.input)
+
+  def run(self, out_sym, B, x6, conv_impl):
+    lib = _lib.load()
+    g = self.g
+    net = g.build_net(self.logits, 2, 0, _lib.PCLS_F16, B, {"conv_impl": conv_impl, "use_graph": 0})
+    try:
+      x = torch.from_numpy(x6).cuda()
+      preds = torch.empty(x6.shape[:3], dtype=torch.int32, device="cuda")
+      _lib.check(lib.pcls_net_forward(net, x.data_ptr(), 6, None, None, None, B, None, None, preds.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream), "forward")
+      out = torch.empty((B, g.H, out_sym.width, out_sym.channels), dtype=torch.float32, device="cuda")
+      _lib.check(lib.pcls_net_read_tensor(net, out_sym.tid, B, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+      torch.cuda.synchronize()
+      return out.cpu().numpy()
+    finally:
+      lib.pcls_net_destroy(net)
+
+
+def _rand_vars(g, rng):
+  for k, v in g.variables.items():
+    if k.endswith("/kernel"):
+      g.variables[k] = (rng.normal(size=v.shape) / np.sqrt(np.prod(v.shape[:-1]) / 2)).astype(np.float32)
+    elif k.endswith("moving_variance"):
+      g.variables[k] = rng.uniform(0.5, 1.5, v.shape).astype(np.float32)
+    elif k.endswith("gamma"):
+      g.variables[k] = rng.uniform(0.8, 1.2, v.shape).astype(np.float32)
+    else:
+      g.variables[k] = rng.normal(0, 0.2, v.shape).astype(np.float32)
+
+
+def _input(rng, B, H, W):
+  x = rng.normal(size=(B, H, W, 6)).astype(np.float32)
+  x[..., 5] = rng.random((B, H, W)) < 0.8
+  return _f16(x)
+
+
+def _nchw(x):
+  return torch.from_numpy(x).permute(0, 3, 1, 2).contiguous()
+
+
+def _nhwc(t):
+  return t.permute(0, 2, 3, 1).contiguous().numpy()
+
+
+def _tp(g):
+  return {k: torch.from_numpy(v) for k, v in g.variables.items()}
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("H,W,c1,c2", [(5, 48, 32, 48), (3, 27, 16, 64), (8, 256, 64, 128), (2, 130, 128, 32)])
+def test_conv_flavours_in_isolation(impl, H, W, c1, c2):
+  """3x3 s1 from the 6-channel input, 1x1, 3x3 s[1,2] (asymmetric SAME for even W / symmetric for odd), transposed
+  [1,4] s2, concat-by-offset and a residual add - each checked against the oracle at its own output."""
+  rng = np.random.default_rng(H * W + c1)
+  B = 2
+  t = TinyNet(H, W)
+  g = t.g
+  a = L.relu(L.BatchNormalization("b0")(L.Conv2D("c0", c1, 3)(g.input)))                      # 3x3 s1, Cin = 6
+  b = L.LeakyReLU(0.1)(L.BatchNormalization("b1")(L.Conv2D("c1", c2, 1, use_bias=False)(a)))  # 1x1
+  c = L.relu(L.Conv2D("c2", c1, 3, strides=[1, 2])(b))                                        # 3x3 s2, bias only
+  d = L.relu(L.Conv2DTranspose("c3", c1)(c))                                                  # deconv back to >= W
+  Wd = d.width
+  e1 = L.relu(L.BatchNormalization("b4")(L.Conv2D("c4", c2, 1)(d)))
+  e3 = L.relu(L.BatchNormalization("b5")(L.Conv2D("c5", c2, 3)(d)))
+  cat = L.concat([e1, e3])
+  _rand_vars(g, rng)
+  x = _input(rng, B, H, W)
+  p = _tp(g)
+  xa = F_relu(O.batch_norm(O._conv(_nchw(x), p, "c0"), p, "b0"))
+  xb = O.leaky(O.batch_norm(O._conv(xa, p, "c1"), p, "b1"))
+  xc = F_relu(O._conv(xb, p, "c2", (1, 2)))
+  xd = F_relu(O.conv2d_transpose_1x4_s2(xc, p["c3/kernel"], p["c3/bias"]))
+  xe = torch.cat([F_relu(O.batch_norm(O._conv(xd, p, "c4"), p, "b4")), F_relu(O.batch_norm(O._conv(xd, p, "c5"), p, "b5"))], 1)
+  assert Wd == xd.shape[3]
+  got = t.run(cat, B, x, impl)
+  ref = _nhwc(xe)
+  err = np.abs(got - ref).max()
+  assert got.shape == ref.shape and err < 3e-2 * max(1.0, np.abs(ref).max()), err
+
+
+def F_relu(x):
+  return torch.relu(x)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_residual_and_skip_adds(impl):
+  rng = np.random.default_rng(3)
+  B, H, W = 2, 4, 64
+  t = TinyNet(H, W)
+  g = t.g
+  a = L.LeakyReLU(0.1)(L.BatchNormalization("b0")(L.Conv2D("c0", 32, 3, use_bias=False)(g.input)))
+  s = L.LeakyReLU(0.1)(L.BatchNormalization("b1")(L.Conv2D("c1", 32, 1)(a)))
+  y = L.LeakyReLU(0.1)(L.BatchNormalization("b2")(L.Conv2D("c2", 32, 3, use_bias=False)(s)))
+  y += s          # block residual
+  y = y + a       # encoder skip
+  _rand_vars(g, rng)
+  x = _input(rng, B, H, W)
+  p = _tp(g)
+  xa = O.leaky(O.batch_norm(O._conv(_nchw(x), p, "c0"), p, "b0"))
+  xs = O.leaky(O.batch_norm(O._conv(xa, p, "c1"), p, "b1"))
+  xy = O.leaky(O.batch_norm(O._conv(xs, p, "c2"), p, "b2")) + xs + xa
+  got = t.run(y, B, x, impl)
+  assert np.abs(got - _nhwc(xy)).max() < 3e-2
+
+
+@pytest.mark.parametrize("C,W", [(64, 70), (128, 33)])
+def test_cam_and_pool(C, W):
+  rng = np.random.default_rng(C)
+  B, H = 2, 11
+  t = TinyNet(H, W)
+  g = t.g
+  a = L.relu(L.BatchNormalization("b0")(L.Conv2D("c0", C, 3)(g.input)))
+  cam = g.cam(a, "cam", C // 16)
+  pooled = L.max_pool2d(cam)
+  _rand_vars(g, rng)
+  x = _input(rng, B, H, W)
+  p = _tp(g)
+  xa = F_relu(O.batch_norm(O._conv(_nchw(x), p, "c0"), p, "b0"))
+  xcam = O.cam(xa, p, "cam")
+  xpool = O.max_pool_same(xcam, 3, (1, 2))
+  got = t.run(pooled, B, x, 1)
+  assert got.shape == _nhwc(xpool).shape and np.abs(got - _nhwc(xpool)).max() < 2e-2
+
+
+def _model(name, cfg, H=None, W=None, seed=1):
+  from pclsegmentation_b200.utils.args_loader import config_map, model_map
+  mc = config_map[cfg]()
+  if H:
+    mc.ZENITH_LEVEL, mc.AZIMUTH_LEVEL = H, W
+  model = model_map[name](mc)
+  model.randomize_batch_norm(seed)
+  return mc, model
+
+
+def _oracle(mc, model, name, lidar, mask):
+  arch = "squeezesegv2" if name == "squeezesegv2" else "darknet"
+  return O.forward(arch, model.variables, lidar, mask, mc.CLASSES.index("None"),
+                   num_layers=getattr(mc, "NUM_LAYERS", 53), output_stride=getattr(mc, "OUTPUT_STRIDE", 16))
+
+
+def _prep(mc, raw):
+  lidar, mask = [], []
+  for b in range(raw.shape[0]):
+    l, m, _ = O.input_stage(raw[b], mc.INPUT_MEAN, mc.INPUT_STD, mc.CLASSES.index("None"))
+    lidar.append(l)
+    mask.append(m)
+  return np.stack(lidar), np.stack(mask)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("name,cfg,H,W,B", [("squeezesegv2", "squeezesegv2", 32, 240, 3),
+                                            ("squeezesegv2", "squeezesegv2kitti", 64, 512, 2),
+                                            ("squeezesegv2", "squeezesegv2nuscenes", 32, 1024, 2),
+                                            ("darknet21", "darknet21", 32, 240, 2),
+                                            ("darknet53", "darknet53kitti", 64, 256, 1)])
+def test_whole_net_logits_and_labels(impl, name, cfg, H, W, B):
+  mc, model = _model(name, cfg, H, W)
+  model.set_option("conv_impl", impl)
+  rng = np.random.default_rng(1234)
+  raw = synth_range_images(rng, B, H, W, valid_rate=0.78, num_classes=mc.NUM_CLASS)
+  lidar, mask = _prep(mc, raw)
+  lg_ref, pr_ref, pd_ref = _oracle(mc, model, name, lidar, mask)
+  # (a) reference call contract: normalised [B,H,W,6] + bool mask, host arrays in, .numpy() out
+  probs, preds = model([lidar, mask])
+  assert tuple(probs.shape) == (B, H, W, mc.NUM_CLASS) and preds.dtype == torch.int32
+  res = model.forward_device(torch.from_numpy(lidar).cuda(), torch.from_numpy(mask).cuda(), want_logits=True)
+  lg = res["logits"].cpu().numpy()
+  scale = max(1.0, float(np.abs(lg_ref).max()) / 4.0)   # tolerance is stated for O(1) logits
+  err = np.abs(lg - lg_ref).max()
+  assert err <= LOGIT_TOL * scale, "max abs logit error %g (scale %g)" % (err, scale)
+  assert np.abs(probs.numpy() - pr_ref).max() < 2e-2
+  agree = (preds.numpy() == pd_ref)[mask].mean()
+  assert agree >= 0.999, agree
+  assert (preds.numpy()[~mask] == mc.CLASSES.index("None")).all()
+  # (b) raw input with the input stage fused into the first load gives the same predictions
+  res2 = model.forward_device(torch.from_numpy(raw).cuda(), None, mean=mc.INPUT_MEAN, std=mc.INPUT_STD,
+                              want_logits=True)
+  assert np.abs(res2["logits"].cpu().numpy() - lg).max() < 1e-3
+  assert (res2["predictions"].cpu().numpy() == preds.numpy()).mean() > 0.9995
+  # (c) predict_step contract
+  p2, y2 = model.predict_step(((lidar, mask), None, None))
+  assert np.array_equal(y2.numpy(), preds.numpy())
+
+
+def test_micro_batch_and_graph_replay_are_equivalent():
+  mc, model = _model("squeezesegv2", "squeezesegv2", 32, 240)
+  rng = np.random.default_rng(2)
+  raw = synth_range_images(rng, 5, 32, 240, num_classes=11)
+  lidar, mask = _prep(mc, raw)
+  model.set_option("use_graph", 0)
+  base = model.forward_device(torch.from_numpy(lidar).cuda(), torch.from_numpy(mask).cuda(), want_logits=True)
+  base = {k: v.clone() for k, v in base.items()}
+  for opts in ({"use_graph": 1}, {"micro_batch": 2, "use_graph": 1}, {"micro_batch": 2, "use_graph": 0}):
+    for k, v in opts.items():
+      model.set_option(k, v)
+    for _ in range(3):  # replays
+      out = model.forward_device(torch.from_numpy(lidar).cuda(), torch.from_numpy(mask).cuda(), want_logits=True)
+    assert torch.equal(out["predictions"], base["predictions"]) and torch.equal(out["logits"], base["logits"])

@@ -1,0 +1,139 @@
+"""Parity of the CUDA projection (through the C ABI) with the oracle and with the reference's own outputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import projection as P
+from tests.util import synth_scan
+
+pytestmark = pytest.mark.gpu
+
+
+def _projector(H, W, fu, fd, lut=None):
+  from pclsegmentation_b200.laserscan import SphericalProjector
+  return SphericalProjector(H, W, fu, fd, label_lut=lut)
+
+
+def _golden(golden_dir, name):
+  with np.load(os.path.join(golden_dir, "projection_%s.npz" % name)) as f:
+    return {k: f[k] for k in f.files}
+
+
+def _lut(golden_dir):
+  with np.load(os.path.join(golden_dir, "semantic_kitti_learning_map.npz")) as f:
+    return P.learning_map_lut(dict(zip(f["keys"].tolist(), f["values"].tolist())))
+
+
+@pytest.mark.parametrize("H,W,fu,fd", [(64, 2048, 3.0, -25.0), (64, 1024, 3.0, -25.0), (32, 1024, 12.0, -30.0),
+                                       (32, 240, 3.0, -25.0)])
+def test_batched_ragged_bit_exact_vs_cr_oracle(H, W, fu, fd):
+  rng = np.random.default_rng(H * W)
+  sizes = [30000, 0, 1, 12345, 20000]                      # ragged batch incl. an empty and a 1-point scan
+  scans = [synth_scan(rng, n, fu, fd, H) for n in sizes]
+  scans[4][100:200] = scans[4][0:100]                      # exact duplicates -> depth ties
+  labels = [rng.integers(0, 260, n).astype(np.uint32) | (rng.integers(0, 99, n).astype(np.uint32) << 16) for n in sizes]
+  lut = np.arange(300, dtype=np.int32)[::-1].copy()
+  out = _projector(H, W, fu, fd, lut).project_scans(scans, labels=labels, empty_fill=0.0, want_sem=True,
+                                                    want_point_outputs=True)
+  image, idx, sem = out["image"].cpu().numpy(), out["proj_idx"].cpu().numpy(), out["proj_sem_label"].cpu().numpy()
+  px, py, ur = out["proj_x"].cpu().numpy(), out["proj_y"].cpu().numpy(), out["unproj_range"].cpu().numpy()
+  off = np.concatenate([[0], np.cumsum(sizes)])
+  for b, s in enumerate(scans):
+    o = P.range_projection(s[:, :3], s[:, 3], H, W, fu, fd, trig="cr")
+    sl = slice(off[b], off[b + 1])
+    assert np.array_equal(px[sl], o["proj_x"]) and np.array_equal(py[sl], o["proj_y"])
+    assert np.array_equal(ur[sl], o["unproj_range"])
+    assert np.array_equal(idx[b], o["proj_idx"])
+    lab = P.label_projection(o["proj_idx"], labels[b])
+    assert np.array_equal(sem[b], lab)
+    ref = P.assemble_range_image(o, lab, lut).astype(np.float32)
+    assert np.array_equal(image[b], ref)                   # bit-exact [H,W,6] incl. the LUT-mapped label channel
+
+
+@pytest.mark.parametrize("name", ["kitti_64x512", "kitti_64x2048", "nusc_32x1024"])
+def test_against_reference_fixture(golden_dir, name):
+  """Fixtures were produced by the reference's LaserScan/SemLaserScan: equality on every pixel that no
+  libm-ambiguous point touches; index may differ only on exact depth ties (reference: unstable argsort)."""
+  g = _golden(golden_dir, name)
+  H, W, fu, fd = int(g["H"]), int(g["W"]), float(g["fov_up"]), float(g["fov_down"])
+  scan = np.concatenate([g["points"], g["remissions"][:, None]], 1).astype(np.float32)
+  out = _projector(H, W, fu, fd, _lut(golden_dir)).project_scans([scan], labels=[g["label"]], empty_fill=0.0,
+                                                                 want_sem=True, want_point_outputs=True)
+  amb = P.ambiguous_points(g["points"], H, W, fu, fd)
+  px, py = out["proj_x"].cpu().numpy(), out["proj_y"].cpu().numpy()
+  assert np.array_equal(out["unproj_range"].cpu().numpy(), g["unproj_range"])
+  assert np.array_equal(px[~amb], g["proj_x"][~amb]) and np.array_equal(py[~amb], g["proj_y"][~amb])
+  touched = np.zeros((H, W), bool)
+  touched[py[amb], px[amb]] = True
+  touched[g["proj_y"][amb], g["proj_x"][amb]] = True
+  idx = out["proj_idx"][0].cpu().numpy()
+  image = out["image"][0].cpu().numpy()
+  same = ~touched & (idx == g["proj_idx"])
+  assert same.mean() > 0.97
+  assert np.array_equal(image[same], g["final_data"][same])
+  ok = ~touched
+  assert np.array_equal(image[ok][:, 4], g["final_data"][ok][:, 4])   # range channel exact even on ties
+  d = P.point_depth(g["points"])
+  tie = ok & (idx != g["proj_idx"])
+  assert np.array_equal(d[idx[tie]], d[g["proj_idx"][tie]]) and (idx[tie] < g["proj_idx"][tie]).all()
+
+
+def test_ring_variant_and_facade_classes(golden_dir):
+  from pclsegmentation_b200.laserscan import LaserScan, SemLaserScan
+  rng = np.random.default_rng(5)
+  n, H, W = 9000, 32, 1024
+  s = synth_scan(rng, n, 10.0, -30.0, H)
+  ring = rng.integers(0, H, n).astype(np.int32)
+  scan = LaserScan(project=True, H=H, W=W, fov_up=None, fov_down=None, use_ring_projection=True)
+  scan.set_points(s[:, :3].copy(), s[:, 3].copy(), ring)
+  o = P.range_projection_ring(s[:, :3], s[:, 3], ring, H, W)
+  for k in ("proj_range", "proj_xyz", "proj_remission", "proj_idx", "proj_x"):
+    assert np.array_equal(getattr(scan, k), o[k]), k
+  assert (scan.proj_range[scan.proj_idx < 0] == -1).all()
+  # KITTI facade incl. labels
+  g = _golden(golden_dir, "kitti_64x512")
+  sem = SemLaserScan(20, {0: [0, 0, 0]}, project=True, H=64, W=512)
+  sem.set_points(g["points"], g["remissions"])
+  sem.set_label(g["label"])
+  o = P.range_projection(g["points"], g["remissions"], 64, 512, 3.0, -25.0, "cr")
+  assert np.array_equal(sem.proj_idx, o["proj_idx"]) and np.array_equal(sem.proj_range, o["proj_range"])
+  assert np.array_equal(sem.proj_xyz, o["proj_xyz"]) and np.array_equal(sem.proj_y, o["proj_y"])
+  assert np.array_equal(sem.proj_sem_label, P.label_projection(o["proj_idx"], g["label"]))
+  inst = np.zeros((64, 512), np.int32)
+  m = o["proj_idx"] >= 0
+  inst[m] = (g["label"] >> 16)[o["proj_idx"][m]]
+  assert np.array_equal(sem.proj_inst_label, inst)
+  assert np.array_equal(sem.proj_mask, (o["proj_idx"] > 0).astype(np.float32))
+
+
+def test_full_size_properties():
+  """BASELINE config 4 size (64 scans x ~120 k points -> 64x2048): size-independent properties checked on the GPU:
+  the winner of every pixel is the minimum (depth, index) over the points that map to it."""
+  rng = np.random.default_rng(4321)
+  B, H, W = 64, 64, 2048
+  sizes = rng.integers(115000, 125001, B)
+  scans = [synth_scan(rng, int(n)) for n in sizes]
+  out = _projector(H, W, 3.0, -25.0).project_scans(scans, empty_fill=0.0, want_point_outputs=True)
+  dev = out["image"].device
+  off = torch.as_tensor(np.concatenate([[0], np.cumsum(sizes)]), device=dev)
+  scan_id = torch.repeat_interleave(torch.arange(B, device=dev), torch.as_tensor(sizes, device=dev))
+  local = torch.arange(int(off[-1]), device=dev) - off[scan_id]
+  depth_bits = out["unproj_range"].view(torch.int32).to(torch.int64)
+  key = (depth_bits << 32) | local
+  pix = (scan_id * H + out["proj_y"].long()) * W + out["proj_x"].long()
+  best = torch.full((B * H * W,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
+  best.scatter_reduce_(0, pix, key, reduce="amin")
+  keys = out["keys"].reshape(-1)
+  occupied = best != torch.iinfo(torch.int64).max
+  assert torch.equal(keys[occupied], best[occupied]) and bool((keys[~occupied] == -1).all())
+  idx = out["proj_idx"].reshape(-1)
+  assert torch.equal(idx[occupied].long(), best[occupied] & 0xFFFFFFFF) and bool((idx[~occupied] == -1).all())
+  img = out["image"].reshape(-1, 6)
+  assert bool((img[~occupied] == 0).all())
+  g = off[(torch.arange(B * H * W, device=dev) // (H * W))[occupied]] + idx[occupied].long()
+  pts = torch.as_tensor(np.concatenate(scans), device=dev)
+  assert torch.equal(img[occupied][:, :4], pts[g])
+  assert torch.equal(img[occupied][:, 4], out["unproj_range"][g])
+  assert 0.5 < occupied.float().mean().item() < 0.9
