@@ -1,7 +1,489 @@
-// tcgen05 implicit-GEMM convolution (placeholder until the kernel lands; every layer uses the direct kernel).
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a.
+//
+// One persistent, warp-specialised kernel runs every convolution flavour of SqueezeSegV2 and Darknet whose channel
+// counts fit UMMA tiles (3x3 s1, 3x3 s[1,2], 1x1, transposed [1,4] s[1,2]):
+//
+//   GEMM view      M = 128 output pixels (BH rows x BW columns of one frame), N = BN output channels,
+//                  K = taps x Cin, walked as (tap, KC-channel chunk) iterations.
+//   A operand      NHWC activations.  For tap (dh, dw) the tile is the SAME box shifted by (dh, dw): one TMA
+//                  tiled load per iteration from a 4-D map (C, W, H, B); out-of-bounds rows/columns are zero-filled
+//                  by TMA, which IS the SAME padding (no im2col buffer, no halo code).  The stride-2 convolutions read a
+//                  5-D view (C, 2, W/2, H, B) of the same buffer: TF's asymmetric SAME padding for even W (0 left /
+//                  1 right) makes tap kx land on (parity kx&1, pair wo + (kx>>1)), never left of the image.
+//   B operand      folded weights packed [tap][Cout][Cin] (K-major), one TMA load per iteration.
+//   MMA            tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BN x K=16, fp32 accumulators in TMEM,
+//                  double-buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   epilogue       tcgen05.ld -> +bias (BatchNorm folded) -> ReLU / LeakyReLU -> + residual(s) -> 16-bit NHWC store at a
+//                  channel offset (tf.concat) or float32 logits.  The transposed convolution runs as two phases
+//                  (even / odd output columns), each a 2-tap GEMM whose rows are scattered to columns 2j + phase.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
+// (TMEM lane quarter = warp_id % 4).  mbarrier rings: full/empty per smem stage, tmem_full/tmem_empty per accumulator.
 #include "net.cuh"
+
+#include <cuda.h>
+#include <cstring>
+
 namespace pcls {
-int Net::tc_prepare() { return PCLS_OK; }
-int Net::tc_launch(ConvLayer&, const ConvParams&, int, cudaStream_t) { set_error("tc path not built"); return PCLS_ERR_STATE; }
-void Net::tc_release() {}
+
+// ---------------------------------------------------------------------------------------------------------------
+// device-side PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], M=128, K=16 per instruction
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernel parameters
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TC_MAX_TAPS = 9;
+constexpr int TC_THREADS = 192;
+
+struct TcParams {
+  // tile geometry
+  int BW, BH, bw_shift;       // BW * BH = 128, BW = 1 << bw_shift
+  int n_wt, n_ht, n_nt, n_phase, num_tiles;
+  int Hgrid, Wgrid;           // extent of the tiled pixel grid (output grid; input grid for the transposed conv)
+  int out_wmul;               // output column = w * out_wmul + phase
+  int Wout;
+  // K walk
+  int ntaps;                  // taps per phase
+  int kchunks;                // cin_pad / KC
+  int KC, BN;
+  int tap_dh[2][TC_MAX_TAPS], tap_dw[2][TC_MAX_TAPS], tap_par[2][TC_MAX_TAPS], tap_w[2][TC_MAX_TAPS];
+  int a_is_5d;
+  // pipeline
+  int stages, a_bytes, b_bytes;
+  uint32_t idesc, desc_hi;    // instruction descriptor; high 32 bits of the smem matrix descriptors
+  uint32_t tmem_cols;
+  // epilogue
+  int cout, out_channels, out_coff, act, out_f32, is_bf16;
+  void* out;
+  const void* res0;
+  const void* res1;
+  int res0_channels, res1_channels;
+  const float* bias;
+};
+
+template <typename T>
+__device__ __forceinline__ void epilogue_store16(const TcParams& p, const uint32_t (&acc)[16], int n_base, int64_t pix,
+                                                 bool valid) {
+  if (!valid) return;
+  if (p.out_f32) {
+    float* o = reinterpret_cast<float*>(p.out) + pix * p.out_channels + p.out_coff;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int co = n_base + j;
+      if (co < p.cout) o[co] = apply_act(__uint_as_float(acc[j]) + __ldg(p.bias + co), p.act);
+    }
+    return;
+  }
+  const T* r0 = p.res0 ? reinterpret_cast<const T*>(p.res0) + pix * p.res0_channels + p.out_coff : nullptr;
+  const T* r1 = p.res1 ? reinterpret_cast<const T*>(p.res1) + pix * p.res1_channels + p.out_coff : nullptr;
+  T* o = reinterpret_cast<T*>(p.out) + pix * p.out_channels + p.out_coff;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int co = n_base + half * 8;
+    if (co + 8 > p.cout) continue;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[half * 8 + j]) + __ldg(p.bias + co + j), p.act);
+    if (r0) {
+      float f[8];
+      unpack8<T>(__ldg(reinterpret_cast<const int4*>(r0 + co)), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += f[j];
+    }
+    if (r1) {
+      float f[8];
+      unpack8<T>(__ldg(reinterpret_cast<const int4*>(r1 + co)), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += f[j];
+    }
+    *reinterpret_cast<int4*>(o + co) = pack8<T>(v);
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ TcParams p, const int num_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  // carve: [stages x (A tile | B tile)] 1024-aligned, then the barriers, then the TMEM base slot
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = (uint32_t)(p.a_bytes + p.b_bytes);
+  const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
+  const int S = p.stages;
+#define FULL_BAR(s) (bar_base + 8u * (uint32_t)(s))
+#define EMPTY_BAR(s) (bar_base + 8u * (uint32_t)(S + (s)))
+#define TFULL_BAR(a) (bar_base + 8u * (uint32_t)(2 * S + (a)))
+#define TEMPTY_BAR(a) (bar_base + 8u * (uint32_t)(2 * S + 2 + (a)))
+  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * S + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < S; ++s) { mbar_init(FULL_BAR(s), 1); mbar_init(EMPTY_BAR(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(TFULL_BAR(a), 1); mbar_init(TEMPTY_BAR(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation: one warp, whole warp executes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int k_iters = p.ntaps * p.kchunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int r = tile;
+        const int nt = r % p.n_nt; r /= p.n_nt;
+        const int ph = r % p.n_phase; r /= p.n_phase;
+        const int wt = r % p.n_wt; r /= p.n_wt;
+        const int ht = r % p.n_ht;
+        const int b = r / p.n_ht;
+        const int w0 = wt * p.BW, h0 = ht * p.BH, n0 = nt * p.BN;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int dh = p.tap_dh[ph][t], dw = p.tap_dw[ph][t], par = p.tap_par[ph][t], tw = p.tap_w[ph][t];
+          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+            const int s = (int)(it % (uint32_t)S);
+            const uint32_t parity = (it / (uint32_t)S) & 1u;
+            mbar_wait(EMPTY_BAR(s), parity ^ 1u);
+            const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
+            const uint32_t b_dst = a_dst + (uint32_t)p.a_bytes;
+            mbar_arrive_expect_tx(FULL_BAR(s), stage_bytes);
+            if (p.a_is_5d) tma_load_5d(a_dst, &map_a, FULL_BAR(s), kc * p.KC, par, w0 + dw, h0 + dh, b);
+            else tma_load_4d(a_dst, &map_a, FULL_BAR(s), kc * p.KC, w0 + dw, h0 + dh, b);
+            tma_load_3d(b_dst, &map_b, FULL_BAR(s), kc * p.KC, n0, tw);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      uint32_t it = 0, tl = 0;
+      const int mma_per_iter = p.KC / 16;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t acc = tl & 1u, acc_parity = (tl >> 1) & 1u;
+        mbar_wait(TEMPTY_BAR(acc), acc_parity ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.BN;
+        for (int k = 0; k < k_iters; ++k, ++it) {
+          const int s = (int)(it % (uint32_t)S);
+          const uint32_t parity = (it / (uint32_t)S) & 1u;
+          mbar_wait(FULL_BAR(s), parity);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
+          const uint32_t b_addr = a_addr + (uint32_t)p.a_bytes;
+          const uint64_t a_desc0 = ((uint64_t)p.desc_hi << 32) | (uint64_t)((a_addr >> 4) & 0x3FFFu) | (1ull << 16);
+          const uint64_t b_desc0 = ((uint64_t)p.desc_hi << 32) | (uint64_t)((b_addr >> 4) & 0x3FFFu) | (1ull << 16);
+          for (int j = 0; j < mma_per_iter; ++j)  // +32 bytes along K inside the swizzle atom per UMMA_K = 16
+            umma_f16(d_tmem, a_desc0 + (uint64_t)(2 * j), b_desc0 + (uint64_t)(2 * j), p.idesc, (k | j) != 0 ? 1u : 0u);
+          umma_commit(EMPTY_BAR(s));  // smem slot free once these MMAs have read it
+        }
+        umma_commit(TFULL_BAR(acc));  // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;
+    const int ml_h = m >> p.bw_shift, ml_w = m & (p.BW - 1);
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      int r = tile;
+      const int nt = r % p.n_nt; r /= p.n_nt;
+      const int ph = r % p.n_phase; r /= p.n_phase;
+      const int wt = r % p.n_wt; r /= p.n_wt;
+      const int ht = r % p.n_ht;
+      const int b = r / p.n_ht;
+      const int h = ht * p.BH + ml_h, w = wt * p.BW + ml_w;
+      const bool valid = h < p.Hgrid && w < p.Wgrid;
+      const int64_t pix = ((int64_t)b * p.Hgrid + h) * p.Wout + (int64_t)w * p.out_wmul + ph;
+      const uint32_t acc = tl & 1u, acc_parity = (tl >> 1) & 1u;
+      mbar_wait(TFULL_BAR(acc), acc_parity);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.BN;
+      const int n0 = nt * p.BN;
+      for (int c = 0; c < p.BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (p.is_bf16) epilogue_store16<__nv_bfloat16>(p, v, n0 + c, pix, valid);
+        else epilogue_store16<__half>(p, v, n0 + c, pix, valid);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(TEMPTY_BAR(acc));
+    }
+  }
+
+  // teardown
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+#undef FULL_BAR
+#undef EMPTY_BAR
+#undef TFULL_BAR
+#undef TEMPTY_BAR
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side: plans (tensor maps, tile geometry) and launch
+// ---------------------------------------------------------------------------------------------------------------
+struct TcPlan {
+  CUtensorMap map_a, map_b;
+  TcParams prm;
+  size_t smem_bytes;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, bool bf16, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int swizzle_bytes) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return PCLS_ERR_CUDA; }
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base,
+                  gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank); return PCLS_ERR_CUDA; }
+  return PCLS_OK;
+}
+
+// Which layers run on tensor cores: the input tensor must carry >= 16 real channels (the 6-channel network input
+// goes through the CUDA-core kernel), and a stride-2 conv needs an even input width (pair view).
+static bool tc_eligible(const ConvParams& p) {
+  if (p.in_channels < 16 || p.cin_pad > p.in_channels) return false;
+  if (p.mode == MODE_3x3_S2 && (p.Win % 2 != 0 || p.pad_left != 0)) return false;
+  if (p.cout_pad > 256 && p.cout_pad % 256 != 0) return false;
+  return true;
+}
+
+int Net::tc_prepare() {
+  const int max_smem = 227 * 1024;
+  static bool attr_set = false;
+  for (auto& L : convs) {
+    ConvParams& cp = L.p;
+    L.tc_ok = false;
+    if (!tc_eligible(cp)) continue;
+    TcPlan* plan = new TcPlan();
+    memset(plan, 0, sizeof(TcPlan));
+    TcParams& q = plan->prm;
+    const bool bf16 = precision == PCLS_BF16;
+    // K chunk / swizzle: the widest of 64/32/16 channels that divides cin_pad
+    q.KC = (cp.cin_pad % 64 == 0) ? 64 : (cp.cin_pad % 32 == 0) ? 32 : 16;
+    const int swz = q.KC * 2;
+    q.kchunks = cp.cin_pad / q.KC;
+    q.BN = cp.cout_pad <= 256 ? cp.cout_pad : 256;
+    q.n_nt = cp.cout_pad / q.BN;
+    // pixel grid tiled by BW x BH = 128
+    const bool deconv = cp.mode == MODE_DECONV;
+    q.Hgrid = cp.H;
+    q.Wgrid = deconv ? cp.Win : cp.Wout;
+    q.Wout = cp.Wout;
+    q.out_wmul = deconv ? 2 : 1;
+    q.n_phase = deconv ? 2 : 1;
+    int bw = 128;
+    while (bw > 1 && bw / 2 >= q.Wgrid) bw /= 2;  // smallest power of two >= Wgrid, capped at 128
+    q.BW = bw; q.BH = 128 / bw;
+    q.bw_shift = 0;
+    while ((1 << q.bw_shift) < bw) ++q.bw_shift;
+    q.n_wt = (q.Wgrid + q.BW - 1) / q.BW;
+    q.n_ht = (q.Hgrid + q.BH - 1) / q.BH;
+    q.num_tiles = q.n_nt * q.n_phase * q.n_wt * q.n_ht;  // per frame
+    // taps
+    q.a_is_5d = cp.mode == MODE_3x3_S2 ? 1 : 0;
+    if (cp.mode == MODE_1x1) {
+      q.ntaps = 1;
+    } else if (cp.mode == MODE_3x3_S1) {
+      q.ntaps = 9;
+      for (int t = 0; t < 9; ++t) { q.tap_dh[0][t] = t / 3 - 1; q.tap_dw[0][t] = t % 3 - 1; q.tap_w[0][t] = t; }
+    } else if (cp.mode == MODE_3x3_S2) {
+      q.ntaps = 9;  // input column 2*wo + kx -> (parity kx & 1, pair wo + (kx >> 1))
+      for (int t = 0; t < 9; ++t) {
+        q.tap_dh[0][t] = t / 3 - 1; q.tap_par[0][t] = (t % 3) & 1; q.tap_dw[0][t] = (t % 3) >> 1; q.tap_w[0][t] = t;
+      }
+    } else {
+      q.ntaps = 2;  // out[2j]   = in[j] w1 + in[j-1] w3 ;  out[2j+1] = in[j+1] w0 + in[j] w2
+      q.tap_dw[0][0] = 0;  q.tap_w[0][0] = 1;
+      q.tap_dw[0][1] = -1; q.tap_w[0][1] = 3;
+      q.tap_dw[1][0] = 1;  q.tap_w[1][0] = 0;
+      q.tap_dw[1][1] = 0;  q.tap_w[1][1] = 2;
+    }
+    // pipeline depth
+    q.a_bytes = 128 * q.KC * 2;
+    q.b_bytes = q.BN * q.KC * 2;
+    const int stage_bytes = q.a_bytes + q.b_bytes;
+    int stages = (max_smem - 2048) / stage_bytes;
+    if (stages > 12) stages = 12;
+    if (stages < 2) { delete plan; continue; }
+    q.stages = stages;
+    plan->smem_bytes = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + (size_t)(2 * stages + 4) * 8 + 16;
+    // descriptors
+    const uint32_t layout = swz == 128 ? 2u : swz == 64 ? 4u : 6u;  // UMMA LayoutType
+    const uint32_t sbo = (uint32_t)(8 * swz) >> 4;                   // 8 rows of one swizzle span
+    q.desc_hi = sbo | (1u << 14) /*descriptor version (sm_100)*/ | (layout << 29);
+    q.idesc = (1u << 4) /*D = f32*/ | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) |
+              ((uint32_t)(q.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * q.BN)) cols <<= 1;
+    q.tmem_cols = cols;
+    // epilogue
+    q.cout = cp.cout; q.out_channels = cp.out_channels; q.out_coff = cp.out_coff; q.act = cp.act;
+    q.out_f32 = cp.out_f32; q.is_bf16 = bf16 ? 1 : 0;
+    q.res0_channels = cp.res0_channels; q.res1_channels = cp.res1_channels;
+    q.bias = cp.bias;
+
+    // tensor maps.  A: activations of the input tensor inside the arena (extent = frames_per_pass frames).
+    char* a_base = (char*)tensor_ptr(L.in, frames_per_pass);
+    const uint64_t C = (uint64_t)cp.in_channels, Wi = (uint64_t)cp.Win, Hh = (uint64_t)cp.H, F = (uint64_t)frames_per_pass;
+    int rc;
+    if (q.a_is_5d) {
+      const uint64_t dims[5] = {C, 2, Wi / 2, Hh, F};
+      const uint64_t str[4] = {C * 2, C * 4, Wi * C * 2, Hh * Wi * C * 2};
+      const uint32_t box[5] = {(uint32_t)q.KC, 1, (uint32_t)q.BW, (uint32_t)q.BH, 1};
+      rc = make_map(&plan->map_a, bf16, a_base, 5, dims, str, box, swz);
+    } else {
+      const uint64_t dims[4] = {C, Wi, Hh, F};
+      const uint64_t str[3] = {C * 2, Wi * C * 2, Hh * Wi * C * 2};
+      const uint32_t box[4] = {(uint32_t)q.KC, (uint32_t)q.BW, (uint32_t)q.BH, 1};
+      rc = make_map(&plan->map_a, bf16, a_base, 4, dims, str, box, swz);
+    }
+    if (rc) { delete plan; return rc; }
+    {
+      const uint64_t dims[3] = {(uint64_t)cp.cin_pad, (uint64_t)cp.cout_pad, (uint64_t)cp.ntaps};
+      const uint64_t str[2] = {(uint64_t)cp.cin_pad * 2, (uint64_t)cp.cin_pad * cp.cout_pad * 2};
+      const uint32_t box[3] = {(uint32_t)q.KC, (uint32_t)q.BN, 1};
+      rc = make_map(&plan->map_b, bf16, const_cast<void*>(cp.w), 3, dims, str, box, swz);
+    }
+    if (rc) { delete plan; return rc; }
+    L.tc = plan;
+    L.tc_ok = true;
+  }
+  if (!attr_set) {
+    PCLS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    attr_set = true;
+  }
+  return PCLS_OK;
+}
+
+int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
+  TcPlan* plan = L.tc;
+  TcParams prm = plan->prm;
+  prm.out = p.out; prm.res0 = p.res0; prm.res1 = p.res1;
+  const int num_tiles = prm.num_tiles * nb;
+  if (num_tiles == 0) return PCLS_OK;
+  const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  conv_tc_kernel<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, prm, num_tiles);
+  return check_launch("conv_tc_kernel");
+}
+
+void Net::tc_release() {
+  for (auto& L : convs) { delete L.tc; L.tc = nullptr; L.tc_ok = false; }
+}
+
 }  // namespace pcls

@@ -31,7 +31,7 @@ def test_head_matches_oracle(n, nc, none):
   _lib.check(lib.pcls_head(lg.data_ptr(), m.view(torch.uint8).data_ptr(), n, nc, none, probs.data_ptr(),
                            preds.data_ptr(), _s()))
   p_ref, pred_ref = O.segmentation_head(torch.from_numpy(logits), torch.from_numpy(mask), none)
-  assert np.allclose(probs.cpu().numpy(), p_ref.numpy(), rtol=0, atol=2e-7)
+  assert np.allclose(probs.cpu().numpy(), p_ref.numpy(), rtol=2e-6, atol=1e-7)
   got = preds.cpu().numpy()
   # argmax is taken over OUR rounded probabilities: it must equal the reference wherever the oracle's top-2
   # probabilities are not within float rounding of each other, and always be a maximiser of our own probabilities
