@@ -94,7 +94,7 @@ def test_ring_variant_and_facade_classes(golden_dir):
   assert (scan.proj_range[scan.proj_idx < 0] == -1).all()
   # KITTI facade incl. labels
   g = _golden(golden_dir, "kitti_64x512")
-  sem = SemLaserScan(20, {0: [0, 0, 0]}, project=True, H=64, W=512)
+  sem = SemLaserScan(20, {k: [k % 256, 0, 0] for k in range(260)}, project=True, H=64, W=512)
   sem.set_points(g["points"], g["remissions"])
   sem.set_label(g["label"])
   o = P.range_projection(g["points"], g["remissions"], 64, 512, 3.0, -25.0, "cr")
