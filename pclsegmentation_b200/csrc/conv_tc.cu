@@ -104,7 +104,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // kernel parameters
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int TC_MAX_TAPS = 9;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 epilogue groups (one per accumulator)
 
 struct TcParams {
   // tile geometry
@@ -132,43 +132,55 @@ struct TcParams {
   const float* bias;
 };
 
+// 32 accumulator columns of one pixel row: +bias (smem), activation, + prefetched residuals, store.
 template <typename T>
-__device__ __forceinline__ void epilogue_store16(const TcParams& p, const uint32_t (&acc)[16], int n_base, int64_t pix,
-                                                 bool valid) {
+__device__ __forceinline__ void epilogue_store32(const TcParams& p, const uint32_t (&acc)[32], const float* bias_s,
+                                                 int n_base, int64_t pix, bool valid, const int4 (&r0)[4],
+                                                 const int4 (&r1)[4]) {
   if (!valid) return;
   if (p.out_f32) {
     float* o = reinterpret_cast<float*>(p.out) + pix * p.out_channels + p.out_coff;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < 32; ++j) {
       const int co = n_base + j;
-      if (co < p.cout) o[co] = apply_act(__uint_as_float(acc[j]) + __ldg(p.bias + co), p.act);
+      if (co < p.cout) o[co] = apply_act(__uint_as_float(acc[j]) + bias_s[co], p.act);
     }
     return;
   }
-  const T* r0 = p.res0 ? reinterpret_cast<const T*>(p.res0) + pix * p.res0_channels + p.out_coff : nullptr;
-  const T* r1 = p.res1 ? reinterpret_cast<const T*>(p.res1) + pix * p.res1_channels + p.out_coff : nullptr;
   T* o = reinterpret_cast<T*>(p.out) + pix * p.out_channels + p.out_coff;
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int co = n_base + half * 8;
+  for (int g = 0; g < 4; ++g) {
+    const int co = n_base + g * 8;
     if (co + 8 > p.cout) continue;
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[half * 8 + j]) + __ldg(p.bias + co + j), p.act);
-    if (r0) {
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[g * 8 + j]) + bias_s[co + j], p.act);
+    if (p.res0) {
       float f[8];
-      unpack8<T>(__ldg(reinterpret_cast<const int4*>(r0 + co)), f);
+      unpack8<T>(r0[g], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += f[j];
     }
-    if (r1) {
+    if (p.res1) {
       float f[8];
-      unpack8<T>(__ldg(reinterpret_cast<const int4*>(r1 + co)), f);
+      unpack8<T>(r1[g], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += f[j];
     }
     *reinterpret_cast<int4*>(o + co) = pack8<T>(v);
   }
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -187,6 +199,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * S + 4);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16u - smem_u32(smem_raw)));  // [n_nt * BN]
+  for (int i = threadIdx.x; i < p.n_nt * p.BN; i += blockDim.x) bias_s[i] = p.bias[i];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -265,12 +279,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue warps =====================
+    // ===================== epilogue: two warp-groups, group g drains accumulator g =====================
+    const int grp = (warp - 2) >> 2;
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;
     const int ml_h = m >> p.bw_shift, ml_w = m & (p.BW - 1);
+    const bool has_res = (p.res0 != nullptr) || (p.res1 != nullptr);
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      if ((int)(tl & 1u) != grp) continue;
       int r = tile;
       const int nt = r % p.n_nt; r /= p.n_nt;
       const int ph = r % p.n_phase; r /= p.n_phase;
@@ -280,21 +297,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int h = ht * p.BH + ml_h, w = wt * p.BW + ml_w;
       const bool valid = h < p.Hgrid && w < p.Wgrid;
       const int64_t pix = ((int64_t)b * p.Hgrid + h) * p.Wout + (int64_t)w * p.out_wmul + ph;
-      const uint32_t acc = tl & 1u, acc_parity = (tl >> 1) & 1u;
-      mbar_wait(TFULL_BAR(acc), acc_parity);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.BN;
+      const uint32_t acc_parity = (tl >> 1) & 1u;
       const int n0 = nt * p.BN;
-      for (int c = 0; c < p.BN; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_row + (uint32_t)c, v);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)grp * (uint32_t)p.BN;
+      // residual rows are prefetched BEFORE waiting for the accumulator, so their DRAM latency overlaps the MMAs
+      int4 r0[4], r1[4];
+      auto load_res = [&](int c) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int co = n0 + c + g * 8;
+          const bool okc = valid && (co + 8 <= p.cout);
+          r0[g] = (p.res0 && okc) ? __ldg(reinterpret_cast<const int4*>(
+                      reinterpret_cast<const uint16_t*>(p.res0) + pix * p.res0_channels + p.out_coff + co)) : make_int4(0, 0, 0, 0);
+          r1[g] = (p.res1 && okc) ? __ldg(reinterpret_cast<const int4*>(
+                      reinterpret_cast<const uint16_t*>(p.res1) + pix * p.res1_channels + p.out_coff + co)) : make_int4(0, 0, 0, 0);
+        }
+      };
+      if (has_res) load_res(0);
+      mbar_wait(TFULL_BAR(grp), acc_parity);
+      tc_fence_after();
+      for (int c = 0; c < p.BN; c += 32) {
+        uint32_t v[32];
+        if (c + 32 <= p.BN) {
+          tmem_ld32(t_row + (uint32_t)c, v);
+        } else {  // BN % 32 == 16 tail
+          uint32_t v16[16];
+          tmem_ld16(t_row + (uint32_t)c, v16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0u; }
+        }
         tmem_ld_wait();
-        if (p.is_bf16) epilogue_store16<__nv_bfloat16>(p, v, n0 + c, pix, valid);
-        else epilogue_store16<__half>(p, v, n0 + c, pix, valid);
+        if (p.is_bf16) epilogue_store32<__nv_bfloat16>(p, v, bias_s, n0 + c, pix, valid, r0, r1);
+        else epilogue_store32<__half>(p, v, bias_s, n0 + c, pix, valid, r0, r1);
+        if (has_res && c + 32 < p.BN) load_res(c + 32);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(TEMPTY_BAR(acc));
+      if (lane == 0) mbar_arrive(TEMPTY_BAR(grp));
     }
   }
 
@@ -418,11 +457,12 @@ int Net::tc_prepare() {
     q.a_bytes = 128 * q.KC * 2;
     q.b_bytes = q.BN * q.KC * 2;
     const int stage_bytes = q.a_bytes + q.b_bytes;
-    int stages = (max_smem - 2048) / stage_bytes;
+    int stages = (max_smem - 2048 - cp.cout_pad * 4) / stage_bytes;
     if (stages > 12) stages = 12;
     if (stages < 2) { delete plan; continue; }
     q.stages = stages;
-    plan->smem_bytes = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + (size_t)(2 * stages + 4) * 8 + 16;
+    plan->smem_bytes = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + (size_t)(2 * stages + 4) * 8 + 16 +
+                       (size_t)cp.cout_pad * 4 /*bias*/;
     // descriptors
     const uint32_t layout = swz == 128 ? 2u : swz == 64 ? 4u : 6u;  // UMMA LayoutType
     const uint32_t sbo = (uint32_t)(8 * swz) >> 4;                   // 8 rows of one swizzle span
