@@ -113,16 +113,23 @@ struct TcParams {
   int Hgrid, Wgrid;           // extent of the tiled pixel grid (output grid; input grid for the transposed conv)
   int out_wmul;               // output column = w * out_wmul + phase
   int Wout;
-  // K walk
-  int ntaps;                  // taps per phase
+  // K walk: per tile, n_groups A loads per K chunk; each A tile feeds `sub` tap MMAs that start `sub_row[s]` rows into it
+  int n_groups, sub;
   int kchunks;                // cin_pad / KC
   int KC, BN;
-  int tap_dh[2][TC_MAX_TAPS], tap_dw[2][TC_MAX_TAPS], tap_par[2][TC_MAX_TAPS], tap_w[2][TC_MAX_TAPS];
+  int grp_dh[2][TC_MAX_TAPS], grp_dw[2][TC_MAX_TAPS], grp_par[2][TC_MAX_TAPS];  // TMA coordinate offsets of the A box
+  int grp_w[2][TC_MAX_TAPS][3];                                                  // weight tap index per (group, sub)
+  int sub_row[3];
   int a_is_5d;
+  int a_rows;                 // rows of the A box: 128, or 130 with the one-pixel halo on both sides
+  int b_resident;             // 1: every weight tile of the layer is loaded into smem once per CTA
+  int ntaps_total;
+  int use_base_offset;
   // pipeline
-  int stages, a_bytes, b_bytes;
+  int stages, a_bytes, b_tile_bytes, bres_bytes;
   uint32_t idesc, desc_hi;    // instruction descriptor; high 32 bits of the smem matrix descriptors
   uint32_t tmem_cols;
+  int n_acc;                  // TMEM accumulator buffers (power of two, n_acc * BN <= 512)
   // epilogue
   int cout, out_channels, out_coff, act, out_f32, is_bf16;
   void* out;
@@ -183,20 +190,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
+template <int KC, int SUB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ TcParams p, const int num_tiles) {
   extern __shared__ uint8_t smem_raw[];
-  // carve: [stages x (A tile | B tile)] 1024-aligned, then the barriers, then the TMEM base slot
+  // carve: [stages x (A tile | B tiles)] 1024-aligned, resident weights, barriers, TMEM base slot, bias
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = (uint32_t)(p.a_bytes + p.b_bytes);
-  const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
   const int S = p.stages;
+  const uint32_t a_bytes = (uint32_t)p.a_bytes, b_tile_bytes = (uint32_t)p.b_tile_bytes;
+  const bool b_resident = p.b_resident != 0;
+  const uint32_t b_stage_bytes = b_resident ? 0u : (uint32_t)SUB * b_tile_bytes;
+  const uint32_t stage_bytes = a_bytes + b_stage_bytes;
+  const uint32_t bres_base = smem_base + (uint32_t)S * stage_bytes;   // resident weights (1024-aligned)
+  const uint32_t bar_base = bres_base + (uint32_t)p.bres_bytes;
 #define FULL_BAR(s) (bar_base + 8u * (uint32_t)(s))
 #define EMPTY_BAR(s) (bar_base + 8u * (uint32_t)(S + (s)))
 #define TFULL_BAR(a) (bar_base + 8u * (uint32_t)(2 * S + (a)))
-#define TEMPTY_BAR(a) (bar_base + 8u * (uint32_t)(2 * S + 2 + (a)))
-  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * S + 4);
+#define TEMPTY_BAR(a) (bar_base + 8u * (uint32_t)(2 * S + 8 + (a)))
+#define BRES_BAR (bar_base + 8u * (uint32_t)(2 * S + 16))
+  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * S + 17);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* bias_s = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16u - smem_u32(smem_raw)));  // [n_nt * BN]
@@ -208,7 +221,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < S; ++s) { mbar_init(FULL_BAR(s), 1); mbar_init(EMPTY_BAR(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(TFULL_BAR(a), 1); mbar_init(TEMPTY_BAR(a), 4); }
+    for (int a = 0; a < 8; ++a) { mbar_init(TFULL_BAR(a), 1); mbar_init(TEMPTY_BAR(a), 4); }
+    mbar_init(BRES_BAR, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -222,32 +236,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int k_iters = p.ntaps * p.kchunks;
+  const int n_groups = p.n_groups, kchunks = p.kchunks, n_nt = p.n_nt, n_phase = p.n_phase, n_wt = p.n_wt, n_ht = p.n_ht;
+  const int BN = p.BN;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (one thread) =====================
     if (lane == 0) {
-      uint32_t it = 0;
+      if (b_resident) {
+        // weight-stationary: every weight tile of the layer once per CTA, laid out in MMA iteration order
+        // [phase][group][K chunk][sub] so that the issuer only increments an address
+        mbar_arrive_expect_tx(BRES_BAR, (uint32_t)(n_phase * n_groups * kchunks * SUB) * b_tile_bytes);
+        uint32_t dst = bres_base;
+        for (int ph = 0; ph < n_phase; ++ph)
+          for (int g = 0; g < n_groups; ++g)
+            for (int kc = 0; kc < kchunks; ++kc)
+#pragma unroll
+              for (int u = 0; u < SUB; ++u, dst += b_tile_bytes)
+                tma_load_3d(dst, &map_b, BRES_BAR, kc * KC, 0, p.grp_w[ph][g][u]);
+      }
+      const uint32_t tx_bytes = (uint32_t)(p.a_rows * KC * 2) + b_stage_bytes;
+      const int BW = p.BW, BH = p.BH;
+      const bool is5d = p.a_is_5d != 0;
+      int stage = 0;
+      uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int r = tile;
-        const int nt = r % p.n_nt; r /= p.n_nt;
-        const int ph = r % p.n_phase; r /= p.n_phase;
-        const int wt = r % p.n_wt; r /= p.n_wt;
-        const int ht = r % p.n_ht;
-        const int b = r / p.n_ht;
-        const int w0 = wt * p.BW, h0 = ht * p.BH, n0 = nt * p.BN;
-        for (int t = 0; t < p.ntaps; ++t) {
-          const int dh = p.tap_dh[ph][t], dw = p.tap_dw[ph][t], par = p.tap_par[ph][t], tw = p.tap_w[ph][t];
-          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-            const int s = (int)(it % (uint32_t)S);
-            const uint32_t parity = (it / (uint32_t)S) & 1u;
-            mbar_wait(EMPTY_BAR(s), parity ^ 1u);
-            const uint32_t a_dst = smem_base + (uint32_t)s * stage_bytes;
-            const uint32_t b_dst = a_dst + (uint32_t)p.a_bytes;
-            mbar_arrive_expect_tx(FULL_BAR(s), stage_bytes);
-            if (p.a_is_5d) tma_load_5d(a_dst, &map_a, FULL_BAR(s), kc * p.KC, par, w0 + dw, h0 + dh, b);
-            else tma_load_4d(a_dst, &map_a, FULL_BAR(s), kc * p.KC, w0 + dw, h0 + dh, b);
-            tma_load_3d(b_dst, &map_b, FULL_BAR(s), kc * p.KC, n0, tw);
+        const int nt = r % n_nt; r /= n_nt;
+        const int ph = r % n_phase; r /= n_phase;
+        const int wt = r % n_wt; r /= n_wt;
+        const int ht = r % n_ht;
+        const int b = r / n_ht;
+        const int w0 = wt * BW, h0 = ht * BH, n0 = nt * BN;
+        for (int g = 0; g < n_groups; ++g) {
+          const int hh = h0 + p.grp_dh[ph][g], ww = w0 + p.grp_dw[ph][g], par = p.grp_par[ph][g];
+          int wtap[SUB];
+#pragma unroll
+          for (int u = 0; u < SUB; ++u) wtap[u] = p.grp_w[ph][g][u];
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(EMPTY_BAR(stage), phase ^ 1u);
+            const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
+            const uint32_t fb = FULL_BAR(stage);
+            mbar_arrive_expect_tx(fb, tx_bytes);
+            if (is5d) tma_load_5d(a_dst, &map_a, fb, kc * KC, par, ww, hh, b);
+            else tma_load_4d(a_dst, &map_a, fb, kc * KC, ww, hh, b);
+            if (!b_resident) {
+#pragma unroll
+              for (int u = 0; u < SUB; ++u)
+                tma_load_3d(a_dst + a_bytes + (uint32_t)u * b_tile_bytes, &map_b, fb, kc * KC, n0, wtap[u]);
+            }
+            if (++stage == S) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -255,51 +292,72 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      uint32_t it = 0, tl = 0;
-      const int mma_per_iter = p.KC / 16;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-        const uint32_t acc = tl & 1u, acc_parity = (tl >> 1) & 1u;
-        mbar_wait(TEMPTY_BAR(acc), acc_parity ^ 1u);  // epilogue has drained this accumulator
+      const uint32_t desc_hi = p.desc_hi, idesc = p.idesc;
+      const uint32_t n_acc = (uint32_t)p.n_acc;
+      uint32_t sub_off[SUB];
+#pragma unroll
+      for (int u = 0; u < SUB; ++u) sub_off[u] = (uint32_t)(p.sub_row[u] * KC * 2);
+      const int k_iters = n_groups * kchunks;
+      const uint32_t bres_phase_bytes = (uint32_t)(k_iters * SUB) * b_tile_bytes;
+      int stage = 0;
+      uint32_t phase = 0, acc = 0, acc_phase = 0;
+      if (b_resident) mbar_wait(BRES_BAR, 0u);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(TEMPTY_BAR(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.BN;
-        for (int k = 0; k < k_iters; ++k, ++it) {
-          const int s = (int)(it % (uint32_t)S);
-          const uint32_t parity = (it / (uint32_t)S) & 1u;
-          mbar_wait(FULL_BAR(s), parity);
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)BN;
+        uint32_t b_res = bres_base + (n_phase > 1 ? (uint32_t)((tile / n_nt) % n_phase) * bres_phase_bytes : 0u);
+        uint32_t accumulate = 0u;
+        for (int k = 0; k < k_iters; ++k) {
+          mbar_wait(FULL_BAR(stage), phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_base + (uint32_t)s * stage_bytes;
-          const uint32_t b_addr = a_addr + (uint32_t)p.a_bytes;
-          const uint64_t a_desc0 = ((uint64_t)p.desc_hi << 32) | (uint64_t)((a_addr >> 4) & 0x3FFFu) | (1ull << 16);
-          const uint64_t b_desc0 = ((uint64_t)p.desc_hi << 32) | (uint64_t)((b_addr >> 4) & 0x3FFFu) | (1ull << 16);
-          for (int j = 0; j < mma_per_iter; ++j)  // +32 bytes along K inside the swizzle atom per UMMA_K = 16
-            umma_f16(d_tmem, a_desc0 + (uint64_t)(2 * j), b_desc0 + (uint64_t)(2 * j), p.idesc, (k | j) != 0 ? 1u : 0u);
-          umma_commit(EMPTY_BAR(s));  // smem slot free once these MMAs have read it
+          const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
+          uint32_t b_addr = b_resident ? b_res : a_addr + a_bytes;
+#pragma unroll
+          for (int u = 0; u < SUB; ++u) {
+            // descriptors: start address (>>4) | LBO = 1 in the low word; SBO / version / swizzle mode in the high word.
+            // A row-shifted start (halo taps) needs no base offset: the swizzle is a function of absolute smem address bits.
+            const uint64_t a_desc = ((uint64_t)desc_hi << 32) | (uint64_t)((((a_addr + sub_off[u]) >> 4) & 0x3FFFu) | 0x10000u);
+            const uint64_t b_desc = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_addr >> 4) & 0x3FFFu) | 0x10000u);
+#pragma unroll
+            for (int j = 0; j < KC / 16; ++j) {  // +32 bytes along K inside the swizzle atom per UMMA_K = 16
+              umma_f16(d_tmem, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j), idesc, accumulate);
+              accumulate = 1u;
+            }
+            b_addr += b_tile_bytes;
+          }
+          b_res += (uint32_t)SUB * b_tile_bytes;
+          umma_commit(EMPTY_BAR(stage));  // smem slot free once these MMAs have read it
+          if (++stage == S) { stage = 0; phase ^= 1u; }
         }
         umma_commit(TFULL_BAR(acc));  // accumulator complete
+        if (++acc == n_acc) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
-    // ===================== epilogue: two warp-groups, group g drains accumulator g =====================
+    // ===================== epilogue: two warp-groups, alternate tiles =====================
     const int grp = (warp - 2) >> 2;
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;
     const int ml_h = m >> p.bw_shift, ml_w = m & (p.BW - 1);
     const bool has_res = (p.res0 != nullptr) || (p.res1 != nullptr);
+    const uint32_t n_acc = (uint32_t)p.n_acc;
+    const int BW = p.BW, BH = p.BH, Hgrid = p.Hgrid, Wgrid = p.Wgrid, Wout = p.Wout, out_wmul = p.out_wmul;
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       if ((int)(tl & 1u) != grp) continue;
       int r = tile;
-      const int nt = r % p.n_nt; r /= p.n_nt;
-      const int ph = r % p.n_phase; r /= p.n_phase;
-      const int wt = r % p.n_wt; r /= p.n_wt;
-      const int ht = r % p.n_ht;
-      const int b = r / p.n_ht;
-      const int h = ht * p.BH + ml_h, w = wt * p.BW + ml_w;
-      const bool valid = h < p.Hgrid && w < p.Wgrid;
-      const int64_t pix = ((int64_t)b * p.Hgrid + h) * p.Wout + (int64_t)w * p.out_wmul + ph;
-      const uint32_t acc_parity = (tl >> 1) & 1u;
-      const int n0 = nt * p.BN;
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)grp * (uint32_t)p.BN;
+      const int nt = r % n_nt; r /= n_nt;
+      const int ph = r % n_phase; r /= n_phase;
+      const int wt = r % n_wt; r /= n_wt;
+      const int ht = r % n_ht;
+      const int b = r / n_ht;
+      const int h = ht * BH + ml_h, w = wt * BW + ml_w;
+      const bool valid = h < Hgrid && w < Wgrid;
+      const int64_t pix = ((int64_t)b * Hgrid + h) * Wout + (int64_t)w * out_wmul + ph;
+      const uint32_t acc = tl & (n_acc - 1u), acc_parity = (tl / n_acc) & 1u;
+      const int n0 = nt * BN;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)BN;
       // residual rows are prefetched BEFORE waiting for the accumulator, so their DRAM latency overlaps the MMAs
       int4 r0[4], r1[4];
       auto load_res = [&](int c) {
@@ -314,11 +372,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       };
       if (has_res) load_res(0);
-      mbar_wait(TFULL_BAR(grp), acc_parity);
+      mbar_wait(TFULL_BAR(acc), acc_parity);
       tc_fence_after();
-      for (int c = 0; c < p.BN; c += 32) {
+      for (int c = 0; c < BN; c += 32) {
         uint32_t v[32];
-        if (c + 32 <= p.BN) {
+        if (c + 32 <= BN) {
           tmem_ld32(t_row + (uint32_t)c, v);
         } else {  // BN % 32 == 16 tail
           uint32_t v16[16];
@@ -329,11 +387,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tmem_ld_wait();
         if (p.is_bf16) epilogue_store32<__nv_bfloat16>(p, v, bias_s, n0 + c, pix, valid, r0, r1);
         else epilogue_store32<__half>(p, v, bias_s, n0 + c, pix, valid, r0, r1);
-        if (has_res && c + 32 < p.BN) load_res(c + 32);
+        if (has_res && c + 32 < BN) load_res(c + 32);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(TEMPTY_BAR(grp));
+      if (lane == 0) mbar_arrive(TEMPTY_BAR(acc));
     }
   }
 
@@ -349,6 +407,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #undef EMPTY_BAR
 #undef TFULL_BAR
 #undef TEMPTY_BAR
+#undef BRES_BAR
+}
+
+typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const TcParams, const int);
+static TcKernelFn tc_kernel_for(int KC, int SUB) {
+  if (SUB == 3) return KC == 64 ? conv_tc_kernel<64, 3> : KC == 32 ? conv_tc_kernel<32, 3> : conv_tc_kernel<16, 3>;
+  return KC == 64 ? conv_tc_kernel<64, 1> : KC == 32 ? conv_tc_kernel<32, 1> : conv_tc_kernel<16, 1>;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -393,6 +458,9 @@ static int make_map(CUtensorMap* map, bool bf16, void* base, int rank, const uin
   return PCLS_OK;
 }
 
+// A/B switches for measurement (pcls_net_set_option before finalize): halo reuse, resident weights, base offset
+int tc_halo_mode = 1, tc_resident_mode = 1, tc_base_offset_mode = 0;  // measured: UMMA swizzles on absolute smem address bits, a row-shifted start needs NO base offset
+
 // Which layers run on tensor cores: the input tensor must carry >= 16 real channels (the 6-channel network input
 // goes through the CUDA-core kernel), and a stride-2 conv needs an even input width (pair view).
 static bool tc_eligible(const ConvParams& p) {
@@ -434,43 +502,67 @@ int Net::tc_prepare() {
     q.n_wt = (q.Wgrid + q.BW - 1) / q.BW;
     q.n_ht = (q.Hgrid + q.BH - 1) / q.BH;
     q.num_tiles = q.n_nt * q.n_phase * q.n_wt * q.n_ht;  // per frame
-    // taps
+    // K walk
     q.a_is_5d = cp.mode == MODE_3x3_S2 ? 1 : 0;
+    q.sub = 1; q.a_rows = 128; q.ntaps_total = cp.ntaps;
+    q.use_base_offset = tc_base_offset_mode;
+    // halo reuse needs the three weight tiles of a row next to the A tile: only when >= 4 stages still fit
+    bool halo = cp.mode == MODE_3x3_S1 && q.BW == 128 && tc_halo_mode;
+    if (halo) {
+      const int all_w_ = cp.ntaps * q.kchunks * q.BN * q.KC * 2;
+      const bool resident_ = tc_resident_mode && q.n_nt == 1 && all_w_ <= 112 * 1024;
+      const int st_ = (130 * q.KC * 2 + 1023) / 1024 * 1024 + (resident_ ? 0 : 3 * q.BN * q.KC * 2);
+      if ((max_smem - 2048 - cp.cout_pad * 4 - (resident_ ? all_w_ + 1024 : 0)) / st_ < 4) halo = false;
+    }
     if (cp.mode == MODE_1x1) {
-      q.ntaps = 1;
+      q.n_groups = 1;
+    } else if (halo) {
+      // one A tile of 130 pixels (one-pixel halo each side, zero-filled by TMA at the image border) per input row
+      // serves the three horizontal taps: tap dw starts (dw + 1) rows into the tile.
+      q.n_groups = 3; q.sub = 3; q.a_rows = 130;
+      for (int g = 0; g < 3; ++g) {
+        q.grp_dh[0][g] = g - 1; q.grp_dw[0][g] = -1;
+        for (int u = 0; u < 3; ++u) q.grp_w[0][g][u] = g * 3 + u;
+      }
+      q.sub_row[0] = 0; q.sub_row[1] = 1; q.sub_row[2] = 2;
     } else if (cp.mode == MODE_3x3_S1) {
-      q.ntaps = 9;
-      for (int t = 0; t < 9; ++t) { q.tap_dh[0][t] = t / 3 - 1; q.tap_dw[0][t] = t % 3 - 1; q.tap_w[0][t] = t; }
+      q.n_groups = 9;
+      for (int t = 0; t < 9; ++t) { q.grp_dh[0][t] = t / 3 - 1; q.grp_dw[0][t] = t % 3 - 1; q.grp_w[0][t][0] = t; }
     } else if (cp.mode == MODE_3x3_S2) {
-      q.ntaps = 9;  // input column 2*wo + kx -> (parity kx & 1, pair wo + (kx >> 1))
+      q.n_groups = 9;  // input column 2*wo + kx -> (parity kx & 1, pair wo + (kx >> 1))
       for (int t = 0; t < 9; ++t) {
-        q.tap_dh[0][t] = t / 3 - 1; q.tap_par[0][t] = (t % 3) & 1; q.tap_dw[0][t] = (t % 3) >> 1; q.tap_w[0][t] = t;
+        q.grp_dh[0][t] = t / 3 - 1; q.grp_par[0][t] = (t % 3) & 1; q.grp_dw[0][t] = (t % 3) >> 1; q.grp_w[0][t][0] = t;
       }
     } else {
-      q.ntaps = 2;  // out[2j]   = in[j] w1 + in[j-1] w3 ;  out[2j+1] = in[j+1] w0 + in[j] w2
-      q.tap_dw[0][0] = 0;  q.tap_w[0][0] = 1;
-      q.tap_dw[0][1] = -1; q.tap_w[0][1] = 3;
-      q.tap_dw[1][0] = 1;  q.tap_w[1][0] = 0;
-      q.tap_dw[1][1] = 0;  q.tap_w[1][1] = 2;
+      q.n_groups = 2;  // out[2j]   = in[j] w1 + in[j-1] w3 ;  out[2j+1] = in[j+1] w0 + in[j] w2
+      q.grp_dw[0][0] = 0;  q.grp_w[0][0][0] = 1;
+      q.grp_dw[0][1] = -1; q.grp_w[0][1][0] = 3;
+      q.grp_dw[1][0] = 1;  q.grp_w[1][0][0] = 0;
+      q.grp_dw[1][1] = 0;  q.grp_w[1][1][0] = 2;
     }
-    // pipeline depth
-    q.a_bytes = 128 * q.KC * 2;
-    q.b_bytes = q.BN * q.KC * 2;
-    const int stage_bytes = q.a_bytes + q.b_bytes;
-    int stages = (max_smem - 2048 - cp.cout_pad * 4) / stage_bytes;
+    // pipeline depth; weights stay resident in smem when the whole layer fits next to >= 4 stages
+    q.a_bytes = (q.a_rows * q.KC * 2 + 1023) / 1024 * 1024;
+    q.b_tile_bytes = q.BN * q.KC * 2;
+    const int all_w = q.n_phase * q.n_groups * q.kchunks * q.sub * q.b_tile_bytes;
+    q.b_resident = (tc_resident_mode && q.n_nt == 1 && all_w <= 112 * 1024) ? 1 : 0;
+    q.bres_bytes = q.b_resident ? (all_w + 1023) / 1024 * 1024 : 0;
+    const int stage_bytes = q.a_bytes + (q.b_resident ? 0 : q.sub * q.b_tile_bytes);
+    int stages = (max_smem - 2048 - cp.cout_pad * 4 - q.bres_bytes) / stage_bytes;
     if (stages > 12) stages = 12;
     if (stages < 2) { delete plan; continue; }
     q.stages = stages;
-    plan->smem_bytes = (size_t)stages * stage_bytes + 1024 /*alignment slack*/ + (size_t)(2 * stages + 4) * 8 + 16 +
-                       (size_t)cp.cout_pad * 4 /*bias*/;
+    plan->smem_bytes = (size_t)stages * stage_bytes + q.bres_bytes + 1024 /*alignment slack*/ +
+                       (size_t)(2 * stages + 17) * 8 + 16 + (size_t)cp.cout_pad * 4 /*bias*/;
     // descriptors
     const uint32_t layout = swz == 128 ? 2u : swz == 64 ? 4u : 6u;  // UMMA LayoutType
     const uint32_t sbo = (uint32_t)(8 * swz) >> 4;                   // 8 rows of one swizzle span
     q.desc_hi = sbo | (1u << 14) /*descriptor version (sm_100)*/ | (layout << 29);
     q.idesc = (1u << 4) /*D = f32*/ | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) |
               ((uint32_t)(q.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    q.n_acc = 2;
+    while (q.n_acc < 8 && q.n_acc * 2 * q.BN <= 512) q.n_acc *= 2;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * q.BN)) cols <<= 1;
+    while (cols < (uint32_t)(q.n_acc * q.BN)) cols <<= 1;
     q.tmem_cols = cols;
     // epilogue
     q.cout = cp.cout; q.out_channels = cp.out_channels; q.out_coff = cp.out_coff; q.act = cp.act;
@@ -490,7 +582,7 @@ int Net::tc_prepare() {
     } else {
       const uint64_t dims[4] = {C, Wi, Hh, F};
       const uint64_t str[3] = {C * 2, Wi * C * 2, Hh * Wi * C * 2};
-      const uint32_t box[4] = {(uint32_t)q.KC, (uint32_t)q.BW, (uint32_t)q.BH, 1};
+      const uint32_t box[4] = {(uint32_t)q.KC, (uint32_t)(q.BH == 1 ? q.a_rows : q.BW), (uint32_t)q.BH, 1};
       rc = make_map(&plan->map_a, bf16, a_base, 4, dims, str, box, swz);
     }
     if (rc) { delete plan; return rc; }
@@ -505,7 +597,9 @@ int Net::tc_prepare() {
     L.tc_ok = true;
   }
   if (!attr_set) {
-    PCLS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    for (int kc = 16; kc <= 64; kc *= 2)
+      for (int sub = 1; sub <= 3; sub += 2)
+        PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(kc, sub), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_set = true;
   }
   return PCLS_OK;
@@ -518,7 +612,7 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
   const int num_tiles = prm.num_tiles * nb;
   if (num_tiles == 0) return PCLS_OK;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  conv_tc_kernel<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, prm, num_tiles);
+  tc_kernel_for(prm.KC, prm.sub)<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, prm, num_tiles);
   return check_launch("conv_tc_kernel");
 }
 

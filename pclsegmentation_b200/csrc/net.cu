@@ -616,6 +616,9 @@ extern "C" int pcls_net_set_option(pcls_net* net, const char* name, int value) {
     PCLS_REQUIRE(value >= 0, "micro_batch must be >= 0");
     n->micro_batch = value; return PCLS_OK;
   }
+  if (!strcmp(name, "tc_halo")) { tc_halo_mode = value; return PCLS_OK; }
+  if (!strcmp(name, "tc_resident")) { tc_resident_mode = value; return PCLS_OK; }
+  if (!strcmp(name, "tc_base_offset")) { tc_base_offset_mode = value; return PCLS_OK; }
   set_error("pcls_net_set_option: unknown option '%s'", name);
   return PCLS_ERR_INVALID;
 }

@@ -38,7 +38,11 @@ class TinyNet:
   def run(self, out_sym, B, x6, conv_impl):
     lib = _lib.load()
     g = self.g
-    net = g.build_net(self.logits, 2, 0, _lib.PCLS_F16, B, {"conv_impl": conv_impl, "use_graph": 0})
+    opts = {"conv_impl": conv_impl, "use_graph": 0}
+    for kv in os.environ.get("PCLS_TEST_OPTS", "").split(","):  # e.g. tc_base_offset=0 (A/B experiments)
+      if "=" in kv:
+        opts[kv.split("=")[0]] = int(kv.split("=")[1])
+    net = g.build_net(self.logits, 2, 0, _lib.PCLS_F16, B, opts)
     try:
       x = torch.from_numpy(x6).cuda()
       preds = torch.empty(x6.shape[:3], dtype=torch.int32, device="cuda")
