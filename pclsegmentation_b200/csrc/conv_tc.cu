@@ -474,7 +474,7 @@ int Net::tc_prepare() {
   const int max_smem = 227 * 1024;
   static bool attr_set = false;
   for (auto& L : convs) {
-    ConvParams& cp = L.p;
+    ConvParams& cp = L.pair_view ? L.ptc : L.p;
     L.tc_ok = false;
     if (!tc_eligible(cp)) continue;
     TcPlan* plan = new TcPlan();
@@ -528,6 +528,9 @@ int Net::tc_prepare() {
     } else if (cp.mode == MODE_3x3_S1) {
       q.n_groups = 9;
       for (int t = 0; t < 9; ++t) { q.grp_dh[0][t] = t / 3 - 1; q.grp_dw[0][t] = t % 3 - 1; q.grp_w[0][t][0] = t; }
+    } else if (cp.mode == MODE_PAIR6) {
+      q.n_groups = 6;  // pixel-pair view of the 8-channel input: pair wo holds kx = 0,1; pair wo + 1 holds kx = 2
+      for (int t = 0; t < 6; ++t) { q.grp_dh[0][t] = t / 2 - 1; q.grp_dw[0][t] = t % 2; q.grp_w[0][t][0] = t; }
     } else if (cp.mode == MODE_3x3_S2) {
       q.n_groups = 9;  // input column 2*wo + kx -> (parity kx & 1, pair wo + (kx >> 1))
       for (int t = 0; t < 9; ++t) {

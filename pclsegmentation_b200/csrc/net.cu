@@ -134,9 +134,65 @@ int Net::add_conv(const pcls_conv_desc& d) {
   L.bias_f32.assign(p.cout_pad, 0.0f);
   for (int co = 0; co < d.cout; ++co) L.bias_f32[co] = (float)bias[co];
 
+  build_pair_view(L);
   convs.push_back(std::move(L));
   ops.push_back({OP_CONV, (int)convs.size() - 1});
   return PCLS_OK;
+}
+
+// The 8-channel network input viewed as pixel pairs [B,H,W/2,16] turns the three kinds of input convolution into
+// shapes the tcgen05 kernel runs (K chunk 16):
+//   1x1 (SqueezeSegV2 conv1_skip)        -> 1x1 on pairs, block-diagonal weights, N = 2 Cout (both pixels of the pair)
+//   3x3 s1 (Darknet conv1)               -> 3x3 on pairs, N = 2 Cout; pixel 2j+p, tap kx reads pair j+dw, parity par
+//                                           with kx = 2 dw + par - p + 1
+//   3x3 s[1,2], even W (SqueezeSegV2 conv1) -> 6 taps (dh, dw in {0,1}); kx = 0,1 live in pair wo, kx = 2 in pair wo+1
+// Weights that fall outside the 3x3 support are zero; outputs are bit-identical in layout ([..,W,C] == [..,W/2,2C]).
+void Net::build_pair_view(ConvLayer& L) {
+  const ConvParams& p = L.p;
+  if (L.in != 0 || W % 2 != 0 || p.out_f32 || L.res0 >= 0 || L.res1 >= 0) return;
+  if (p.mode == MODE_3x3_S2 && p.pad_left != 0) return;
+  if (p.mode == MODE_DECONV) return;
+  const bool doubled = p.mode != MODE_3x3_S2;
+  if (doubled && (p.out_coff != 0 || p.cout != p.out_channels)) return;
+  ConvParams q = p;
+  q.Win = W / 2; q.Wout = W / 2; q.in_channels = 16; q.cin = 16; q.cin_pad = 16; q.pad_left = 0;
+  const int co_n = p.cout;
+  if (doubled) { q.cout = 2 * co_n; q.out_channels = 2 * p.out_channels; }
+  q.cout_pad = (q.cout + 15) / 16 * 16;
+  if (q.cout_pad > 256) return;
+  auto wf = [&](int tap, int co, int ci) { return L.w_f32[((size_t)tap * p.cout_pad + co) * p.cin_pad + ci]; };
+  if (p.mode == MODE_1x1) {
+    q.mode = MODE_1x1; q.ntaps = 1;
+    L.w_tc.assign((size_t)q.cout_pad * 16, 0.0f);
+    for (int px = 0; px < 2; ++px)
+      for (int co = 0; co < co_n; ++co)
+        for (int ci = 0; ci < p.cin; ++ci) L.w_tc[(size_t)(px * co_n + co) * 16 + px * 8 + ci] = wf(0, co, ci);
+  } else if (p.mode == MODE_3x3_S1) {
+    q.mode = MODE_3x3_S1; q.ntaps = 9;
+    L.w_tc.assign((size_t)9 * q.cout_pad * 16, 0.0f);
+    for (int dh = 0; dh < 3; ++dh)
+      for (int dw = -1; dw <= 1; ++dw)
+        for (int px = 0; px < 2; ++px)
+          for (int par = 0; par < 2; ++par) {
+            const int kx = 2 * dw + par - px + 1;
+            if (kx < 0 || kx > 2) continue;
+            for (int co = 0; co < co_n; ++co)
+              for (int ci = 0; ci < p.cin; ++ci)
+                L.w_tc[((size_t)(dh * 3 + dw + 1) * q.cout_pad + px * co_n + co) * 16 + par * 8 + ci] = wf(dh * 3 + kx, co, ci);
+          }
+  } else {
+    q.mode = MODE_PAIR6; q.ntaps = 6;
+    L.w_tc.assign((size_t)6 * q.cout_pad * 16, 0.0f);
+    for (int dh = 0; dh < 3; ++dh)
+      for (int kx = 0; kx < 3; ++kx)
+        for (int co = 0; co < co_n; ++co)
+          for (int ci = 0; ci < p.cin; ++ci)
+            L.w_tc[((size_t)(dh * 2 + (kx >> 1)) * q.cout_pad + co) * 16 + (kx & 1) * 8 + ci] = wf(dh * 3 + kx, co, ci);
+  }
+  L.bias_tc.assign(q.cout_pad, 0.0f);
+  for (int n = 0; n < q.cout; ++n) L.bias_tc[n] = L.bias_f32[n % co_n];
+  L.ptc = q;
+  L.pair_view = true;
 }
 
 int Net::add_pool(int in, int out) {
@@ -278,7 +334,10 @@ int Net::finalize(int logits_tensor_, int num_classes_, int none_index_) {
 
   // upload weights
   size_t wbytes = 0;
-  for (auto& L : convs) wbytes += align_up(L.w_f32.size() * 2, 256) + align_up(L.bias_f32.size() * 4, 256);
+  for (auto& L : convs) {
+    wbytes += align_up(L.w_f32.size() * 2, 256) + align_up(L.bias_f32.size() * 4, 256);
+    if (L.pair_view) wbytes += align_up(L.w_tc.size() * 2, 256) + align_up(L.bias_tc.size() * 4, 256);
+  }
   for (auto& L : cams) wbytes += align_up(L.h.size() * 4, 256);
   PCLS_CHECK_CUDA(cudaMalloc(&weights, std::max<size_t>(wbytes, 256)));
   weight_bytes = wbytes;
@@ -290,6 +349,13 @@ int Net::finalize(int logits_tensor_, int num_classes_, int none_index_) {
     L.p.w = (char*)weights + off; off += align_up(packed.size() * 2, 256);
     PCLS_CHECK_CUDA(cudaMemcpy((char*)weights + off, L.bias_f32.data(), L.bias_f32.size() * 4, cudaMemcpyHostToDevice));
     L.p.bias = (const float*)((char*)weights + off); off += align_up(L.bias_f32.size() * 4, 256);
+    if (L.pair_view) {
+      if (precision == PCLS_F16) pack_to<__half>(packed, L.w_tc); else pack_to<__nv_bfloat16>(packed, L.w_tc);
+      PCLS_CHECK_CUDA(cudaMemcpy((char*)weights + off, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
+      L.ptc.w = (char*)weights + off; off += align_up(packed.size() * 2, 256);
+      PCLS_CHECK_CUDA(cudaMemcpy((char*)weights + off, L.bias_tc.data(), L.bias_tc.size() * 4, cudaMemcpyHostToDevice));
+      L.ptc.bias = (const float*)((char*)weights + off); off += align_up(L.bias_tc.size() * 4, 256);
+    }
   }
   for (auto& L : cams) {
     PCLS_CHECK_CUDA(cudaMemcpy((char*)weights + off, L.h.data(), L.h.size() * 4, cudaMemcpyHostToDevice));
@@ -330,7 +396,15 @@ int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool ra
       p.out = (L.out == logits_tensor) ? (void*)logits_buf : tensor_ptr(L.out, nb);
       p.res0 = L.res0 >= 0 ? tensor_ptr(L.res0, nb) : nullptr;
       p.res1 = L.res1 >= 0 ? tensor_ptr(L.res1, nb) : nullptr;
-      if (conv_impl == 0 && L.tc_ok) rc = tc_launch(L, p, nb, s);
+      if (conv_impl == 0 && L.tc_ok) {
+        if (L.pair_view) {  // same buffers, pair-view geometry
+          ConvParams pv = L.ptc;
+          pv.in = p.in; pv.out = p.out; pv.res0 = nullptr; pv.res1 = nullptr;
+          rc = tc_launch(L, pv, nb, s);
+        } else {
+          rc = tc_launch(L, p, nb, s);
+        }
+      }
       else rc = launch_conv_direct<T>(p, nb, s);
     } else if (op.type == OP_POOL) {
       const PoolLayer& L = pools[op.index];

@@ -23,6 +23,13 @@ struct ConvLayer {
   std::vector<float> bias_f32;  // folded [cout_pad]
   bool tc_ok = false;
   TcPlan* tc = nullptr;
+  // Pixel-pair view for the convolutions that read the 8-channel network input (tensor-core path only):
+  // [B,H,W,8] is viewed as [B,H,W/2,16]; `ptc` / `w_tc` / `bias_tc` describe the equivalent convolution on pairs.
+  bool pair_view = false;
+  ConvParams ptc;
+  std::vector<float> w_tc, bias_tc;
+  void* w_tc_dev = nullptr;
+  float* bias_tc_dev = nullptr;
 };
 
 struct PoolLayer { int in, out, pad_left; };
@@ -72,6 +79,7 @@ struct Net {
   int add_tensor(int width, int channels, bool logits);
   size_t tensor_frame_bytes(const TensorInfo& t) const;
   int add_conv(const pcls_conv_desc& d);
+  void build_pair_view(ConvLayer& L);
   int add_pool(int in, int out);
   int add_cam(const pcls_cam_desc& d);
   void op_tensors(const OpRef& op, std::vector<int>& reads, std::vector<int>& writes) const;

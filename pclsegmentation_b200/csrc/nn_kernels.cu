@@ -251,107 +251,132 @@ template int launch_maxpool3x3_s2<__nv_bfloat16>(const __nv_bfloat16*, __nv_bflo
                                                  cudaStream_t);
 
 // --------------------------------------------------------------------------------------------------
-// CAM (nets/SqueezeSegV2.py:66-70), one kernel:
+// CAM (nets/SqueezeSegV2.py:66-70), one row-streaming kernel:
 //   pool = maxpool7x7_SAME(x); s = relu(W1^T pool + b1); e = sigmoid(W2^T s + b2); out = x * e
-// CTA tile = CAM_TH rows x CAM_TW cols x C channels.  Pass 1: horizontal 7-max from global (L1-resident
-// re-reads) into shared memory for CAM_TH+6 rows.  Pass 2: vertical 7-max from shared memory, then the two
-// tiny 1x1 convolutions: a thread owns 8 channels of a pixel, partial dot products are reduced across the
-// C/8 lanes of the pixel with xor-shuffles.
+// A CTA owns a strip of TW columns of one frame and walks down the H rows.  Each input row is staged ONCE in
+// shared memory (TW + 6 columns, double buffered, next row prefetched into registers while the current one is
+// processed); a thread owns 8 channels of one column, takes the horizontal 7-max from the staged row and keeps the
+// last seven horizontal maxima plus the last four inputs in registers, so the vertical 7-max and the gate of row
+// h - 3 need no further memory traffic.  HBM traffic: (TW + 6) / TW reads + 1 write of the tensor.
+// The two 1x1 convolutions are tiny: partial dot products per 8-channel lane, xor-shuffle reduction over the
+// C/8 lanes of a pixel.
 // --------------------------------------------------------------------------------------------------
-constexpr int CAM_TH = 8;
+template <typename T> __device__ __forceinline__ int4 neg_inf8();
+template <> __device__ __forceinline__ int4 neg_inf8<__half>() { return make_int4(0xFC00FC00, 0xFC00FC00, 0xFC00FC00, 0xFC00FC00); }
+template <> __device__ __forceinline__ int4 neg_inf8<__nv_bfloat16>() { return make_int4(0xFF80FF80, 0xFF80FF80, 0xFF80FF80, 0xFF80FF80); }
 
 template <typename T, int C>
 __global__ void __launch_bounds__(256)
-cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int H, int W, int TW) {
-  constexpr int CV = C / 8;        // 16-byte vectors per pixel (8 or 16)
-  constexpr int R = C / 16;        // reduced channels (4 or 8)
-  extern __shared__ __align__(16) unsigned char cam_smem[];
-  int4* hmax = reinterpret_cast<int4*>(cam_smem);                        // [(TH+6)][TW][CV]
-  float* w1s = reinterpret_cast<float*>(hmax + (CAM_TH + 6) * TW * CV);  // [C][R]
-  float* w2s = w1s + C * R;                                              // [R][C]
-  float* b1s = w2s + R * C;                                              // [R]
-  float* b2s = b1s + R;                                                  // [C]
-  for (int i = threadIdx.x; i < C * R; i += blockDim.x) { w1s[i] = p.w1[i]; w2s[i] = p.w2[i]; }
-  for (int i = threadIdx.x; i < R; i += blockDim.x) b1s[i] = p.b1[i];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) b2s[i] = p.b2[i];
-
-  const int w0 = blockIdx.x * TW, h0 = blockIdx.y * CAM_TH;
-  const int64_t b = blockIdx.z;
-  const int4* img = in + b * H * W * CV;
-
-  // pass 1: horizontal max over cols w-3..w+3 (clipped), rows h0-3 .. h0+TH+2
-  const int n1 = (CAM_TH + 6) * TW * CV;
-  for (int i = threadIdx.x; i < n1; i += blockDim.x) {
-    const int cv = i % CV;
-    const int c = (i / CV) % TW;
-    const int r = i / (CV * TW);
-    const int h = h0 + r - 3, w = w0 + c;
-    int4 m = make_int4(0, 0, 0, 0);
-    if (h >= 0 && h < H && w < W) {
-      const int4* row = img + (int64_t)h * W * CV + cv;
-      m = __ldg(row + (int64_t)w * CV);
-#pragma unroll
-      for (int d = -3; d <= 3; ++d) {
-        const int ww = w + d;
-        if (d != 0 && ww >= 0 && ww < W) m = max8<T>(m, __ldg(row + (int64_t)ww * CV));
-      }
-    }
-    hmax[i] = m;
+cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int H, int W) {
+  constexpr int CV = C / 8;          // 16-byte vectors per pixel (8 or 16)
+  constexpr int R = C / 16;          // reduced channels (4 or 8)
+  constexpr int TW = 256 / CV;       // columns per CTA (32 or 16)
+  constexpr int ROWV = (TW + 6) * CV;  // vectors per staged row
+  constexpr int LPT = (ROWV + 255) / 256;
+  __shared__ int4 rowbuf[2][ROWV];
+  __shared__ float w1s[C * R], w2s[R * C], b1s[R], b2s[C];
+  // bank-conflict-free layouts: the CV lanes of a pixel read consecutive words, lanes of other pixels broadcast
+  //   w1s[(k * R + j) * CV + cv] = W1[cv * 8 + k][j],  w2s[(j * 8 + k) * CV + cv] = W2[j][cv * 8 + k],  b2s[k * CV + cv]
+  for (int i = threadIdx.x; i < C * R; i += 256) {
+    { const int ch = i / R, j = i % R; w1s[((ch % 8) * R + j) * CV + ch / 8] = p.w1[i]; }
+    { const int j = i / C, ch = i % C; w2s[(j * 8 + ch % 8) * CV + ch / 8] = p.w2[i]; }
   }
-  __syncthreads();
+  for (int i = threadIdx.x; i < R; i += 256) b1s[i] = p.b1[i];
+  for (int i = threadIdx.x; i < C; i += 256) b2s[(i % 8) * CV + i / 8] = p.b2[i];
 
-  // pass 2: CV lanes per pixel
-  const int n2 = CAM_TH * TW * CV;
-  for (int i0 = 0; i0 < n2; i0 += blockDim.x) {
-    const int i = i0 + threadIdx.x;
-    const bool in_tile = i < n2;
-    const int cv = i % CV;
-    const int c = (i / CV) % TW;
-    const int r = i / (CV * TW);
-    const int h = h0 + r, w = w0 + c;
-    const bool valid = in_tile && h < H && w < W;
-    float pooled[8];
-    if (valid) {
-      int4 m = hmax[((r + 3) * TW + c) * CV + cv];
+  const int w0 = blockIdx.x * TW;
+  const int64_t b = blockIdx.y;
+  const int4* img = in + b * H * W * CV;
+  int4* oimg = out + b * H * W * CV;
+  const int cv = threadIdx.x % CV, c = threadIdx.x / CV;  // this thread's column (0..TW-1) and channel vector
+  const int4 NEG = neg_inf8<T>();
+
+  // prefetch registers for the next staged row
+  int4 pre[LPT];
+  auto fetch = [&](int r) {
 #pragma unroll
-      for (int d = -3; d <= 3; ++d) {
-        const int hh = h + d;
-        if (d != 0 && hh >= 0 && hh < H) m = max8<T>(m, hmax[((r + 3 + d) * TW + c) * CV + cv]);
+    for (int k = 0; k < LPT; ++k) {
+      const int i = threadIdx.x + k * 256;
+      pre[k] = NEG;
+      if (i < ROWV && r >= 0 && r < H) {
+        const int col = w0 - 3 + i / CV;
+        if (col >= 0 && col < W) pre[k] = __ldg(img + ((int64_t)r * W + col) * CV + (i % CV));
       }
-      unpack8<T>(m, pooled);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) pooled[k] = 0.0f;
     }
-    float sq[R];
+  };
+  auto stage = [&](int buf) {
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-      float a = 0.0f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) a = fmaf(pooled[k], w1s[(cv * 8 + k) * R + j], a);
-      sq[j] = a;
+    for (int k = 0; k < LPT; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < ROWV) rowbuf[buf][i] = pre[k];
     }
-    // reduce over the CV lanes of this pixel (CV = 8 or 16 consecutive lanes, aligned)
+  };
+
+  int4 win[7];   // horizontal maxima of the last seven input rows (oldest first)
+  int4 xr[4];    // inputs of the last four rows at this thread's pixel (oldest first)
 #pragma unroll
-    for (int off = CV / 2; off >= 1; off >>= 1)
+  for (int k = 0; k < 7; ++k) win[k] = NEG;
 #pragma unroll
-      for (int j = 0; j < R; ++j) sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], off);
+  for (int k = 0; k < 4; ++k) xr[k] = NEG;
+
+  fetch(-3 + 3);  // first staged row is input row 0 (rows -3..-1 are padding and already -inf in the window)
+  stage(0);
+  __syncthreads();
+  const bool col_ok = (w0 + c) < W;
+  for (int r = 0; r < H + 3; ++r) {          // r = newest input row in the window; output row o = r - 3
+    const int buf = r & 1;
+    if (r + 1 < H + 3) fetch(r + 1);        // rows >= H come back as -inf
+    // horizontal 7-max of row r at this column: staged columns c .. c+6 (c+3 is the centre)
+    int4 hm = rowbuf[buf][(c + 0) * CV + cv];
 #pragma unroll
-    for (int j = 0; j < R; ++j) sq[j] = fmaxf(sq[j] + b1s[j], 0.0f);
-    if (valid) {
-      const int64_t off = ((int64_t)h * W + w) * CV + cv;
-      float x[8];
-      unpack8<T>(__ldg(img + off), x);
+    for (int d = 1; d < 7; ++d) hm = max8<T>(hm, rowbuf[buf][(c + d) * CV + cv]);
+    const int4 centre = rowbuf[buf][(c + 3) * CV + cv];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float e = b2s[cv * 8 + k];
+    for (int k = 0; k < 6; ++k) win[k] = win[k + 1];
+    win[6] = hm;
 #pragma unroll
-        for (int j = 0; j < R; ++j) e = fmaf(sq[j], w2s[j * C + cv * 8 + k], e);
-        e = 1.0f / (1.0f + expf(-e));
-        x[k] *= e;
+    for (int k = 0; k < 3; ++k) xr[k] = xr[k + 1];
+    xr[3] = centre;
+    const int o = r - 3;
+    if (o >= 0) {  // uniform across the CTA
+      int4 vm = win[0];
+#pragma unroll
+      for (int k = 1; k < 7; ++k) vm = max8<T>(vm, win[k]);
+      float pooled[8];
+      unpack8<T>(vm, pooled);
+      if (!col_ok) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pooled[k] = 0.0f;
       }
-      out[b * H * W * CV + off] = pack8<T>(x);
+      float sq[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        float a = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a = fmaf(pooled[k], w1s[(k * R + j) * CV + cv], a);
+        sq[j] = a;
+      }
+#pragma unroll
+      for (int off = CV / 2; off >= 1; off >>= 1)
+#pragma unroll
+        for (int j = 0; j < R; ++j) sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], off);
+#pragma unroll
+      for (int j = 0; j < R; ++j) sq[j] = fmaxf(sq[j] + b1s[j], 0.0f);
+      if (col_ok) {
+        float x[8];
+        unpack8<T>(xr[0], x);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float e = b2s[k * CV + cv];
+#pragma unroll
+          for (int j = 0; j < R; ++j) e = fmaf(sq[j], w2s[(j * 8 + k) * CV + cv], e);
+          x[k] *= __frcp_rn(1.0f + __expf(-e));
+        }
+        oimg[((int64_t)o * W + (w0 + c)) * CV + cv] = pack8<T>(x);
+      }
     }
+    stage(buf ^ 1);
+    __syncthreads();
   }
 }
 
@@ -360,19 +385,12 @@ int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, cud
   if (B == 0) return PCLS_OK;
   PCLS_REQUIRE(p.C == 64 || p.C == 128, "CAM: channels must be 64 or 128, got %d", p.C);
   PCLS_REQUIRE(p.R == p.C / 16, "CAM: reduced channels must be C/16");
-  const int TW = 32;  // TW * CV is a multiple of the warp size, so the CV lanes of a pixel share a warp
-  const int CV = p.C / 8;
-  const size_t smem = (size_t)(CAM_TH + 6) * TW * CV * 16 + (size_t)(2 * p.C * p.R + p.R + p.C) * sizeof(float);
-  dim3 grid((unsigned)ceil_div(W, TW), (unsigned)ceil_div(H, CAM_TH), (unsigned)B);
-  if (p.C == 64) {
-    static bool attr64 = false;
-    if (!attr64) { PCLS_CHECK_CUDA(cudaFuncSetAttribute(cam_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr64 = true; }
-    cam_kernel<T, 64><<<grid, 256, smem, s>>>(reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), p, H, W, TW);
-  } else {
-    static bool attr128 = false;
-    if (!attr128) { PCLS_CHECK_CUDA(cudaFuncSetAttribute(cam_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr128 = true; }
-    cam_kernel<T, 128><<<grid, 256, smem, s>>>(reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), p, H, W, TW);
-  }
+  const int TW = 256 / (p.C / 8);
+  dim3 grid((unsigned)ceil_div(W, TW), (unsigned)B);
+  if (p.C == 64)
+    cam_kernel<T, 64><<<grid, 256, 0, s>>>(reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), p, H, W);
+  else
+    cam_kernel<T, 128><<<grid, 256, 0, s>>>(reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), p, H, W);
   return check_launch("cam_kernel");
 }
 template int launch_cam<__half>(const __half*, __half*, const CamParams&, int, int, int, cudaStream_t);

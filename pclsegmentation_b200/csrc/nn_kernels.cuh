@@ -7,7 +7,8 @@ namespace pcls {
 // Geometry of one convolution-like op as "taps": output pixel (h, wo) reads, for tap t, the input pixel
 // (h + dh[t], wo * w_mul + dw[t]) when parity[t] < 0 or parity[t] == (wo & 1); transposed convs use
 // w_shift: input column = (wo + dw[t]) >> 1.
-enum ConvMode { MODE_1x1 = 0, MODE_3x3_S1 = 1, MODE_3x3_S2 = 2, MODE_DECONV = 3 };
+enum ConvMode { MODE_1x1 = 0, MODE_3x3_S1 = 1, MODE_3x3_S2 = 2, MODE_DECONV = 3,
+                MODE_PAIR6 = 4 /* tensor-core only: 3x3 s[1,2] on the pixel-pair view, taps (dh, dw in {0,1}) */ };
 
 struct ConvParams {
   int mode;
