@@ -36,6 +36,7 @@ WORKLOADS = {
   "squeezesegv2_nuscenes_32x1024_b32": ("squeezesegv2", "squeezesegv2nuscenes", 32, 1024, 32),
 }
 DEFAULT_WORKLOAD = "squeezesegv2_kitti_64x2048_b32"
+PROJECTION_WORKLOADS = ("projection_kitti_64x2048_b64", "darknet53_projection_64x2048_b64")
 
 
 def make_config(workload):
@@ -394,13 +395,81 @@ def run_ours(args):
     dist.destroy_process_group()
 
 
+def run_projection(args):
+  """Side benchmarks (not the headline line): BASELINE config 4.
+  projection_kitti_64x2048_b64      64 raw scans (~120 k points) -> [64,64,2048,6] range images + proj_idx
+  darknet53_projection_64x2048_b64  the same projection fused with the Darknet53 forward + head (scans in, labels out)"""
+  import torch
+  from pclsegmentation_b200.laserscan import SphericalProjector
+  from pclsegmentation_b200.pipeline import ScanSegmenter
+  from pclsegmentation_b200.utils.args_loader import config_map, model_map
+  from tests.util import synth_scan
+  torch.cuda.set_device(0)
+  dev = torch.device("cuda", 0)
+  B, H, W = (args.batch or 64), 64, 2048
+  rng = np.random.default_rng(4321)
+  sizes = rng.integers(115000, 125001, B)
+  bufs = []
+  for k in range(3):  # rotate over three resident scan sets (3 x 123 MB > L2)
+    scans = np.concatenate([synth_scan(rng, int(n)) for n in sizes])
+    bufs.append(torch.from_numpy(scans).to(dev))
+  offsets = torch.as_tensor(np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)).to(dev)
+  total = int(sizes.sum())
+  fused = args.workload.startswith("darknet53")
+  if fused:
+    mc = config_map["darknet53kitti"]()
+    mc.AZIMUTH_LEVEL = W
+    model = model_map["darknet53"](mc)
+    model.randomize_batch_norm(1)
+    seg = ScanSegmenter(model, 3.0, -25.0)
+    step = lambda i: seg.segment_device(bufs[i % 3], offsets)
+  else:
+    proj = SphericalProjector(H, W, 3.0, -25.0)
+    step = lambda i: proj.project(bufs[i % 3], offsets, empty_fill=0.0)
+  for i in range(max(args.warmup, 3)):
+    step(i)
+  torch.cuda.synchronize()
+  sampler = ClockSampler(0)
+  sampler.start()
+  time.sleep(0.3)
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for i in range(args.steps):
+    step(i)
+  e1.record()
+  torch.cuda.synchronize()
+  ms = e0.elapsed_time(e1) / args.steps
+  clocks = sampler.stop()
+  peaks = measured_peaks()
+  line = {"metric": "scans/sec (%s)" % args.workload, "value": B / (ms / 1e3), "unit": "scans/s", "n_gpus": 1,
+          "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+          "scaling": "weak", "vs_baseline": None, "dtype": "f32/i32 (projection)" + (" + f16 net" if fused else ""),
+          "data": "synthetic", "config": {"workload": args.workload, "scans": B, "points": total, "H": H, "W": W},
+          "clocks": clocks}
+  if not fused:
+    alg = 16 * total + B * H * W * (24 + 4)   # SURVEY.md §8(d): 16 N read + H W (6*4 + 4) written
+    line["roofline"] = {"bound": "hbm", "achieved": alg / (ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": alg / (ms / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                        "kernel": "project_scatter + project_resolve (+ key memset)", "peak_source": peaks["source"]}
+    if not args.no_cpu_baseline:  # the oracle restatement, single thread, bounded sample
+      from oracle import projection as P
+      host = bufs[0][: int(offsets[4].item())].cpu().numpy()
+      t0 = time.perf_counter()
+      for b in range(4):
+        s = host[int(offsets[b]): int(offsets[b + 1])]
+        P.assemble_range_image(P.range_projection(s[:, :3], s[:, 3], H, W, 3.0, -25.0, "libm"))
+      line["cpu_baseline"] = {"value": 4 / (time.perf_counter() - t0), "unit": "scans/s", "cores": 1, "kind": "port",
+                              "sample": "4 scans of the same batch, numpy oracle restatement of LaserScan, 1 thread"}
+  print(json.dumps(line))
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
   ap.add_argument("--steps", type=int, default=20)
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-  ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+  ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + list(PROJECTION_WORKLOADS))
   ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch")
   ap.add_argument("--conv-impl", type=int, default=None)
   ap.add_argument("--use-graph", type=int, default=None)
@@ -409,7 +478,9 @@ def main():
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--ref-frames", type=int, default=2, help="--impl reference: frames per step (bounded sample)")
   args = ap.parse_args()
-  if args.impl == "reference":
+  if args.workload in PROJECTION_WORKLOADS:
+    run_projection(args)
+  elif args.impl == "reference":
     run_reference(args)
   else:
     run_ours(args)

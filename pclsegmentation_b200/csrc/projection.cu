@@ -24,6 +24,7 @@ struct ProjConsts {
   float fov;           // f32(|fov_down| + |fov_up|)
   float pi;            // f32(pi)
   float Wf, Hf;
+  float thr_x, thr_y;  // distance from an integer below which the float64 trig path decides the pixel
   int W, H;
 };
 
@@ -53,22 +54,34 @@ project_scatter_kernel(const float4* __restrict__ points, const int32_t* __restr
     const uint32_t local = (uint32_t)(i - __ldg(offsets + b));
 
     const float depth = point_depth(p.x, p.y, p.z);
-    // yaw = -arctan2(y, x) (:126): float64 evaluation rounded once == correctly rounded float32
-    const float yaw = -(float)atan2((double)p.y, (double)p.x);
-    // proj_x = 0.5 * (yaw / pi + 1.0); proj_x *= W (:130,:134)
+    // Column.  Reference: yaw = -arctan2(y, x); proj_x = 0.5 * (yaw / pi + 1.0); proj_x *= W; floor; clamp (:126-140).
+    // The contract is the CORRECTLY ROUNDED float32 arctan2 (float64 evaluation rounded once).  Only floor(proj_x)
+    // leaves the kernel, so the 2-ulp float32 atan2f decides it unless proj_x lands within `thr` of an integer;
+    // only those few points (< 1 %) pay for the float64 evaluation.  thr >> the propagated 2-ulp error (< 1e-3 px).
+    float yaw = -atan2f(p.y, p.x);
     float fx = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(__fdiv_rn(yaw, c.pi), 1.0f)), c.Wf);
-    fx = floorf(fx);
-    bool ok = isfinite(fx);
-    int col = (int)fmaxf(0.0f, fminf((float)(c.W - 1), fx));  // :138-140
+    float fl = floorf(fx);
+    if (!(fx - fl >= c.thr_x && fx - fl <= 1.0f - c.thr_x)) {  // near an integer, or not finite
+      yaw = -(float)atan2((double)p.y, (double)p.x);
+      fx = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(__fdiv_rn(yaw, c.pi), 1.0f)), c.Wf);
+      fl = floorf(fx);
+    }
+    bool ok = isfinite(fl);
+    int col = (int)fmaxf(0.0f, fminf((float)(c.W - 1), fl));  // :138-140
     int row;
     if (ring == nullptr) {
-      // pitch = arcsin(z / depth) (:127); proj_y = (1 - (pitch + |fov_down|) / fov) * H (:131,:135)
+      // pitch = arcsin(z / depth) (:127); proj_y = (1 - (pitch + |fov_down|) / fov) * H (:131,:135); same scheme
       const float q = __fdiv_rn(p.z, depth);
-      const float pitch = (float)asin((double)q);
+      float pitch = asinf(q);
       float fy = __fmul_rn(__fsub_rn(1.0f, __fdiv_rn(__fadd_rn(pitch, c.abs_fov_down), c.fov)), c.Hf);
-      fy = floorf(fy);
-      ok = ok && isfinite(fy);
-      row = (int)fmaxf(0.0f, fminf((float)(c.H - 1), fy));  // :143-145
+      float fly = floorf(fy);
+      if (!(fy - fly >= c.thr_y && fy - fly <= 1.0f - c.thr_y)) {
+        pitch = (float)asin((double)q);
+        fy = __fmul_rn(__fsub_rn(1.0f, __fdiv_rn(__fadd_rn(pitch, c.abs_fov_down), c.fov)), c.Hf);
+        fly = floorf(fy);
+      }
+      ok = ok && isfinite(fly);
+      row = (int)fmaxf(0.0f, fminf((float)(c.H - 1), fly));  // :143-145
     } else {
       row = (c.H - 1) - __ldg(ring + i);  // laserscan_nuscenes.py:215
       ok = ok && row >= 0 && row < c.H;
@@ -158,6 +171,9 @@ extern "C" int pcls_project_scatter(const float* points, const int32_t* ring, co
   c.fov = (float)fov;
   c.pi = (float)pi;
   c.W = W; c.H = H; c.Wf = (float)W; c.Hf = (float)H;
+  // 2-ulp atan2f/asinf (CUDA math) + four float32 roundings move proj_x by < 0.5e-6 W and proj_y by < 4e-6 H / fov
+  c.thr_x = fmaxf(4e-3f, 4e-6f * (float)W);
+  c.thr_y = fmaxf(4e-3f, 3e-5f * (float)H / (float)fov);
   project_scatter_kernel<<<grid_for(total_points, 256), 256, 0, s>>>(
       reinterpret_cast<const float4*>(points), ring, offsets, B, total_points, c,
       reinterpret_cast<unsigned long long*>(keys), proj_x, proj_y, unproj_range);
