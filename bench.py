@@ -318,7 +318,7 @@ def run_ours(args):
 
   net = model._net
   n_ops = lib.pcls_net_num_ops(net)
-  pb = min(B, 8) if not args.micro_batch else min(B, args.micro_batch)
+  pb = B if not args.micro_batch else min(B, args.micro_batch)   # profile at the benchmarked batch
   ms = (ctypes.c_float * n_ops)()
   acc = np.zeros(n_ops)
   mean_p = (ctypes.c_double * 5)(*mc.INPUT_MEAN.reshape(-1))

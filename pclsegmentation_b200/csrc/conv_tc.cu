@@ -488,7 +488,7 @@ int Net::tc_prepare() {
     q.BN = cp.cout_pad <= 256 ? cp.cout_pad : 256;
     q.n_nt = cp.cout_pad / q.BN;
     // pixel grid tiled by BW x BH = 128
-    const bool deconv = cp.mode == MODE_DECONV;
+    const bool deconv = cp.mode == MODE_DECONV;  // (two-phase form; MODE_ROW3 is the single-pass form)
     q.Hgrid = cp.H;
     q.Wgrid = deconv ? cp.Win : cp.Wout;
     q.Wout = cp.Wout;
@@ -507,7 +507,7 @@ int Net::tc_prepare() {
     q.sub = 1; q.a_rows = 128; q.ntaps_total = cp.ntaps;
     q.use_base_offset = tc_base_offset_mode;
     // halo reuse needs the three weight tiles of a row next to the A tile: only when >= 4 stages still fit
-    bool halo = cp.mode == MODE_3x3_S1 && q.BW == 128 && tc_halo_mode;
+    bool halo = (cp.mode == MODE_3x3_S1 || cp.mode == MODE_ROW3) && q.BW == 128 && tc_halo_mode;
     if (halo) {
       const int all_w_ = cp.ntaps * q.kchunks * q.BN * q.KC * 2;
       const bool resident_ = tc_resident_mode && q.n_nt == 1 && all_w_ <= 112 * 1024;
@@ -516,7 +516,7 @@ int Net::tc_prepare() {
     }
     if (cp.mode == MODE_1x1) {
       q.n_groups = 1;
-    } else if (halo) {
+    } else if (halo && cp.mode == MODE_3x3_S1) {
       // one A tile of 130 pixels (one-pixel halo each side, zero-filled by TMA at the image border) per input row
       // serves the three horizontal taps: tap dw starts (dw + 1) rows into the tile.
       q.n_groups = 3; q.sub = 3; q.a_rows = 130;
@@ -525,6 +525,13 @@ int Net::tc_prepare() {
         for (int u = 0; u < 3; ++u) q.grp_w[0][g][u] = g * 3 + u;
       }
       q.sub_row[0] = 0; q.sub_row[1] = 1; q.sub_row[2] = 2;
+    } else if (halo && cp.mode == MODE_ROW3) {
+      q.n_groups = 1; q.sub = 3; q.a_rows = 130;
+      q.grp_dh[0][0] = 0; q.grp_dw[0][0] = -1;
+      for (int u = 0; u < 3; ++u) { q.grp_w[0][0][u] = u; q.sub_row[u] = u; }
+    } else if (cp.mode == MODE_ROW3) {
+      q.n_groups = 3;
+      for (int t = 0; t < 3; ++t) { q.grp_dh[0][t] = 0; q.grp_dw[0][t] = t - 1; q.grp_w[0][t][0] = t; }
     } else if (cp.mode == MODE_3x3_S1) {
       q.n_groups = 9;
       for (int t = 0; t < 9; ++t) { q.grp_dh[0][t] = t / 3 - 1; q.grp_dw[0][t] = t % 3 - 1; q.grp_w[0][t][0] = t; }

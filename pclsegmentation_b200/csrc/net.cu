@@ -147,8 +147,35 @@ int Net::add_conv(const pcls_conv_desc& d) {
 //                                           with kx = 2 dw + par - p + 1
 //   3x3 s[1,2], even W (SqueezeSegV2 conv1) -> 6 taps (dh, dw in {0,1}); kx = 0,1 live in pair wo, kx = 2 in pair wo+1
 // Weights that fall outside the 3x3 support are zero; outputs are bit-identical in layout ([..,W,C] == [..,W/2,2C]).
+// Transposed [1,4] / stride [1,2] convolution as ONE 3-tap GEMM producing both output parities:
+//   out[2j]   = in[j] w1 + in[j-1] w3        out[2j+1] = in[j+1] w0 + in[j] w2
+// => N = 2 Cout, taps dw = -1: [w3 | 0], dw = 0: [w1 | w2], dw = +1: [0 | w0]; the output tensor [.., 2W, C]
+// (channel offset 0, C == tensor channels) is the same memory as [.., W, 2C], so stores are contiguous.
+void Net::build_deconv_row3(ConvLayer& L) {
+  const ConvParams& p = L.p;
+  if (p.mode != MODE_DECONV || p.out_f32 || p.out_coff != 0 || p.cout != p.out_channels) return;
+  if (2 * p.cout_pad > 256 || p.cout % 8 != 0) return;
+  ConvParams q = p;
+  q.mode = MODE_ROW3; q.ntaps = 3; q.Wout = p.Win;
+  q.cout = 2 * p.cout; q.cout_pad = (q.cout + 15) / 16 * 16; q.out_channels = 2 * p.out_channels;
+  q.res0_channels = 2 * p.res0_channels; q.res1_channels = 2 * p.res1_channels;
+  auto wf = [&](int tap, int co, int ci) { return L.w_f32[((size_t)tap * p.cout_pad + co) * p.cin_pad + ci]; };
+  L.w_tc.assign((size_t)3 * q.cout_pad * p.cin_pad, 0.0f);
+  auto put = [&](int t, int half, int k) {
+    for (int co = 0; co < p.cout; ++co)
+      for (int ci = 0; ci < p.cin; ++ci)
+        L.w_tc[((size_t)t * q.cout_pad + half * p.cout + co) * p.cin_pad + ci] = wf(k, co, ci);
+  };
+  put(0, 0, 3); put(1, 0, 1); put(1, 1, 2); put(2, 1, 0);
+  L.bias_tc.assign(q.cout_pad, 0.0f);
+  for (int n = 0; n < q.cout; ++n) L.bias_tc[n] = L.bias_f32[n % p.cout];
+  L.ptc = q;
+  L.pair_view = true;
+}
+
 void Net::build_pair_view(ConvLayer& L) {
   const ConvParams& p = L.p;
+  if (p.mode == MODE_DECONV) { build_deconv_row3(L); return; }
   if (L.in != 0 || W % 2 != 0 || p.out_f32 || L.res0 >= 0 || L.res1 >= 0) return;
   if (p.mode == MODE_3x3_S2 && p.pad_left != 0) return;
   if (p.mode == MODE_DECONV) return;
@@ -397,9 +424,9 @@ int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool ra
       p.res0 = L.res0 >= 0 ? tensor_ptr(L.res0, nb) : nullptr;
       p.res1 = L.res1 >= 0 ? tensor_ptr(L.res1, nb) : nullptr;
       if (conv_impl == 0 && L.tc_ok) {
-        if (L.pair_view) {  // same buffers, pair-view geometry
+        if (L.pair_view) {  // same buffers, re-viewed geometry
           ConvParams pv = L.ptc;
-          pv.in = p.in; pv.out = p.out; pv.res0 = nullptr; pv.res1 = nullptr;
+          pv.in = p.in; pv.out = p.out; pv.res0 = p.res0; pv.res1 = p.res1;
           rc = tc_launch(L, pv, nb, s);
         } else {
           rc = tc_launch(L, p, nb, s);

@@ -80,6 +80,7 @@ struct Net {
   size_t tensor_frame_bytes(const TensorInfo& t) const;
   int add_conv(const pcls_conv_desc& d);
   void build_pair_view(ConvLayer& L);
+  void build_deconv_row3(ConvLayer& L);
   int add_pool(int in, int out);
   int add_cam(const pcls_cam_desc& d);
   void op_tensors(const OpRef& op, std::vector<int>& reads, std::vector<int>& writes) const;

@@ -8,7 +8,9 @@ namespace pcls {
 // (h + dh[t], wo * w_mul + dw[t]) when parity[t] < 0 or parity[t] == (wo & 1); transposed convs use
 // w_shift: input column = (wo + dw[t]) >> 1.
 enum ConvMode { MODE_1x1 = 0, MODE_3x3_S1 = 1, MODE_3x3_S2 = 2, MODE_DECONV = 3,
-                MODE_PAIR6 = 4 /* tensor-core only: 3x3 s[1,2] on the pixel-pair view, taps (dh, dw in {0,1}) */ };
+                MODE_PAIR6 = 4 /* tensor-core only: 3x3 s[1,2] on the pixel-pair view, taps (dh, dw in {0,1}) */,
+                MODE_ROW3 = 5 /* tensor-core only: 1x3 conv (taps dw = -1,0,+1); the transposed conv with both output
+                                 parities as N = 2 Cout */ };
 
 struct ConvParams {
   int mode;
