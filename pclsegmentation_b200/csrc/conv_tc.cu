@@ -72,6 +72,21 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void group_barrier(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const int4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -130,6 +145,8 @@ struct TcParams {
   uint32_t idesc, desc_hi;    // instruction descriptor; high 32 bits of the smem matrix descriptors
   uint32_t tmem_cols;
   int n_acc;                  // TMEM accumulator buffers (power of two, n_acc * BN <= 512)
+  // TMA-store epilogue: output staged in smem in blocks of `cbw` channels (128 rows x cbw), two buffers per group
+  int tma_store, cbw, c_is_5d, c_stage_bytes;
   // epilogue
   int cout, out_channels, out_coff, act, out_f32, is_bf16;
   void* out;
@@ -178,6 +195,35 @@ __device__ __forceinline__ void epilogue_store32(const TcParams& p, const uint32
   }
 }
 
+// 32 accumulator columns of one pixel row -> +bias, activation, +residuals -> four 16-byte chunks of the staged tile
+template <typename T>
+__device__ __forceinline__ void epilogue_stage32(const TcParams& p, const uint32_t (&acc)[32], const float* bias_s,
+                                                 int n_base, int ngroups, const int4 (&r0)[4], const int4 (&r1)[4],
+                                                 uint32_t row_addr, int chunk0, int row, bool swizzled) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (g >= ngroups) break;
+    const int co = n_base + g * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[g * 8 + j]) + bias_s[co + j], p.act);
+    if (p.res0) {
+      float f[8];
+      unpack8<T>(r0[g], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += f[j];
+    }
+    if (p.res1) {
+      float f[8];
+      unpack8<T>(r1[g], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += f[j];
+    }
+    const int chunk = chunk0 + g;
+    st_shared_v4(row_addr + (uint32_t)((swizzled ? (chunk ^ (row & 7)) : chunk) << 4), pack8<T>(v));
+  }
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -193,7 +239,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 template <int KC, int SUB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ TcParams p, const int num_tiles) {
+               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ TcParams p, const int num_tiles) {
   extern __shared__ uint8_t smem_raw[];
   // carve: [stages x (A tile | B tiles)] 1024-aligned, resident weights, barriers, TMEM base slot, bias
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -203,7 +249,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t b_stage_bytes = b_resident ? 0u : (uint32_t)SUB * b_tile_bytes;
   const uint32_t stage_bytes = a_bytes + b_stage_bytes;
   const uint32_t bres_base = smem_base + (uint32_t)S * stage_bytes;   // resident weights (1024-aligned)
-  const uint32_t bar_base = bres_base + (uint32_t)p.bres_bytes;
+  const uint32_t cstage_base = bres_base + (uint32_t)p.bres_bytes;  // output staging: [group][2] x c_stage_bytes
+  const uint32_t bar_base = cstage_base + (p.tma_store ? 4u * (uint32_t)p.c_stage_bytes : 0u);
 #define FULL_BAR(s) (bar_base + 8u * (uint32_t)(s))
 #define EMPTY_BAR(s) (bar_base + 8u * (uint32_t)(S + (s)))
 #define TFULL_BAR(a) (bar_base + 8u * (uint32_t)(2 * S + (a)))
@@ -220,6 +267,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     for (int s = 0; s < S; ++s) { mbar_init(FULL_BAR(s), 1); mbar_init(EMPTY_BAR(s), 1); }
     for (int a = 0; a < 8; ++a) { mbar_init(TFULL_BAR(a), 1); mbar_init(TEMPTY_BAR(a), 4); }
     mbar_init(BRES_BAR, 1);
@@ -343,7 +391,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const bool has_res = (p.res0 != nullptr) || (p.res1 != nullptr);
     const uint32_t n_acc = (uint32_t)p.n_acc;
     const int BW = p.BW, BH = p.BH, Hgrid = p.Hgrid, Wgrid = p.Wgrid, Wout = p.Wout, out_wmul = p.out_wmul;
-    uint32_t tl = 0;
+    uint32_t tl = 0, blk = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       if ((int)(tl & 1u) != grp) continue;
       int r = tile;
@@ -374,6 +422,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (has_res) load_res(0);
       mbar_wait(TFULL_BAR(acc), acc_parity);
       tc_fence_after();
+      if (p.tma_store) {
+        // ---- TMEM -> registers -> swizzled smem tile -> TMA bulk tensor store (full lines, edges clipped by TMA) ----
+        const int cbw = p.cbw;
+        const bool swz = cbw == 64;
+        const bool issuer = (q == 2) && lane == 0;            // first warp of the group (warp 2 or 6)
+        const int bar_id = 1 + grp;
+        for (int cb = 0; cb < BN; cb += cbw, ++blk) {
+          const uint32_t buf = cstage_base + (uint32_t)((grp * 2 + (int)(blk & 1u)) * p.c_stage_bytes);
+          const uint32_t row_addr = buf + (uint32_t)(m * cbw * 2);
+          for (int c = 0; c < cbw; c += 32) {
+            uint32_t v[32];
+            const int ng = (cbw - c) >= 32 ? 4 : 2;
+            if (ng == 4) {
+              tmem_ld32(t_row + (uint32_t)(cb + c), v);
+            } else {
+              uint32_t v16[16];
+              tmem_ld16(t_row + (uint32_t)(cb + c), v16);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0u; }
+            }
+            tmem_ld_wait();
+            if (p.is_bf16) epilogue_stage32<__nv_bfloat16>(p, v, bias_s, n0 + cb + c, ng, r0, r1, row_addr, c >> 3, m, swz);
+            else epilogue_stage32<__half>(p, v, bias_s, n0 + cb + c, ng, r0, r1, row_addr, c >> 3, m, swz);
+            if (has_res && cb + c + 32 < BN) load_res(cb + c + 32);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> visible to the TMA engine
+          if (issuer) bulk_wait_read0();   // the previous store of this group has finished reading the OTHER buffer
+          group_barrier(bar_id);
+          if (issuer) {
+            const int c0 = p.out_coff + n0 + cb;
+            if (p.c_is_5d) tma_store_5d(&map_c, buf, c0, ph, wt * BW, ht * BH, b);
+            else tma_store_4d(&map_c, buf, c0, wt * BW, ht * BH, b);
+            bulk_commit();
+          }
+        }
+      } else
       for (int c = 0; c < BN; c += 32) {
         uint32_t v[32];
         if (c + 32 <= BN) {
@@ -393,6 +477,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(TEMPTY_BAR(acc));
     }
+    if (p.tma_store && q == 2 && lane == 0) bulk_wait_all();  // smem must outlive the last stores
   }
 
   // teardown
@@ -410,7 +495,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #undef BRES_BAR
 }
 
-typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const TcParams, const int);
+typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const int);
 static TcKernelFn tc_kernel_for(int KC, int SUB) {
   if (SUB == 3) return KC == 64 ? conv_tc_kernel<64, 3> : KC == 32 ? conv_tc_kernel<32, 3> : conv_tc_kernel<16, 3>;
   return KC == 64 ? conv_tc_kernel<64, 1> : KC == 32 ? conv_tc_kernel<32, 1> : conv_tc_kernel<16, 1>;
@@ -420,7 +505,7 @@ static TcKernelFn tc_kernel_for(int KC, int SUB) {
 // host side: plans (tensor maps, tile geometry) and launch
 // ---------------------------------------------------------------------------------------------------------------
 struct TcPlan {
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_c;
   TcParams prm;
   size_t smem_bytes;
 };
@@ -450,7 +535,8 @@ static int make_map(CUtensorMap* map, bool bf16, void* base, int rank, const uin
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                              : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+                              : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                              : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base,
                   gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -459,6 +545,7 @@ static int make_map(CUtensorMap* map, bool bf16, void* base, int rank, const uin
 }
 
 // A/B switches for measurement (pcls_net_set_option before finalize): halo reuse, resident weights, base offset
+int tc_tma_store_mode = 1;
 int tc_halo_mode = 1, tc_resident_mode = 1, tc_base_offset_mode = 0;  // measured: UMMA swizzles on absolute smem address bits, a row-shifted start needs NO base offset
 
 // Which layers run on tensor cores: the input tensor must carry >= 16 real channels (the 6-channel network input
@@ -512,7 +599,7 @@ int Net::tc_prepare() {
       const int all_w_ = cp.ntaps * q.kchunks * q.BN * q.KC * 2;
       const bool resident_ = tc_resident_mode && q.n_nt == 1 && all_w_ <= 112 * 1024;
       const int st_ = (130 * q.KC * 2 + 1023) / 1024 * 1024 + (resident_ ? 0 : 3 * q.BN * q.KC * 2);
-      if ((max_smem - 2048 - cp.cout_pad * 4 - (resident_ ? all_w_ + 1024 : 0)) / st_ < 4) halo = false;
+      if ((max_smem - 2048 - 65536 - cp.cout_pad * 4 - (resident_ ? all_w_ + 1024 : 0)) / st_ < 4) halo = false;
     }
     if (cp.mode == MODE_1x1) {
       q.n_groups = 1;
@@ -550,6 +637,16 @@ int Net::tc_prepare() {
       q.grp_dw[1][0] = 1;  q.grp_w[1][0][0] = 0;
       q.grp_dw[1][1] = 0;  q.grp_w[1][1][0] = 2;
     }
+    // TMA-store epilogue: 16-bit outputs whose N tile splits into blocks of <= 64 channels
+    q.tma_store = 0; q.cbw = 0; q.c_stage_bytes = 0; q.c_is_5d = deconv ? 1 : 0;
+    // (measured: for N tiles narrower than 64 channels the direct 16-byte stores are faster than staging)
+    if (tc_tma_store_mode && !cp.out_f32 && cp.cout == cp.cout_pad && (q.BN % 64 == 0 || tc_tma_store_mode > 1) &&
+        (cp.out_channels * 2) % 16 == 0) {
+      q.tma_store = 1;
+      q.cbw = q.BN < 64 ? q.BN : 64;
+      q.c_stage_bytes = (128 * q.cbw * 2 + 1023) / 1024 * 1024;
+    }
+    const int cstage_total = q.tma_store ? 4 * q.c_stage_bytes : 0;
     // pipeline depth; weights stay resident in smem when the whole layer fits next to >= 4 stages
     q.a_bytes = (q.a_rows * q.KC * 2 + 1023) / 1024 * 1024;
     q.b_tile_bytes = q.BN * q.KC * 2;
@@ -557,11 +654,11 @@ int Net::tc_prepare() {
     q.b_resident = (tc_resident_mode && q.n_nt == 1 && all_w <= 112 * 1024) ? 1 : 0;
     q.bres_bytes = q.b_resident ? (all_w + 1023) / 1024 * 1024 : 0;
     const int stage_bytes = q.a_bytes + (q.b_resident ? 0 : q.sub * q.b_tile_bytes);
-    int stages = (max_smem - 2048 - cp.cout_pad * 4 - q.bres_bytes) / stage_bytes;
+    int stages = (max_smem - 2048 - cp.cout_pad * 4 - q.bres_bytes - cstage_total) / stage_bytes;
     if (stages > 12) stages = 12;
     if (stages < 2) { delete plan; continue; }
     q.stages = stages;
-    plan->smem_bytes = (size_t)stages * stage_bytes + q.bres_bytes + 1024 /*alignment slack*/ +
+    plan->smem_bytes = (size_t)stages * stage_bytes + q.bres_bytes + cstage_total + 1024 /*alignment slack*/ +
                        (size_t)(2 * stages + 17) * 8 + 16 + (size_t)cp.cout_pad * 4 /*bias*/;
     // descriptors
     const uint32_t layout = swz == 128 ? 2u : swz == 64 ? 4u : 6u;  // UMMA LayoutType
@@ -603,6 +700,25 @@ int Net::tc_prepare() {
       rc = make_map(&plan->map_b, bf16, const_cast<void*>(cp.w), 3, dims, str, box, swz);
     }
     if (rc) { delete plan; return rc; }
+    if (q.tma_store) {  // C: the output tensor (or its re-viewed form) inside the arena
+      char* c_base = (char*)tensor_ptr(L.out, frames_per_pass);
+      const uint64_t Co = (uint64_t)cp.out_channels, Wo = (uint64_t)cp.Wout;
+      const int csw = q.cbw == 64 ? 128 : 0;
+      if (q.c_is_5d) {  // two-phase transposed conv: phase = output column parity
+        const uint64_t dims[5] = {Co, 2, Wo / 2, Hh, F};
+        const uint64_t str[4] = {Co * 2, Co * 4, Wo * Co * 2, Hh * Wo * Co * 2};
+        const uint32_t box[5] = {(uint32_t)q.cbw, 1, (uint32_t)q.BW, (uint32_t)q.BH, 1};
+        rc = make_map(&plan->map_c, bf16, c_base, 5, dims, str, box, csw);
+      } else {
+        const uint64_t dims[4] = {Co, Wo, Hh, F};
+        const uint64_t str[3] = {Co * 2, Wo * Co * 2, Hh * Wo * Co * 2};
+        const uint32_t box[4] = {(uint32_t)q.cbw, (uint32_t)q.BW, (uint32_t)q.BH, 1};
+        rc = make_map(&plan->map_c, bf16, c_base, 4, dims, str, box, csw);
+      }
+      if (rc) { delete plan; return rc; }
+    } else {
+      plan->map_c = plan->map_a;  // unused
+    }
     L.tc = plan;
     L.tc_ok = true;
   }
@@ -622,7 +738,7 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
   const int num_tiles = prm.num_tiles * nb;
   if (num_tiles == 0) return PCLS_OK;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  tc_kernel_for(prm.KC, prm.sub)<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, prm, num_tiles);
+  tc_kernel_for(prm.KC, prm.sub)<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, prm, num_tiles);
   return check_launch("conv_tc_kernel");
 }
 

@@ -718,6 +718,7 @@ extern "C" int pcls_net_set_option(pcls_net* net, const char* name, int value) {
     n->micro_batch = value; return PCLS_OK;
   }
   if (!strcmp(name, "tc_halo")) { tc_halo_mode = value; return PCLS_OK; }
+  if (!strcmp(name, "tc_tma_store")) { tc_tma_store_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_resident")) { tc_resident_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_base_offset")) { tc_base_offset_mode = value; return PCLS_OK; }
   set_error("pcls_net_set_option: unknown option '%s'", name);
