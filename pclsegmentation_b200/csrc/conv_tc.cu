@@ -147,6 +147,10 @@ struct TcParams {
   int n_acc;                  // TMEM accumulator buffers (power of two, n_acc * BN <= 512)
   // TMA-store epilogue: output staged in smem in blocks of `cbw` channels (128 rows x cbw), two buffers per group
   int tma_store, cbw, c_is_5d, c_stage_bytes;
+  // pixel-group view (G > 1): an A row holds G adjacent pixels x Cin channels; accumulator columns [p*cout_blk, ..) belong
+  // to pixel p of the group.  cout_blk = 1 << 30 when G == 1.
+  int G, cout_blk;
+  uint32_t desc_hi_b, idesc_blk;
   // epilogue
   int cout, out_channels, out_coff, act, out_f32, is_bf16;
   void* out;
@@ -162,6 +166,31 @@ __device__ __forceinline__ void epilogue_store32(const TcParams& p, const uint32
                                                  int n_base, int64_t pix, bool valid, const int4 (&r0)[4],
                                                  const int4 (&r1)[4]) {
   if (!valid) return;
+  if (p.G > 1) {  // pixel-group view: column n -> pixel n / cout_blk of the group, channel n % cout_blk
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int n = n_base + g * 8;
+      const int pp = n / p.cout_blk, co = n - pp * p.cout_blk;
+      if (co + 8 > p.cout) continue;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[g * 8 + j]) + bias_s[n + j], p.act);
+      if (p.res0) {
+        float f[8];
+        unpack8<T>(r0[g], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += f[j];
+      }
+      if (p.res1) {
+        float f[8];
+        unpack8<T>(r1[g], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += f[j];
+      }
+      *reinterpret_cast<int4*>(reinterpret_cast<T*>(p.out) + (pix + pp) * p.out_channels + p.out_coff + co) = pack8<T>(v);
+    }
+    return;
+  }
   if (p.out_f32) {
     float* o = reinterpret_cast<float*>(p.out) + pix * p.out_channels + p.out_coff;
 #pragma unroll
@@ -236,7 +265,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
-template <int KC, int SUB>
+template <int KC, int SUB, int G>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ TcParams p, const int num_tiles) {
@@ -260,7 +289,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* bias_s = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16u - smem_u32(smem_raw)));  // [n_nt * BN]
-  for (int i = threadIdx.x; i < p.n_nt * p.BN; i += blockDim.x) bias_s[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.n_nt * p.BN; i += blockDim.x) bias_s[i] = p.bias[G > 1 ? i % p.cout_blk : i];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -360,19 +389,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(FULL_BAR(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
-          uint32_t b_addr = b_resident ? b_res : a_addr + a_bytes;
+          if constexpr (G == 1) {
+            uint32_t b_addr = b_resident ? b_res : a_addr + a_bytes;
 #pragma unroll
-          for (int u = 0; u < SUB; ++u) {
-            // descriptors: start address (>>4) | LBO = 1 in the low word; SBO / version / swizzle mode in the high word.
-            // A row-shifted start (halo taps) needs no base offset: the swizzle is a function of absolute smem address bits.
-            const uint64_t a_desc = ((uint64_t)desc_hi << 32) | (uint64_t)((((a_addr + sub_off[u]) >> 4) & 0x3FFFu) | 0x10000u);
-            const uint64_t b_desc = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_addr >> 4) & 0x3FFFu) | 0x10000u);
+            for (int u = 0; u < SUB; ++u) {
+              // descriptors: start address (>>4) | LBO = 1 in the low word; SBO / version / swizzle mode in the high word.
+              // A row-shifted start (halo taps) needs no base offset: the swizzle is a function of absolute smem address bits.
+              const uint64_t a_desc = ((uint64_t)desc_hi << 32) | (uint64_t)((((a_addr + sub_off[u]) >> 4) & 0x3FFFu) | 0x10000u);
+              const uint64_t b_desc = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_addr >> 4) & 0x3FFFu) | 0x10000u);
 #pragma unroll
-            for (int j = 0; j < KC / 16; ++j) {  // +32 bytes along K inside the swizzle atom per UMMA_K = 16
-              umma_f16(d_tmem, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j), idesc, accumulate);
-              accumulate = 1u;
+              for (int j = 0; j < KC / 16; ++j) {  // +32 bytes along K inside the swizzle atom per UMMA_K = 16
+                umma_f16(d_tmem, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j), idesc, accumulate);
+                accumulate = 1u;
+              }
+              b_addr += b_tile_bytes;
             }
-            b_addr += b_tile_bytes;
+          } else {
+            // pixel-group view, banded issue: output pixel p of the group and horizontal tap u read input pixel
+            // t = p + u - 1, i.e. group dq = floor(t / G) (row offset dq + 1 in the halo tile) and K offset (t mod G) * Cin;
+            // the product lands in accumulator columns [p * cout_blk, ..).  One small MMA per (p, u, 16 channels).
+            constexpr int CIN = KC / G;
+            const uint32_t desc_hi_b = p.desc_hi_b, idesc_blk = p.idesc_blk, cout_blk = (uint32_t)p.cout_blk;
+#pragma unroll
+            for (int u = 0; u < SUB; ++u) {
+              const uint32_t b_addr = b_res + (uint32_t)u * b_tile_bytes;
+              const uint64_t b_desc = ((uint64_t)desc_hi_b << 32) | (uint64_t)(((b_addr >> 4) & 0x3FFFu) | 0x10000u);
+#pragma unroll
+              for (int pp = 0; pp < G; ++pp) {
+                constexpr int dummy = 0; (void)dummy;
+                const int t = pp + (SUB == 3 ? u - 1 : 0);
+                const int dq = t < 0 ? -1 : (t >= G ? 1 : 0);
+                const int par = t - dq * G;
+                const uint32_t a_start = a_addr + (uint32_t)((SUB == 3 ? dq + 1 : 0) * KC * 2 + par * CIN * 2);
+                const uint64_t a_desc = ((uint64_t)desc_hi << 32) | (uint64_t)(((a_start >> 4) & 0x3FFFu) | 0x10000u);
+#pragma unroll
+                for (int j = 0; j < CIN / 16; ++j)
+                  umma_f16(d_tmem + (uint32_t)pp * cout_blk, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j),
+                           idesc_blk, (k | u | j) != 0 ? 1u : 0u);
+              }
+            }
           }
           b_res += (uint32_t)SUB * b_tile_bytes;
           umma_commit(EMPTY_BAR(stage));  // smem slot free once these MMAs have read it
@@ -388,7 +443,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;
     const int ml_h = m >> p.bw_shift, ml_w = m & (p.BW - 1);
-    const bool has_res = (p.res0 != nullptr) || (p.res1 != nullptr);
     const uint32_t n_acc = (uint32_t)p.n_acc;
     const int BW = p.BW, BH = p.BH, Hgrid = p.Hgrid, Wgrid = p.Wgrid, Wout = p.Wout, out_wmul = p.out_wmul;
     uint32_t tl = 0, blk = 0;
@@ -407,16 +461,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int n0 = nt * BN;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)BN;
       // residual rows are prefetched BEFORE waiting for the accumulator, so their DRAM latency overlaps the MMAs
+      // residual rows of the first 32 columns are prefetched BEFORE waiting for the accumulator (their DRAM latency
+      // overlaps the MMAs of this tile); later chunks are fetched one chunk ahead
       int4 r0[4], r1[4];
+      const bool has_res = (p.res0 != nullptr) || (p.res1 != nullptr);
       auto load_res = [&](int c) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const int co = n0 + c + g * 8;
+          const int n = n0 + c + g * 8;
+          const int pp = G > 1 ? n / p.cout_blk : 0;
+          const int co = n - pp * (G > 1 ? p.cout_blk : 0);
           const bool okc = valid && (co + 8 <= p.cout);
           r0[g] = (p.res0 && okc) ? __ldg(reinterpret_cast<const int4*>(
-                      reinterpret_cast<const uint16_t*>(p.res0) + pix * p.res0_channels + p.out_coff + co)) : make_int4(0, 0, 0, 0);
+                      reinterpret_cast<const uint16_t*>(p.res0) + (pix + pp) * p.res0_channels + p.out_coff + co)) : make_int4(0, 0, 0, 0);
           r1[g] = (p.res1 && okc) ? __ldg(reinterpret_cast<const int4*>(
-                      reinterpret_cast<const uint16_t*>(p.res1) + pix * p.res1_channels + p.out_coff + co)) : make_int4(0, 0, 0, 0);
+                      reinterpret_cast<const uint16_t*>(p.res1) + (pix + pp) * p.res1_channels + p.out_coff + co)) : make_int4(0, 0, 0, 0);
         }
       };
       if (has_res) load_res(0);
@@ -424,54 +483,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       if (p.tma_store) {
         // ---- TMEM -> registers -> swizzled smem tile -> TMA bulk tensor store (full lines, edges clipped by TMA) ----
-        const int cbw = p.cbw;
-        const bool swz = cbw == 64;
+        // blocks of 64 channels (128-byte rows, SWIZZLE_128B)
         const bool issuer = (q == 2) && lane == 0;            // first warp of the group (warp 2 or 6)
         const int bar_id = 1 + grp;
-        for (int cb = 0; cb < BN; cb += cbw, ++blk) {
+        for (int cb = 0; cb < BN; cb += 64, ++blk) {
           const uint32_t buf = cstage_base + (uint32_t)((grp * 2 + (int)(blk & 1u)) * p.c_stage_bytes);
-          const uint32_t row_addr = buf + (uint32_t)(m * cbw * 2);
-          for (int c = 0; c < cbw; c += 32) {
-            uint32_t v[32];
-            const int ng = (cbw - c) >= 32 ? 4 : 2;
-            if (ng == 4) {
-              tmem_ld32(t_row + (uint32_t)(cb + c), v);
-            } else {
-              uint32_t v16[16];
-              tmem_ld16(t_row + (uint32_t)(cb + c), v16);
+          const uint32_t row_addr = buf + (uint32_t)(m * 128);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0u; }
-            }
+          for (int ci = 0; ci < 2; ++ci) {
+            const int cc = cb + ci * 32;
+            uint32_t v[32];
+            tmem_ld32(t_row + (uint32_t)cc, v);
             tmem_ld_wait();
-            if (p.is_bf16) epilogue_stage32<__nv_bfloat16>(p, v, bias_s, n0 + cb + c, ng, r0, r1, row_addr, c >> 3, m, swz);
-            else epilogue_stage32<__half>(p, v, bias_s, n0 + cb + c, ng, r0, r1, row_addr, c >> 3, m, swz);
-            if (has_res && cb + c + 32 < BN) load_res(cb + c + 32);
+            if (p.is_bf16) epilogue_stage32<__nv_bfloat16>(p, v, bias_s, n0 + cc, 4, r0, r1, row_addr, ci * 4, m, true);
+            else epilogue_stage32<__half>(p, v, bias_s, n0 + cc, 4, r0, r1, row_addr, ci * 4, m, true);
+            if (has_res && cc + 32 < BN) load_res(cc + 32);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> visible to the TMA engine
           if (issuer) bulk_wait_read0();   // the previous store of this group has finished reading the OTHER buffer
           group_barrier(bar_id);
           if (issuer) {
-            const int c0 = p.out_coff + n0 + cb;
-            if (p.c_is_5d) tma_store_5d(&map_c, buf, c0, ph, wt * BW, ht * BH, b);
+            const int pp = G > 1 ? (n0 + cb) / p.cout_blk : 0;
+            const int c0 = p.out_coff + n0 + cb - pp * (G > 1 ? p.cout_blk : 0);
+            if (p.c_is_5d) tma_store_5d(&map_c, buf, c0, G > 1 ? pp : ph, wt * BW, ht * BH, b);
             else tma_store_4d(&map_c, buf, c0, wt * BW, ht * BH, b);
             bulk_commit();
           }
         }
-      } else
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        if (c + 32 <= BN) {
-          tmem_ld32(t_row + (uint32_t)c, v);
-        } else {  // BN % 32 == 16 tail
-          uint32_t v16[16];
-          tmem_ld16(t_row + (uint32_t)c, v16);
+      } else {
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          if (c + 32 <= BN) {
+            tmem_ld32(t_row + (uint32_t)c, v);
+          } else {  // BN % 32 == 16 tail
+            uint32_t v16[16];
+            tmem_ld16(t_row + (uint32_t)c, v16);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0u; }
+            for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0u; }
+          }
+          tmem_ld_wait();
+          if (p.is_bf16) epilogue_store32<__nv_bfloat16>(p, v, bias_s, n0 + c, pix, valid, r0, r1);
+          else epilogue_store32<__half>(p, v, bias_s, n0 + c, pix, valid, r0, r1);
+          if (has_res && c + 32 < BN) load_res(c + 32);
         }
-        tmem_ld_wait();
-        if (p.is_bf16) epilogue_store32<__nv_bfloat16>(p, v, bias_s, n0 + c, pix, valid, r0, r1);
-        else epilogue_store32<__half>(p, v, bias_s, n0 + c, pix, valid, r0, r1);
-        if (has_res && c + 32 < BN) load_res(c + 32);
       }
       tc_fence_before();
       __syncwarp();
@@ -496,14 +550,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const int);
-static TcKernelFn tc_kernel_for(int KC, int SUB) {
-  if (SUB == 3) return KC == 64 ? conv_tc_kernel<64, 3> : KC == 32 ? conv_tc_kernel<32, 3> : conv_tc_kernel<16, 3>;
-  return KC == 64 ? conv_tc_kernel<64, 1> : KC == 32 ? conv_tc_kernel<32, 1> : conv_tc_kernel<16, 1>;
+static TcKernelFn tc_kernel_for(int KC, int SUB, int G) {
+  if (G == 4) return SUB == 3 ? conv_tc_kernel<64, 3, 4> : conv_tc_kernel<64, 1, 4>;
+  if (G == 2) {
+    if (KC == 64) return SUB == 3 ? conv_tc_kernel<64, 3, 2> : conv_tc_kernel<64, 1, 2>;
+    return SUB == 3 ? conv_tc_kernel<32, 3, 2> : conv_tc_kernel<32, 1, 2>;
+  }
+  if (SUB == 3) return KC == 64 ? conv_tc_kernel<64, 3, 1> : KC == 32 ? conv_tc_kernel<32, 3, 1> : conv_tc_kernel<16, 3, 1>;
+  return KC == 64 ? conv_tc_kernel<64, 1, 1> : KC == 32 ? conv_tc_kernel<32, 1, 1> : conv_tc_kernel<16, 1, 1>;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// host side: plans (tensor maps, tile geometry) and launch
-// ---------------------------------------------------------------------------------------------------------------
 struct TcPlan {
   CUtensorMap map_a, map_b, map_c;
   TcParams prm;
@@ -545,7 +601,7 @@ static int make_map(CUtensorMap* map, bool bf16, void* base, int rank, const uin
 }
 
 // A/B switches for measurement (pcls_net_set_option before finalize): halo reuse, resident weights, base offset
-int tc_tma_store_mode = 1;
+int tc_tma_store_mode = 1, tc_group_mode = 1;
 int tc_halo_mode = 1, tc_resident_mode = 1, tc_base_offset_mode = 0;  // measured: UMMA swizzles on absolute smem address bits, a row-shifted start needs NO base offset
 
 // Which layers run on tensor cores: the input tensor must carry >= 16 real channels (the 6-channel network input
@@ -570,16 +626,30 @@ int Net::tc_prepare() {
     const bool bf16 = precision == PCLS_BF16;
     // K chunk / swizzle: the widest of 64/32/16 channels that divides cin_pad
     q.KC = (cp.cin_pad % 64 == 0) ? 64 : (cp.cin_pad % 32 == 0) ? 32 : 16;
-    const int swz = q.KC * 2;
     q.kchunks = cp.cin_pad / q.KC;
     q.BN = cp.cout_pad <= 256 ? cp.cout_pad : 256;
     q.n_nt = cp.cout_pad / q.BN;
+    // Pixel-group view for narrow inputs (Cin = 16 / 32): TMA moves about one box row per ~8 cycles whatever its
+    // width, so G adjacent pixels are viewed as ONE row of G*Cin channels (<= 128 bytes) and the MMAs are issued
+    // banded (kernel comment).  Needs the whole tensor row to be contiguous (Cin == tensor channels).
+    int G = 1;
+    if (tc_group_mode && tc_resident_mode && (cp.mode == MODE_1x1 || cp.mode == MODE_3x3_S1 || cp.mode == MODE_ROW3) &&
+        (cp.cin_pad == 16 || cp.cin_pad == 32) && cp.in_channels == cp.cin_pad && cp.cout == cp.cout_pad && !cp.out_f32 &&
+        cp.Wout == cp.Win) {
+      for (int g = 64 / cp.cin_pad; g >= 2; g /= 2)
+        if (cp.Win % g == 0 && cp.Win / g >= 128 && g * cp.cout_pad <= 256) { G = g; break; }
+    }
+    const int cin_blk = cp.cin_pad;
+    q.G = G; q.cout_blk = G > 1 ? cp.cout_pad : (1 << 30);
+    if (G > 1) { q.KC = G * cin_blk; q.kchunks = 1; q.BN = G * cp.cout_pad; q.n_nt = 1; }
+    const int swz = q.KC * 2;
+    const int swz_b = G > 1 ? cin_blk * 2 : swz;
     // pixel grid tiled by BW x BH = 128
     const bool deconv = cp.mode == MODE_DECONV;  // (two-phase form; MODE_ROW3 is the single-pass form)
     q.Hgrid = cp.H;
-    q.Wgrid = deconv ? cp.Win : cp.Wout;
+    q.Wgrid = deconv ? cp.Win : cp.Wout / G;
     q.Wout = cp.Wout;
-    q.out_wmul = deconv ? 2 : 1;
+    q.out_wmul = deconv ? 2 : G;
     q.n_phase = deconv ? 2 : 1;
     int bw = 128;
     while (bw > 1 && bw / 2 >= q.Wgrid) bw /= 2;  // smallest power of two >= Wgrid, capped at 128
@@ -596,10 +666,16 @@ int Net::tc_prepare() {
     // halo reuse needs the three weight tiles of a row next to the A tile: only when >= 4 stages still fit
     bool halo = (cp.mode == MODE_3x3_S1 || cp.mode == MODE_ROW3) && q.BW == 128 && tc_halo_mode;
     if (halo) {
-      const int all_w_ = cp.ntaps * q.kchunks * q.BN * q.KC * 2;
+      const int btile_ = G > 1 ? cp.cout_pad * cin_blk * 2 : q.BN * q.KC * 2;
+      const int all_w_ = cp.ntaps * q.kchunks * btile_;
       const bool resident_ = tc_resident_mode && q.n_nt == 1 && all_w_ <= 112 * 1024;
-      const int st_ = (130 * q.KC * 2 + 1023) / 1024 * 1024 + (resident_ ? 0 : 3 * q.BN * q.KC * 2);
+      const int st_ = (130 * q.KC * 2 + 1023) / 1024 * 1024 + (resident_ ? 0 : 3 * btile_);
       if ((max_smem - 2048 - 65536 - cp.cout_pad * 4 - (resident_ ? all_w_ + 1024 : 0)) / st_ < 4) halo = false;
+    }
+    if (G > 1 && cp.mode != MODE_1x1 && !halo) {  // the banded issue of a 3-tap row needs the halo tile
+      delete plan;
+      set_error("internal: pixel-group plan without halo tile");
+      return PCLS_ERR_STATE;
     }
     if (cp.mode == MODE_1x1) {
       q.n_groups = 1;
@@ -638,9 +714,10 @@ int Net::tc_prepare() {
       q.grp_dw[1][1] = 0;  q.grp_w[1][1][0] = 2;
     }
     // TMA-store epilogue: 16-bit outputs whose N tile splits into blocks of <= 64 channels
-    q.tma_store = 0; q.cbw = 0; q.c_stage_bytes = 0; q.c_is_5d = deconv ? 1 : 0;
+    q.tma_store = 0; q.cbw = 0; q.c_stage_bytes = 0; q.c_is_5d = (deconv || G > 1) ? 1 : 0;
     // (measured: for N tiles narrower than 64 channels the direct 16-byte stores are faster than staging)
-    if (tc_tma_store_mode && !cp.out_f32 && cp.cout == cp.cout_pad && (q.BN % 64 == 0 || tc_tma_store_mode > 1) &&
+    if (tc_tma_store_mode && !cp.out_f32 && cp.cout == cp.cout_pad && q.BN % 64 == 0 &&
+        (G == 1 || cp.cout_pad % 64 == 0) &&
         (cp.out_channels * 2) % 16 == 0) {
       q.tma_store = 1;
       q.cbw = q.BN < 64 ? q.BN : 64;
@@ -649,10 +726,11 @@ int Net::tc_prepare() {
     const int cstage_total = q.tma_store ? 4 * q.c_stage_bytes : 0;
     // pipeline depth; weights stay resident in smem when the whole layer fits next to >= 4 stages
     q.a_bytes = (q.a_rows * q.KC * 2 + 1023) / 1024 * 1024;
-    q.b_tile_bytes = q.BN * q.KC * 2;
+    q.b_tile_bytes = G > 1 ? cp.cout_pad * cin_blk * 2 : q.BN * q.KC * 2;
     const int all_w = q.n_phase * q.n_groups * q.kchunks * q.sub * q.b_tile_bytes;
     q.b_resident = (tc_resident_mode && q.n_nt == 1 && all_w <= 112 * 1024) ? 1 : 0;
     q.bres_bytes = q.b_resident ? (all_w + 1023) / 1024 * 1024 : 0;
+    if (G > 1 && !q.b_resident) { delete plan; set_error("internal: pixel-group plan needs resident weights"); return PCLS_ERR_STATE; }
     const int stage_bytes = q.a_bytes + (q.b_resident ? 0 : q.sub * q.b_tile_bytes);
     int stages = (max_smem - 2048 - cp.cout_pad * 4 - q.bres_bytes - cstage_total) / stage_bytes;
     if (stages > 12) stages = 12;
@@ -664,6 +742,12 @@ int Net::tc_prepare() {
     const uint32_t layout = swz == 128 ? 2u : swz == 64 ? 4u : 6u;  // UMMA LayoutType
     const uint32_t sbo = (uint32_t)(8 * swz) >> 4;                   // 8 rows of one swizzle span
     q.desc_hi = sbo | (1u << 14) /*descriptor version (sm_100)*/ | (layout << 29);
+    {
+      const uint32_t layout_b = swz_b == 128 ? 2u : swz_b == 64 ? 4u : 6u;
+      q.desc_hi_b = ((uint32_t)(8 * swz_b) >> 4) | (1u << 14) | (layout_b << 29);
+      q.idesc_blk = (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) |
+                    ((uint32_t)(cp.cout_pad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    }
     q.idesc = (1u << 4) /*D = f32*/ | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) |
               ((uint32_t)(q.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     q.n_acc = 2;
@@ -679,7 +763,7 @@ int Net::tc_prepare() {
 
     // tensor maps.  A: activations of the input tensor inside the arena (extent = frames_per_pass frames).
     char* a_base = (char*)tensor_ptr(L.in, frames_per_pass);
-    const uint64_t C = (uint64_t)cp.in_channels, Wi = (uint64_t)cp.Win, Hh = (uint64_t)cp.H, F = (uint64_t)frames_per_pass;
+    const uint64_t C = (uint64_t)cp.in_channels * G, Wi = (uint64_t)cp.Win / G, Hh = (uint64_t)cp.H, F = (uint64_t)frames_per_pass;
     int rc;
     if (q.a_is_5d) {
       const uint64_t dims[5] = {C, 2, Wi / 2, Hh, F};
@@ -696,17 +780,18 @@ int Net::tc_prepare() {
     {
       const uint64_t dims[3] = {(uint64_t)cp.cin_pad, (uint64_t)cp.cout_pad, (uint64_t)cp.ntaps};
       const uint64_t str[2] = {(uint64_t)cp.cin_pad * 2, (uint64_t)cp.cin_pad * cp.cout_pad * 2};
-      const uint32_t box[3] = {(uint32_t)q.KC, (uint32_t)q.BN, 1};
-      rc = make_map(&plan->map_b, bf16, const_cast<void*>(cp.w), 3, dims, str, box, swz);
+      const uint32_t box[3] = {(uint32_t)(G > 1 ? cin_blk : q.KC), (uint32_t)(G > 1 ? cp.cout_pad : q.BN), 1};
+      rc = make_map(&plan->map_b, bf16, const_cast<void*>(cp.w), 3, dims, str, box, swz_b);
     }
     if (rc) { delete plan; return rc; }
     if (q.tma_store) {  // C: the output tensor (or its re-viewed form) inside the arena
       char* c_base = (char*)tensor_ptr(L.out, frames_per_pass);
       const uint64_t Co = (uint64_t)cp.out_channels, Wo = (uint64_t)cp.Wout;
       const int csw = q.cbw == 64 ? 128 : 0;
-      if (q.c_is_5d) {  // two-phase transposed conv: phase = output column parity
-        const uint64_t dims[5] = {Co, 2, Wo / 2, Hh, F};
-        const uint64_t str[4] = {Co * 2, Co * 4, Wo * Co * 2, Hh * Wo * Co * 2};
+      if (q.c_is_5d) {  // two-phase transposed conv: dim 1 = output column parity; pixel groups: dim 1 = pixel in group
+        const uint64_t gg = G > 1 ? (uint64_t)G : 2;
+        const uint64_t dims[5] = {Co, gg, Wo / gg, Hh, F};
+        const uint64_t str[4] = {Co * 2, Co * 2 * gg, Wo * Co * 2, Hh * Wo * Co * 2};
         const uint32_t box[5] = {(uint32_t)q.cbw, 1, (uint32_t)q.BW, (uint32_t)q.BH, 1};
         rc = make_map(&plan->map_c, bf16, c_base, 5, dims, str, box, csw);
       } else {
@@ -725,7 +810,10 @@ int Net::tc_prepare() {
   if (!attr_set) {
     for (int kc = 16; kc <= 64; kc *= 2)
       for (int sub = 1; sub <= 3; sub += 2)
-        PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(kc, sub), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        for (int g = 1; g <= 4; g *= 2) {
+          if ((g == 4 && kc != 64) || (g == 2 && kc == 16)) continue;
+          PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(kc, sub, g), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        }
     attr_set = true;
   }
   return PCLS_OK;
@@ -738,7 +826,7 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
   const int num_tiles = prm.num_tiles * nb;
   if (num_tiles == 0) return PCLS_OK;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  tc_kernel_for(prm.KC, prm.sub)<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, prm, num_tiles);
+  tc_kernel_for(prm.KC, prm.sub, prm.G)<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, prm, num_tiles);
   return check_launch("conv_tc_kernel");
 }
 

@@ -719,6 +719,7 @@ extern "C" int pcls_net_set_option(pcls_net* net, const char* name, int value) {
   }
   if (!strcmp(name, "tc_halo")) { tc_halo_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_tma_store")) { tc_tma_store_mode = value; return PCLS_OK; }
+  if (!strcmp(name, "tc_group")) { tc_group_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_resident")) { tc_resident_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_base_offset")) { tc_base_offset_mode = value; return PCLS_OK; }
   set_error("pcls_net_set_option: unknown option '%s'", name);

@@ -122,6 +122,40 @@ def F_relu(x):
   return torch.relu(x)
 
 
+@pytest.mark.parametrize("W,cs,ce", [(512, 16, 64), (1024, 16, 32), (512, 32, 64), (256, 32, 128), (512, 16, 16)])
+def test_wide_narrow_channel_layers(W, cs, ce):
+  """The shapes of the benchmark's narrow-channel Fire layers (Cin = 16 / 32 at W >= 256): pixel-group view (G = 4 / 2),
+  banded MMA issue, halo tiles, resident weights, TMA-store epilogue with the 5-D group map, residual prefetch and the
+  single-pass transposed conv - each against the oracle."""
+  rng = np.random.default_rng(W + cs + ce)
+  B, H = 2, 3
+  t = TinyNet(H, W)
+  g = t.g
+  a = L.relu(L.BatchNormalization("b0")(L.Conv2D("c0", 64, 3)(g.input)))                 # [W, 64] (pair view)
+  skip = L.relu(L.BatchNormalization("bs")(L.Conv2D("cs", 2 * ce, 1)(a)))                # the tensor added at the end
+  sq = L.relu(L.BatchNormalization("b1")(L.Conv2D("c1", cs, 1)(a)))                      # squeeze -> cs channels
+  e1 = L.relu(L.BatchNormalization("b2")(L.Conv2D("c2", ce, 1)(sq)))                     # grouped 1x1
+  e3 = L.relu(L.BatchNormalization("b3")(L.Conv2D("c3", ce, 3)(sq)))                     # grouped 3x3 (halo)
+  cat = L.add(L.concat([e1, e3]), skip)                                                  # concat offsets + residual
+  sq2 = L.relu(L.BatchNormalization("b4")(L.Conv2D("c4", cs, 1)(cat)))
+  up = L.relu(L.Conv2DTranspose("c5", cs)(sq2))                                          # grouped single-pass deconv
+  _rand_vars(g, rng)
+  x = _input(rng, B, H, W)
+  p = _tp(g)
+  xa = F_relu(O.batch_norm(O._conv(_nchw(x), p, "c0"), p, "b0"))
+  xs = F_relu(O.batch_norm(O._conv(xa, p, "cs"), p, "bs"))
+  xq = F_relu(O.batch_norm(O._conv(xa, p, "c1"), p, "b1"))
+  xcat = torch.cat([F_relu(O.batch_norm(O._conv(xq, p, "c2"), p, "b2")), F_relu(O.batch_norm(O._conv(xq, p, "c3"), p, "b3"))], 1) + xs
+  xq2 = F_relu(O.batch_norm(O._conv(xcat, p, "c4"), p, "b4"))
+  xup = F_relu(O.conv2d_transpose_1x4_s2(xq2, p["c5/kernel"], p["c5/bias"]))
+  for impl in IMPLS:
+    got = TinyNet.run(t, up, B, x, impl)
+    ref = _nhwc(xup)
+    assert got.shape == ref.shape
+    err = np.abs(got - ref).max()
+    assert err < 3e-2 * max(1.0, np.abs(ref).max()), (impl, err)
+
+
 @pytest.mark.parametrize("impl", IMPLS)
 def test_residual_and_skip_adds(impl):
   rng = np.random.default_rng(3)
