@@ -87,6 +87,9 @@ __device__ __forceinline__ void group_barrier(int id) { asm volatile("bar.sync %
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const int4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ unsigned long long clk() { unsigned long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)); return t; }
+#define DBG_T0 const unsigned long long _t0 = dbg ? clk() : 0ull
+#define DBG_ADD(slot) if (dbg) dbg_acc[slot] += clk() - _t0
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -149,7 +152,7 @@ struct TcParams {
   int tma_store, cbw, c_is_5d, c_stage_bytes;
   // pixel-group view (G > 1): an A row holds G adjacent pixels x Cin channels; accumulator columns [p*cout_blk, ..) belong
   // to pixel p of the group.  cout_blk = 1 << 30 when G == 1.
-  int G, cout_blk;
+  int G, cout_blk, cout_blk_shift;
   uint32_t desc_hi_b, idesc_blk;
   // epilogue
   int cout, out_channels, out_coff, act, out_f32, is_bf16;
@@ -158,99 +161,34 @@ struct TcParams {
   const void* res1;
   int res0_channels, res1_channels;
   const float* bias;
+  unsigned long long* dbg;    // optional [gridDim.x][16] cycle counters (pcls_net_set_option "tc_debug")
 };
 
-// 32 accumulator columns of one pixel row: +bias (smem), activation, + prefetched residuals, store.
+// 8 accumulator columns -> +bias, activation, +residuals -> one 16-byte vector of 16-bit outputs.
+// Branch-free activation: act(v) = max(v, v * slope) with slope 1 (none), 0 (ReLU), 0.1 (LeakyReLU).
 template <typename T>
-__device__ __forceinline__ void epilogue_store32(const TcParams& p, const uint32_t (&acc)[32], const float* bias_s,
-                                                 int n_base, int64_t pix, bool valid, const int4 (&r0)[4],
-                                                 const int4 (&r1)[4]) {
-  if (!valid) return;
-  if (p.G > 1) {  // pixel-group view: column n -> pixel n / cout_blk of the group, channel n % cout_blk
+__device__ __forceinline__ int4 epilogue_vec8(const uint32_t* acc, const float* bias8, float slope, bool has_r0,
+                                              const int4& r0, bool has_r1, const int4& r1) {
+  const float4 b0 = *reinterpret_cast<const float4*>(bias8);
+  const float4 b1 = *reinterpret_cast<const float4*>(bias8 + 4);
+  float v[8] = {__uint_as_float(acc[0]) + b0.x, __uint_as_float(acc[1]) + b0.y, __uint_as_float(acc[2]) + b0.z,
+                __uint_as_float(acc[3]) + b0.w, __uint_as_float(acc[4]) + b1.x, __uint_as_float(acc[5]) + b1.y,
+                __uint_as_float(acc[6]) + b1.z, __uint_as_float(acc[7]) + b1.w};
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int n = n_base + g * 8;
-      const int pp = n / p.cout_blk, co = n - pp * p.cout_blk;
-      if (co + 8 > p.cout) continue;
-      float v[8];
+  for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], v[j] * slope);
+  if (has_r0) {
+    float f[8];
+    unpack8<T>(r0, f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[g * 8 + j]) + bias_s[n + j], p.act);
-      if (p.res0) {
-        float f[8];
-        unpack8<T>(r0[g], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] += f[j];
-      }
-      if (p.res1) {
-        float f[8];
-        unpack8<T>(r1[g], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] += f[j];
-      }
-      *reinterpret_cast<int4*>(reinterpret_cast<T*>(p.out) + (pix + pp) * p.out_channels + p.out_coff + co) = pack8<T>(v);
-    }
-    return;
+    for (int j = 0; j < 8; ++j) v[j] += f[j];
   }
-  if (p.out_f32) {
-    float* o = reinterpret_cast<float*>(p.out) + pix * p.out_channels + p.out_coff;
+  if (has_r1) {
+    float f[8];
+    unpack8<T>(r1, f);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int co = n_base + j;
-      if (co < p.cout) o[co] = apply_act(__uint_as_float(acc[j]) + bias_s[co], p.act);
-    }
-    return;
+    for (int j = 0; j < 8; ++j) v[j] += f[j];
   }
-  T* o = reinterpret_cast<T*>(p.out) + pix * p.out_channels + p.out_coff;
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int co = n_base + g * 8;
-    if (co + 8 > p.cout) continue;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[g * 8 + j]) + bias_s[co + j], p.act);
-    if (p.res0) {
-      float f[8];
-      unpack8<T>(r0[g], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += f[j];
-    }
-    if (p.res1) {
-      float f[8];
-      unpack8<T>(r1[g], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += f[j];
-    }
-    *reinterpret_cast<int4*>(o + co) = pack8<T>(v);
-  }
-}
-
-// 32 accumulator columns of one pixel row -> +bias, activation, +residuals -> four 16-byte chunks of the staged tile
-template <typename T>
-__device__ __forceinline__ void epilogue_stage32(const TcParams& p, const uint32_t (&acc)[32], const float* bias_s,
-                                                 int n_base, int ngroups, const int4 (&r0)[4], const int4 (&r1)[4],
-                                                 uint32_t row_addr, int chunk0, int row, bool swizzled) {
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    if (g >= ngroups) break;
-    const int co = n_base + g * 8;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = apply_act(__uint_as_float(acc[g * 8 + j]) + bias_s[co + j], p.act);
-    if (p.res0) {
-      float f[8];
-      unpack8<T>(r0[g], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += f[j];
-    }
-    if (p.res1) {
-      float f[8];
-      unpack8<T>(r1[g], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += f[j];
-    }
-    const int chunk = chunk0 + g;
-    st_shared_v4(row_addr + (uint32_t)((swizzled ? (chunk ^ (row & 7)) : chunk) << 4), pack8<T>(v));
-  }
+  return pack8<T>(v);
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -265,7 +203,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
-template <int KC, int SUB, int G>
+template <typename T, int KC, int SUB, int G>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ TcParams p, const int num_tiles) {
@@ -288,10 +226,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * S + 17);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  float* bias_s = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16u - smem_u32(smem_raw)));  // [n_nt * BN]
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (((tmem_slot + 16u + 15u) & ~15u) - smem_u32(smem_raw)));  // [n_nt * BN], 16-byte aligned
   for (int i = threadIdx.x; i < p.n_nt * p.BN; i += blockDim.x) bias_s[i] = p.bias[G > 1 ? i % p.cout_blk : i];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned long long* const dbg = p.dbg;
+  unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const unsigned long long dbg_start = dbg ? clk() : 0ull;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -350,7 +291,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int u = 0; u < SUB; ++u) wtap[u] = p.grp_w[ph][g][u];
           for (int kc = 0; kc < kchunks; ++kc) {
-            mbar_wait(EMPTY_BAR(stage), phase ^ 1u);
+            { DBG_T0; mbar_wait(EMPTY_BAR(stage), phase ^ 1u); DBG_ADD(0); }
             const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
             const uint32_t fb = FULL_BAR(stage);
             mbar_arrive_expect_tx(fb, tx_bytes);
@@ -380,13 +321,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t phase = 0, acc = 0, acc_phase = 0;
       if (b_resident) mbar_wait(BRES_BAR, 0u);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(TEMPTY_BAR(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+        { DBG_T0; mbar_wait(TEMPTY_BAR(acc), acc_phase ^ 1u); DBG_ADD(1); }  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)BN;
         uint32_t b_res = bres_base + (n_phase > 1 ? (uint32_t)((tile / n_nt) % n_phase) * bres_phase_bytes : 0u);
         uint32_t accumulate = 0u;
         for (int k = 0; k < k_iters; ++k) {
-          mbar_wait(FULL_BAR(stage), phase);
+          { DBG_T0; mbar_wait(FULL_BAR(stage), phase); DBG_ADD(2); }
           tc_fence_after();
           const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
           if constexpr (G == 1) {
@@ -445,6 +386,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int ml_h = m >> p.bw_shift, ml_w = m & (p.BW - 1);
     const uint32_t n_acc = (uint32_t)p.n_acc;
     const int BW = p.BW, BH = p.BH, Hgrid = p.Hgrid, Wgrid = p.Wgrid, Wout = p.Wout, out_wmul = p.out_wmul;
+    const int cout = p.cout, out_channels = p.out_channels, out_coff = p.out_coff;
+    const int blk_shift = p.cout_blk_shift;              // pixel-group view: column n -> pixel n >> blk_shift
+    const int blk_mask = G > 1 ? (1 << blk_shift) - 1 : -1;
+    const float slope = p.act == PCLS_ACT_RELU ? 0.0f : (p.act == PCLS_ACT_LEAKY ? 0.1f : 1.0f);
+    const uint16_t* res0 = reinterpret_cast<const uint16_t*>(p.res0);
+    const uint16_t* res1 = reinterpret_cast<const uint16_t*>(p.res1);
+    const int res0_channels = p.res0_channels, res1_channels = p.res1_channels;
+    const bool has_r0 = res0 != nullptr, has_r1 = res1 != nullptr, has_res = has_r0 || has_r1;
+    const bool tma_store = p.tma_store != 0, out_f32 = p.out_f32 != 0, c_is_5d = p.c_is_5d != 0;
+    const uint32_t c_stage_bytes = (uint32_t)p.c_stage_bytes;
+    T* const outp = reinterpret_cast<T*>(p.out);
+    const bool issuer = (q == 2) && lane == 0;            // first warp of the group (warp 2 or 6) issues the TMA stores
+    const int bar_id = 1 + grp;
     uint32_t tl = 0, blk = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
       if ((int)(tl & 1u) != grp) continue;
@@ -460,57 +414,75 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t acc = tl & (n_acc - 1u), acc_parity = (tl / n_acc) & 1u;
       const int n0 = nt * BN;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)BN;
-      // residual rows are prefetched BEFORE waiting for the accumulator, so their DRAM latency overlaps the MMAs
+      // element offset of (this row's pixel-in-group, channel) for accumulator column n, or -1 when out of range
+      auto elem_off = [&](int n, int channels) -> int64_t {
+        const int pp = G > 1 ? n >> blk_shift : 0;
+        const int co = n & blk_mask;
+        return (valid && co + 8 <= cout) ? (pix + pp) * channels + out_coff + co : (int64_t)-1;
+      };
       // residual rows of the first 32 columns are prefetched BEFORE waiting for the accumulator (their DRAM latency
       // overlaps the MMAs of this tile); later chunks are fetched one chunk ahead
       int4 r0[4], r1[4];
-      const bool has_res = (p.res0 != nullptr) || (p.res1 != nullptr);
       auto load_res = [&](int c) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int n = n0 + c + g * 8;
-          const int pp = G > 1 ? n / p.cout_blk : 0;
-          const int co = n - pp * (G > 1 ? p.cout_blk : 0);
-          const bool okc = valid && (co + 8 <= p.cout);
-          r0[g] = (p.res0 && okc) ? __ldg(reinterpret_cast<const int4*>(
-                      reinterpret_cast<const uint16_t*>(p.res0) + (pix + pp) * p.res0_channels + p.out_coff + co)) : make_int4(0, 0, 0, 0);
-          r1[g] = (p.res1 && okc) ? __ldg(reinterpret_cast<const int4*>(
-                      reinterpret_cast<const uint16_t*>(p.res1) + (pix + pp) * p.res1_channels + p.out_coff + co)) : make_int4(0, 0, 0, 0);
+          if (has_r0) { const int64_t o = elem_off(n, res0_channels); r0[g] = o >= 0 ? __ldg(reinterpret_cast<const int4*>(res0 + o)) : make_int4(0, 0, 0, 0); }
+          if (has_r1) { const int64_t o = elem_off(n, res1_channels); r1[g] = o >= 0 ? __ldg(reinterpret_cast<const int4*>(res1 + o)) : make_int4(0, 0, 0, 0); }
         }
       };
       if (has_res) load_res(0);
-      mbar_wait(TFULL_BAR(acc), acc_parity);
+      { DBG_T0; mbar_wait(TFULL_BAR(acc), acc_parity); DBG_ADD(3); }
+      const unsigned long long _te = dbg ? clk() : 0ull;
       tc_fence_after();
-      if (p.tma_store) {
+      if (out_f32) {
+        // float32 logits (conv14 / head): cout <= 32 columns of interest, plain stores
+        float* o = reinterpret_cast<float*>(p.out) + pix * out_channels + out_coff;
+        for (int c = 0; c < BN; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_row + (uint32_t)c, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int co = n0 + c + j;
+              if (co < cout) { const float x = __uint_as_float(v[j]) + bias_s[co]; o[co] = fmaxf(x, x * slope); }
+            }
+          }
+        }
+      } else if (tma_store) {
         // ---- TMEM -> registers -> swizzled smem tile -> TMA bulk tensor store (full lines, edges clipped by TMA) ----
         // blocks of 64 channels (128-byte rows, SWIZZLE_128B)
-        const bool issuer = (q == 2) && lane == 0;            // first warp of the group (warp 2 or 6)
-        const int bar_id = 1 + grp;
         for (int cb = 0; cb < BN; cb += 64, ++blk) {
-          const uint32_t buf = cstage_base + (uint32_t)((grp * 2 + (int)(blk & 1u)) * p.c_stage_bytes);
+          const uint32_t buf = cstage_base + (uint32_t)(grp * 2 + (int)(blk & 1u)) * c_stage_bytes;
           const uint32_t row_addr = buf + (uint32_t)(m * 128);
-#pragma unroll
+#pragma unroll 1
           for (int ci = 0; ci < 2; ++ci) {
             const int cc = cb + ci * 32;
             uint32_t v[32];
             tmem_ld32(t_row + (uint32_t)cc, v);
             tmem_ld_wait();
-            if (p.is_bf16) epilogue_stage32<__nv_bfloat16>(p, v, bias_s, n0 + cc, 4, r0, r1, row_addr, ci * 4, m, true);
-            else epilogue_stage32<__half>(p, v, bias_s, n0 + cc, 4, r0, r1, row_addr, ci * 4, m, true);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int4 o = epilogue_vec8<T>(v + g * 8, bias_s + n0 + cc + g * 8, slope, has_r0, r0[g], has_r1, r1[g]);
+              st_shared_v4(row_addr + (uint32_t)((((ci * 4 + g) ^ (m & 7))) << 4), o);
+            }
             if (has_res && cc + 32 < BN) load_res(cc + 32);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> visible to the TMA engine
-          if (issuer) bulk_wait_read0();   // the previous store of this group has finished reading the OTHER buffer
-          group_barrier(bar_id);
+          { DBG_T0; if (issuer) bulk_wait_read0(); DBG_ADD(4); }   // the previous store of this group has finished reading the OTHER buffer
+          { DBG_T0; group_barrier(bar_id); DBG_ADD(5); }
           if (issuer) {
-            const int pp = G > 1 ? (n0 + cb) / p.cout_blk : 0;
-            const int c0 = p.out_coff + n0 + cb - pp * (G > 1 ? p.cout_blk : 0);
-            if (p.c_is_5d) tma_store_5d(&map_c, buf, c0, G > 1 ? pp : ph, wt * BW, ht * BH, b);
+            const int pp = G > 1 ? (n0 + cb) >> blk_shift : 0;
+            const int c0 = out_coff + ((n0 + cb) & blk_mask);
+            if (c_is_5d) tma_store_5d(&map_c, buf, c0, G > 1 ? pp : ph, wt * BW, ht * BH, b);
             else tma_store_4d(&map_c, buf, c0, wt * BW, ht * BH, b);
             bulk_commit();
           }
         }
       } else {
+        // ---- direct 16-byte stores (N tiles narrower than 64 channels per pixel) ----
+#pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
           uint32_t v[32];
           if (c + 32 <= BN) {
@@ -522,18 +494,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0u; }
           }
           tmem_ld_wait();
-          if (p.is_bf16) epilogue_store32<__nv_bfloat16>(p, v, bias_s, n0 + c, pix, valid, r0, r1);
-          else epilogue_store32<__half>(p, v, bias_s, n0 + c, pix, valid, r0, r1);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = n0 + c + g * 8;
+            const int64_t o = (c + g * 8 < BN) ? elem_off(n, out_channels) : (int64_t)-1;
+            if (o >= 0)
+              *reinterpret_cast<int4*>(outp + o) =
+                  epilogue_vec8<T>(v + g * 8, bias_s + n, slope, has_r0, r0[g], has_r1, r1[g]);
+          }
           if (has_res && c + 32 < BN) load_res(c + 32);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(TEMPTY_BAR(acc));
+      if (dbg) { dbg_acc[6] += clk() - _te; dbg_acc[7] += 1; }
     }
     if (p.tma_store && q == 2 && lane == 0) bulk_wait_all();  // smem must outlive the last stores
   }
 
+  if (dbg && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 6)) {
+    unsigned long long* o = dbg + (size_t)blockIdx.x * 24;
+    if (warp == 0) { o[0] = dbg_acc[0]; o[8] = clk() - dbg_start; }
+    if (warp == 1) { o[1] = dbg_acc[1]; o[2] = dbg_acc[2]; o[9] = clk() - dbg_start; }
+    if (warp == 2) { for (int i = 3; i < 8; ++i) o[i] = dbg_acc[i]; o[10] = clk() - dbg_start; }
+    if (warp == 6) { for (int i = 3; i < 8; ++i) o[8 + i] = dbg_acc[i]; }
+  }
   // teardown
   __syncwarp();
   tc_fence_before();
@@ -550,14 +536,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const int);
-static TcKernelFn tc_kernel_for(int KC, int SUB, int G) {
-  if (G == 4) return SUB == 3 ? conv_tc_kernel<64, 3, 4> : conv_tc_kernel<64, 1, 4>;
+template <typename T>
+static TcKernelFn tc_kernel_for_t(int KC, int SUB, int G) {
+  if (G == 4) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 4> : conv_tc_kernel<T, 64, 1, 4>;
   if (G == 2) {
-    if (KC == 64) return SUB == 3 ? conv_tc_kernel<64, 3, 2> : conv_tc_kernel<64, 1, 2>;
-    return SUB == 3 ? conv_tc_kernel<32, 3, 2> : conv_tc_kernel<32, 1, 2>;
+    if (KC == 64) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 2> : conv_tc_kernel<T, 64, 1, 2>;
+    return SUB == 3 ? conv_tc_kernel<T, 32, 3, 2> : conv_tc_kernel<T, 32, 1, 2>;
   }
-  if (SUB == 3) return KC == 64 ? conv_tc_kernel<64, 3, 1> : KC == 32 ? conv_tc_kernel<32, 3, 1> : conv_tc_kernel<16, 3, 1>;
-  return KC == 64 ? conv_tc_kernel<64, 1, 1> : KC == 32 ? conv_tc_kernel<32, 1, 1> : conv_tc_kernel<16, 1, 1>;
+  if (SUB == 3) return KC == 64 ? conv_tc_kernel<T, 64, 3, 1> : KC == 32 ? conv_tc_kernel<T, 32, 3, 1> : conv_tc_kernel<T, 16, 3, 1>;
+  return KC == 64 ? conv_tc_kernel<T, 64, 1, 1> : KC == 32 ? conv_tc_kernel<T, 32, 1, 1> : conv_tc_kernel<T, 16, 1, 1>;
+}
+static TcKernelFn tc_kernel_for(int KC, int SUB, int G, int is_bf16) {
+  return is_bf16 ? tc_kernel_for_t<__nv_bfloat16>(KC, SUB, G) : tc_kernel_for_t<__half>(KC, SUB, G);
 }
 
 struct TcPlan {
@@ -602,6 +592,7 @@ static int make_map(CUtensorMap* map, bool bf16, void* base, int rank, const uin
 
 // A/B switches for measurement (pcls_net_set_option before finalize): halo reuse, resident weights, base offset
 int tc_tma_store_mode = 1, tc_group_mode = 1;
+unsigned long long* tc_debug_buf = nullptr;  // [148][24] counters of the most recent launch when enabled
 int tc_halo_mode = 1, tc_resident_mode = 1, tc_base_offset_mode = 0;  // measured: UMMA swizzles on absolute smem address bits, a row-shifted start needs NO base offset
 
 // Which layers run on tensor cores: the input tensor must carry >= 16 real channels (the 6-channel network input
@@ -637,10 +628,12 @@ int Net::tc_prepare() {
         (cp.cin_pad == 16 || cp.cin_pad == 32) && cp.in_channels == cp.cin_pad && cp.cout == cp.cout_pad && !cp.out_f32 &&
         cp.Wout == cp.Win) {
       for (int g = 64 / cp.cin_pad; g >= 2; g /= 2)
-        if (cp.Win % g == 0 && cp.Win / g >= 128 && g * cp.cout_pad <= 256) { G = g; break; }
+        if (cp.Win % g == 0 && cp.Win / g >= 128 && g * cp.cout_pad <= 256 && (cp.cout_pad & (cp.cout_pad - 1)) == 0) { G = g; break; }
     }
     const int cin_blk = cp.cin_pad;
     q.G = G; q.cout_blk = G > 1 ? cp.cout_pad : (1 << 30);
+    q.cout_blk_shift = 0;
+    while ((1 << q.cout_blk_shift) < q.cout_blk && q.cout_blk_shift < 30) ++q.cout_blk_shift;
     if (G > 1) { q.KC = G * cin_blk; q.kchunks = 1; q.BN = G * cp.cout_pad; q.n_nt = 1; }
     const int swz = q.KC * 2;
     const int swz_b = G > 1 ? cin_blk * 2 : swz;
@@ -737,7 +730,7 @@ int Net::tc_prepare() {
     if (stages < 2) { delete plan; continue; }
     q.stages = stages;
     plan->smem_bytes = (size_t)stages * stage_bytes + q.bres_bytes + cstage_total + 1024 /*alignment slack*/ +
-                       (size_t)(2 * stages + 17) * 8 + 16 + (size_t)cp.cout_pad * 4 /*bias*/;
+                       (size_t)(2 * stages + 17) * 8 + 48 + (size_t)cp.cout_pad * 4 /*bias*/;
     // descriptors
     const uint32_t layout = swz == 128 ? 2u : swz == 64 ? 4u : 6u;  // UMMA LayoutType
     const uint32_t sbo = (uint32_t)(8 * swz) >> 4;                   // 8 rows of one swizzle span
@@ -812,7 +805,8 @@ int Net::tc_prepare() {
       for (int sub = 1; sub <= 3; sub += 2)
         for (int g = 1; g <= 4; g *= 2) {
           if ((g == 4 && kc != 64) || (g == 2 && kc == 16)) continue;
-          PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(kc, sub, g), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+          for (int bf = 0; bf < 2; ++bf)
+            PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(kc, sub, g, bf), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         }
     attr_set = true;
   }
@@ -823,10 +817,11 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
   TcPlan* plan = L.tc;
   TcParams prm = plan->prm;
   prm.out = p.out; prm.res0 = p.res0; prm.res1 = p.res1;
+  prm.dbg = tc_debug_buf;
   const int num_tiles = prm.num_tiles * nb;
   if (num_tiles == 0) return PCLS_OK;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  tc_kernel_for(prm.KC, prm.sub, prm.G)<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, prm, num_tiles);
+  tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16)<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, prm, num_tiles);
   return check_launch("conv_tc_kernel");
 }
 

@@ -442,6 +442,18 @@ int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool ra
       rc = launch_cam<T>((const T*)tensor_ptr(L.in, nb), (T*)tensor_ptr(L.out, nb), L.p, nb, H, tensors[L.in].width, s);
     }
     if (rc) return rc;
+    if (tc_debug_buf && ev && op.type == OP_CONV) {  // development aid: print the counters of this launch
+      cudaStreamSynchronize(s);
+      std::vector<unsigned long long> h(148 * 24);
+      cudaMemcpy(h.data(), tc_debug_buf, h.size() * 8, cudaMemcpyDeviceToHost);
+      cudaMemset(tc_debug_buf, 0, h.size() * 8);
+      double a[24] = {0};
+      for (int c = 0; c < 148; ++c) for (int i = 0; i < 24; ++i) a[i] += (double)h[c * 24 + i] / 148.0;
+      const ConvParams& cp = convs[op.index].p;
+      fprintf(stderr, "[tc_debug] conv mode %d %dx%d w%d | cycles/CTA: total %.0f | producer wait-empty %.0f | issuer wait-tempty %.0f wait-full %.0f | "
+              "epi(g0) wait-tfull %.0f store-drain %.0f barrier %.0f busy %.0f tiles %.0f | epi(g1) wait-tfull %.0f busy %.0f tiles %.0f\n",
+              cp.mode, cp.cin, cp.cout, cp.Wout, a[8], a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[11], a[14], a[15]);
+    }
   }
   if (ev) cudaEventRecord(ev[evi++], s);
   rc = launch_head(logits_buf, mask_buf, n_pixels, num_classes, none_index, probs, preds, s);
@@ -720,6 +732,11 @@ extern "C" int pcls_net_set_option(pcls_net* net, const char* name, int value) {
   if (!strcmp(name, "tc_halo")) { tc_halo_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_tma_store")) { tc_tma_store_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_group")) { tc_group_mode = value; return PCLS_OK; }
+  if (!strcmp(name, "tc_debug")) {  // per-role wait-cycle counters of conv_tc_kernel (development aid)
+    if (value && !tc_debug_buf) { PCLS_CHECK_CUDA(cudaMalloc(&tc_debug_buf, 148 * 24 * 8)); PCLS_CHECK_CUDA(cudaMemset(tc_debug_buf, 0, 148 * 24 * 8)); }
+    if (!value && tc_debug_buf) { cudaFree(tc_debug_buf); tc_debug_buf = nullptr; }
+    return PCLS_OK;
+  }
   if (!strcmp(name, "tc_resident")) { tc_resident_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_base_offset")) { tc_base_offset_mode = value; return PCLS_OK; }
   set_error("pcls_net_set_option: unknown option '%s'", name);
