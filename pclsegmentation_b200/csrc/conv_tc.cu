@@ -203,7 +203,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
-template <typename T, int KC, int SUB, int G>
+template <typename T, int KC, int SUB, int G, bool RES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ TcParams p, const int num_tiles) {
@@ -393,7 +393,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint16_t* res0 = reinterpret_cast<const uint16_t*>(p.res0);
     const uint16_t* res1 = reinterpret_cast<const uint16_t*>(p.res1);
     const int res0_channels = p.res0_channels, res1_channels = p.res1_channels;
-    const bool has_r0 = res0 != nullptr, has_r1 = res1 != nullptr, has_res = has_r0 || has_r1;
+    const bool has_r0 = res0 != nullptr, has_r1 = res1 != nullptr;
     const bool tma_store = p.tma_store != 0, out_f32 = p.out_f32 != 0, c_is_5d = p.c_is_5d != 0;
     const uint32_t c_stage_bytes = (uint32_t)p.c_stage_bytes;
     T* const outp = reinterpret_cast<T*>(p.out);
@@ -420,21 +420,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int co = n & blk_mask;
         return (valid && co + 8 <= cout) ? (pix + pp) * channels + out_coff + co : (int64_t)-1;
       };
-      // residual rows of the first 32 columns are prefetched BEFORE waiting for the accumulator (their DRAM latency
-      // overlaps the MMAs of this tile); later chunks are fetched one chunk ahead
-      int4 r0[4], r1[4];
-      auto load_res = [&](int c) {
+      // Residual rows (RES kernels only).  residual0 of a whole 128-column batch is prefetched BEFORE waiting for the
+      // accumulator, so its DRAM latency overlaps the MMAs of this tile; the second residual (Darknet decoder only,
+      // compute-bound layers) is fetched one chunk ahead.
+      int4 rb0[RES ? 16 : 1], r1[4];
+      auto load_r0_batch = [&](int cs) {
+        if constexpr (RES) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int n = n0 + c + g * 8;
-          if (has_r0) { const int64_t o = elem_off(n, res0_channels); r0[g] = o >= 0 ? __ldg(reinterpret_cast<const int4*>(res0 + o)) : make_int4(0, 0, 0, 0); }
-          if (has_r1) { const int64_t o = elem_off(n, res1_channels); r1[g] = o >= 0 ? __ldg(reinterpret_cast<const int4*>(res1 + o)) : make_int4(0, 0, 0, 0); }
+          for (int i = 0; i < 16; ++i) {
+            const int64_t o = (has_r0 && cs + i * 8 < BN) ? elem_off(n0 + cs + i * 8, res0_channels) : (int64_t)-1;
+            rb0[i] = o >= 0 ? __ldg(reinterpret_cast<const int4*>(res0 + o)) : make_int4(0, 0, 0, 0);
+          }
         }
       };
-      if (has_res) load_res(0);
+      auto load_r1 = [&](int c) {
+        if constexpr (RES) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int64_t o = has_r1 ? elem_off(n0 + c + g * 8, res1_channels) : (int64_t)-1;
+            r1[g] = o >= 0 ? __ldg(reinterpret_cast<const int4*>(res1 + o)) : make_int4(0, 0, 0, 0);
+          }
+        }
+      };
+      load_r0_batch(0);
+      if (has_r1) load_r1(0);
       { DBG_T0; mbar_wait(TFULL_BAR(acc), acc_parity); DBG_ADD(3); }
       const unsigned long long _te = dbg ? clk() : 0ull;
       tc_fence_after();
+      // one 32-column chunk: TMEM -> registers -> 4 output vectors, handed to `sink(g, vector)`
+      auto chunk = [&](int cc, const int4* r0v, auto&& sink) {
+        uint32_t v[32];
+        if (cc + 32 <= BN) {
+          tmem_ld32(t_row + (uint32_t)cc, v);
+        } else {  // BN % 32 == 16 tail
+          uint32_t v16[16];
+          tmem_ld16(t_row + (uint32_t)cc, v16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0u; }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          sink(g, epilogue_vec8<T>(v + g * 8, bias_s + n0 + cc + g * 8, slope, RES && has_r0, r0v[RES ? g : 0],
+                                   RES && has_r1, r1[g]));
+        if (RES && has_r1 && cc + 32 < BN) load_r1(cc + 32);
+      };
       if (out_f32) {
         // float32 logits (conv14 / head): cout <= 32 columns of interest, plain stores
         float* o = reinterpret_cast<float*>(p.out) + pix * out_channels + out_coff;
@@ -453,24 +483,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       } else if (tma_store) {
         // ---- TMEM -> registers -> swizzled smem tile -> TMA bulk tensor store (full lines, edges clipped by TMA) ----
         // blocks of 64 channels (128-byte rows, SWIZZLE_128B)
-        for (int cb = 0; cb < BN; cb += 64, ++blk) {
-          const uint32_t buf = cstage_base + (uint32_t)(grp * 2 + (int)(blk & 1u)) * c_stage_bytes;
-          const uint32_t row_addr = buf + (uint32_t)(m * 128);
-#pragma unroll 1
-          for (int ci = 0; ci < 2; ++ci) {
-            const int cc = cb + ci * 32;
-            uint32_t v[32];
-            tmem_ld32(t_row + (uint32_t)cc, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int4 o = epilogue_vec8<T>(v + g * 8, bias_s + n0 + cc + g * 8, slope, has_r0, r0[g], has_r1, r1[g]);
-              st_shared_v4(row_addr + (uint32_t)((((ci * 4 + g) ^ (m & 7))) << 4), o);
-            }
-            if (has_res && cc + 32 < BN) load_res(cc + 32);
-          }
+        auto store_block = [&](int cb, uint32_t buf) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> visible to the TMA engine
-          { DBG_T0; if (issuer) bulk_wait_read0(); DBG_ADD(4); }   // the previous store of this group has finished reading the OTHER buffer
+          { DBG_T0; if (issuer) bulk_wait_read0(); DBG_ADD(4); }   // previous store of this group finished reading the OTHER buffer
           { DBG_T0; group_barrier(bar_id); DBG_ADD(5); }
           if (issuer) {
             const int pp = G > 1 ? (n0 + cb) >> blk_shift : 0;
@@ -479,30 +494,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             else tma_store_4d(&map_c, buf, c0, wt * BW, ht * BH, b);
             bulk_commit();
           }
+        };
+        if constexpr (RES) {
+          for (int cs = 0; cs < BN; cs += 128) {
+            if (cs > 0) load_r0_batch(cs);
+#pragma unroll
+            for (int bi = 0; bi < 2; ++bi) {
+              const int cb = cs + bi * 64;
+              if (cb < BN) {
+                const uint32_t buf = cstage_base + (uint32_t)(grp * 2 + (int)(blk & 1u)) * c_stage_bytes;
+                const uint32_t row_addr = buf + (uint32_t)(m * 128);
+#pragma unroll
+                for (int ci = 0; ci < 2; ++ci)
+                  chunk(cb + ci * 32, rb0 + bi * 8 + ci * 4, [&](int g, const int4& o) {
+                    st_shared_v4(row_addr + (uint32_t)(((ci * 4 + g) ^ (m & 7)) << 4), o); });
+                store_block(cb, buf);
+                ++blk;
+              }
+            }
+          }
+        } else {
+          for (int cb = 0; cb < BN; cb += 64, ++blk) {
+            const uint32_t buf = cstage_base + (uint32_t)(grp * 2 + (int)(blk & 1u)) * c_stage_bytes;
+            const uint32_t row_addr = buf + (uint32_t)(m * 128);
+#pragma unroll 1
+            for (int ci = 0; ci < 2; ++ci)
+              chunk(cb + ci * 32, rb0, [&](int g, const int4& o) {
+                st_shared_v4(row_addr + (uint32_t)(((ci * 4 + g) ^ (m & 7)) << 4), o); });
+            store_block(cb, buf);
+          }
         }
       } else {
         // ---- direct 16-byte stores (N tiles narrower than 64 channels per pixel) ----
+        auto direct = [&](int c, const int4* r0v) {
+          chunk(c, r0v, [&](int g, const int4& o) {
+            const int64_t off = (c + g * 8 < BN) ? elem_off(n0 + c + g * 8, out_channels) : (int64_t)-1;
+            if (off >= 0) *reinterpret_cast<int4*>(outp + off) = o;
+          });
+        };
+        if constexpr (RES) {
+          for (int cs = 0; cs < BN; cs += 128) {
+            if (cs > 0) load_r0_batch(cs);
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci)
+              if (cs + ci * 32 < BN) direct(cs + ci * 32, rb0 + ci * 4);
+          }
+        } else {
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
-          if (c + 32 <= BN) {
-            tmem_ld32(t_row + (uint32_t)c, v);
-          } else {  // BN % 32 == 16 tail
-            uint32_t v16[16];
-            tmem_ld16(t_row + (uint32_t)c, v16);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0u; }
-          }
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = n0 + c + g * 8;
-            const int64_t o = (c + g * 8 < BN) ? elem_off(n, out_channels) : (int64_t)-1;
-            if (o >= 0)
-              *reinterpret_cast<int4*>(outp + o) =
-                  epilogue_vec8<T>(v + g * 8, bias_s + n, slope, has_r0, r0[g], has_r1, r1[g]);
-          }
-          if (has_res && c + 32 < BN) load_res(c + 32);
+          for (int c = 0; c < BN; c += 32) direct(c, rb0);
         }
       }
       tc_fence_before();
@@ -536,18 +575,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const int);
-template <typename T>
+template <typename T, bool RES>
 static TcKernelFn tc_kernel_for_t(int KC, int SUB, int G) {
-  if (G == 4) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 4> : conv_tc_kernel<T, 64, 1, 4>;
+  if (G == 4) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 4, RES> : conv_tc_kernel<T, 64, 1, 4, RES>;
   if (G == 2) {
-    if (KC == 64) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 2> : conv_tc_kernel<T, 64, 1, 2>;
-    return SUB == 3 ? conv_tc_kernel<T, 32, 3, 2> : conv_tc_kernel<T, 32, 1, 2>;
+    if (KC == 64) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 2, RES> : conv_tc_kernel<T, 64, 1, 2, RES>;
+    return SUB == 3 ? conv_tc_kernel<T, 32, 3, 2, RES> : conv_tc_kernel<T, 32, 1, 2, RES>;
   }
-  if (SUB == 3) return KC == 64 ? conv_tc_kernel<T, 64, 3, 1> : KC == 32 ? conv_tc_kernel<T, 32, 3, 1> : conv_tc_kernel<T, 16, 3, 1>;
-  return KC == 64 ? conv_tc_kernel<T, 64, 1, 1> : KC == 32 ? conv_tc_kernel<T, 32, 1, 1> : conv_tc_kernel<T, 16, 1, 1>;
+  if (SUB == 3) return KC == 64 ? conv_tc_kernel<T, 64, 3, 1, RES> : KC == 32 ? conv_tc_kernel<T, 32, 3, 1, RES> : conv_tc_kernel<T, 16, 3, 1, RES>;
+  return KC == 64 ? conv_tc_kernel<T, 64, 1, 1, RES> : KC == 32 ? conv_tc_kernel<T, 32, 1, 1, RES> : conv_tc_kernel<T, 16, 1, 1, RES>;
 }
-static TcKernelFn tc_kernel_for(int KC, int SUB, int G, int is_bf16) {
-  return is_bf16 ? tc_kernel_for_t<__nv_bfloat16>(KC, SUB, G) : tc_kernel_for_t<__half>(KC, SUB, G);
+static TcKernelFn tc_kernel_for(int KC, int SUB, int G, int is_bf16, int res) {
+  if (res) return is_bf16 ? tc_kernel_for_t<__nv_bfloat16, true>(KC, SUB, G) : tc_kernel_for_t<__half, true>(KC, SUB, G);
+  return is_bf16 ? tc_kernel_for_t<__nv_bfloat16, false>(KC, SUB, G) : tc_kernel_for_t<__half, false>(KC, SUB, G);
 }
 
 struct TcPlan {
@@ -806,7 +846,8 @@ int Net::tc_prepare() {
         for (int g = 1; g <= 4; g *= 2) {
           if ((g == 4 && kc != 64) || (g == 2 && kc == 16)) continue;
           for (int bf = 0; bf < 2; ++bf)
-            PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(kc, sub, g, bf), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+            for (int rs = 0; rs < 2; ++rs)
+              PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(kc, sub, g, bf, rs), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         }
     attr_set = true;
   }
@@ -821,7 +862,7 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
   const int num_tiles = prm.num_tiles * nb;
   if (num_tiles == 0) return PCLS_OK;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16)<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, prm, num_tiles);
+  tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0)<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, prm, num_tiles);
   return check_launch("conv_tc_kernel");
 }
 
