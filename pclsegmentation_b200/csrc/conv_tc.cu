@@ -84,6 +84,17 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void group_barrier(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
+  const int sz = pred ? 16 : 0;  // src-size 0 -> the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ int4 ld_shared_v4(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const int4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -153,6 +164,7 @@ struct TcParams {
   // pixel-group view (G > 1): an A row holds G adjacent pixels x Cin channels; accumulator columns [p*cout_blk, ..) belong
   // to pixel p of the group.  cout_blk = 1 << 30 when G == 1.
   int G, cout_blk, cout_blk_shift;
+  int res_smem;               // RES kernels: 1 = residual0 staged through smem with cp.async, 0 = per-chunk LDG
   uint32_t desc_hi_b, idesc_blk;
   // epilogue
   int cout, out_channels, out_coff, act, out_f32, is_bf16;
@@ -217,7 +229,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t stage_bytes = a_bytes + b_stage_bytes;
   const uint32_t bres_base = smem_base + (uint32_t)S * stage_bytes;   // resident weights (1024-aligned)
   const uint32_t cstage_base = bres_base + (uint32_t)p.bres_bytes;  // output staging: [group][2] x c_stage_bytes
-  const uint32_t bar_base = cstage_base + (p.tma_store ? 4u * (uint32_t)p.c_stage_bytes : 0u);
+  const uint32_t rstage_base = cstage_base + (p.tma_store ? 4u * (uint32_t)p.c_stage_bytes : 0u);  // residual0 staging (RES)
+  const uint32_t bar_base = rstage_base + ((RES && p.res_smem) ? 2u * 32768u : 0u);
 #define FULL_BAR(s) (bar_base + 8u * (uint32_t)(s))
 #define EMPTY_BAR(s) (bar_base + 8u * (uint32_t)(S + (s)))
 #define TFULL_BAR(a) (bar_base + 8u * (uint32_t)(2 * S + (a)))
@@ -420,35 +433,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int co = n & blk_mask;
         return (valid && co + 8 <= cout) ? (pix + pp) * channels + out_coff + co : (int64_t)-1;
       };
-      // Residual rows (RES kernels only).  residual0 of a whole 128-column batch is prefetched BEFORE waiting for the
-      // accumulator, so its DRAM latency overlaps the MMAs of this tile; the second residual (Darknet decoder only,
-      // compute-bound layers) is fetched one chunk ahead.
-      int4 rb0[RES ? 16 : 1], r1[4];
-      auto load_r0_batch = [&](int cs) {
+      // Residual rows (RES kernels only).  residual0 of a 128-column batch is copied global -> shared with cp.async
+      // (16 bytes per vector, thread-private slots, zero-fill for out-of-range rows) BEFORE waiting for the accumulator:
+      // no registers are held, the DRAM latency overlaps the MMAs of this tile and the chunk loop stays compact.
+      // The second residual (Darknet decoder only, compute-bound layers) is fetched one chunk ahead.
+      const uint32_t rslot = rstage_base + (uint32_t)grp * 32768u + (uint32_t)(m & 127) * 16u;  // + i * 2048 per vector
+      int4 r0[4], r1[4];
+      const bool res_smem = RES && p.res_smem != 0 && has_r0;
+      auto prefetch_r0 = [&](int cs) {
         if constexpr (RES) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int64_t o = (has_r0 && cs + i * 8 < BN) ? elem_off(n0 + cs + i * 8, res0_channels) : (int64_t)-1;
-            rb0[i] = o >= 0 ? __ldg(reinterpret_cast<const int4*>(res0 + o)) : make_int4(0, 0, 0, 0);
+          if (res_smem) {
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+              const int64_t o = (cs + i * 8 < BN) ? elem_off(n0 + cs + i * 8, res0_channels) : (int64_t)-1;
+              cp_async16(rslot + (uint32_t)i * 2048u, res0 + (o >= 0 ? o : 0), o >= 0);
+            }
+            cp_async_commit();
           }
         }
       };
-      auto load_r1 = [&](int c) {
+      auto load_r1 = [&](int c) {   // register path: residual1, and residual0 when it is not staged through smem
         if constexpr (RES) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int64_t o = has_r1 ? elem_off(n0 + c + g * 8, res1_channels) : (int64_t)-1;
             r1[g] = o >= 0 ? __ldg(reinterpret_cast<const int4*>(res1 + o)) : make_int4(0, 0, 0, 0);
+            if (has_r0 && !res_smem) {
+              const int64_t o0 = elem_off(n0 + c + g * 8, res0_channels);
+              r0[g] = o0 >= 0 ? __ldg(reinterpret_cast<const int4*>(res0 + o0)) : make_int4(0, 0, 0, 0);
+            }
           }
         }
       };
-      load_r0_batch(0);
-      if (has_r1) load_r1(0);
+      const bool reg_res = RES && (has_r1 || (has_r0 && !res_smem));
+      prefetch_r0(0);
+      if (reg_res) load_r1(0);
       { DBG_T0; mbar_wait(TFULL_BAR(acc), acc_parity); DBG_ADD(3); }
       const unsigned long long _te = dbg ? clk() : 0ull;
       tc_fence_after();
+      if (res_smem) cp_async_wait_all();
       // one 32-column chunk: TMEM -> registers -> 4 output vectors, handed to `sink(g, vector)`
-      auto chunk = [&](int cc, const int4* r0v, auto&& sink) {
+      auto chunk = [&](int cc, auto&& sink) {
         uint32_t v[32];
         if (cc + 32 <= BN) {
           tmem_ld32(t_row + (uint32_t)cc, v);
@@ -459,11 +484,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0u; }
         }
         tmem_ld_wait();
+        if constexpr (RES) {
+          if (res_smem && cc > 0 && (cc & 127) == 0) { prefetch_r0(cc); cp_async_wait_all(); }  // next 128-column batch
+        }
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          sink(g, epilogue_vec8<T>(v + g * 8, bias_s + n0 + cc + g * 8, slope, RES && has_r0, r0v[RES ? g : 0],
-                                   RES && has_r1, r1[g]));
-        if (RES && has_r1 && cc + 32 < BN) load_r1(cc + 32);
+        for (int g = 0; g < 4; ++g) {
+          int4 r0v = make_int4(0, 0, 0, 0);
+          if constexpr (RES) { r0v = res_smem ? ld_shared_v4(rslot + (uint32_t)(((cc & 127) >> 3) + g) * 2048u) : r0[g]; }
+          sink(g, epilogue_vec8<T>(v + g * 8, bias_s + n0 + cc + g * 8, slope, RES && has_r0, r0v, RES && has_r1, r1[g]));
+        }
+        if (reg_res && cc + 32 < BN) load_r1(cc + 32);
       };
       if (out_f32) {
         // float32 logits (conv14 / head): cout <= 32 columns of interest, plain stores
@@ -483,7 +513,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       } else if (tma_store) {
         // ---- TMEM -> registers -> swizzled smem tile -> TMA bulk tensor store (full lines, edges clipped by TMA) ----
         // blocks of 64 channels (128-byte rows, SWIZZLE_128B)
-        auto store_block = [&](int cb, uint32_t buf) {
+        for (int cb = 0; cb < BN; cb += 64, ++blk) {
+          const uint32_t buf = cstage_base + (uint32_t)(grp * 2 + (int)(blk & 1u)) * c_stage_bytes;
+          const uint32_t row_addr = buf + (uint32_t)(m * 128);
+#pragma unroll 1
+          for (int ci = 0; ci < 2; ++ci)
+            chunk(cb + ci * 32, [&](int g, const int4& o) {
+              st_shared_v4(row_addr + (uint32_t)(((ci * 4 + g) ^ (m & 7)) << 4), o); });
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> visible to the TMA engine
           { DBG_T0; if (issuer) bulk_wait_read0(); DBG_ADD(4); }   // previous store of this group finished reading the OTHER buffer
           { DBG_T0; group_barrier(bar_id); DBG_ADD(5); }
@@ -494,55 +530,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             else tma_store_4d(&map_c, buf, c0, wt * BW, ht * BH, b);
             bulk_commit();
           }
-        };
-        if constexpr (RES) {
-          for (int cs = 0; cs < BN; cs += 128) {
-            if (cs > 0) load_r0_batch(cs);
-#pragma unroll
-            for (int bi = 0; bi < 2; ++bi) {
-              const int cb = cs + bi * 64;
-              if (cb < BN) {
-                const uint32_t buf = cstage_base + (uint32_t)(grp * 2 + (int)(blk & 1u)) * c_stage_bytes;
-                const uint32_t row_addr = buf + (uint32_t)(m * 128);
-#pragma unroll
-                for (int ci = 0; ci < 2; ++ci)
-                  chunk(cb + ci * 32, rb0 + bi * 8 + ci * 4, [&](int g, const int4& o) {
-                    st_shared_v4(row_addr + (uint32_t)(((ci * 4 + g) ^ (m & 7)) << 4), o); });
-                store_block(cb, buf);
-                ++blk;
-              }
-            }
-          }
-        } else {
-          for (int cb = 0; cb < BN; cb += 64, ++blk) {
-            const uint32_t buf = cstage_base + (uint32_t)(grp * 2 + (int)(blk & 1u)) * c_stage_bytes;
-            const uint32_t row_addr = buf + (uint32_t)(m * 128);
-#pragma unroll 1
-            for (int ci = 0; ci < 2; ++ci)
-              chunk(cb + ci * 32, rb0, [&](int g, const int4& o) {
-                st_shared_v4(row_addr + (uint32_t)(((ci * 4 + g) ^ (m & 7)) << 4), o); });
-            store_block(cb, buf);
-          }
         }
       } else {
         // ---- direct 16-byte stores (N tiles narrower than 64 channels per pixel) ----
-        auto direct = [&](int c, const int4* r0v) {
-          chunk(c, r0v, [&](int g, const int4& o) {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32)
+          chunk(c, [&](int g, const int4& o) {
             const int64_t off = (c + g * 8 < BN) ? elem_off(n0 + c + g * 8, out_channels) : (int64_t)-1;
             if (off >= 0) *reinterpret_cast<int4*>(outp + off) = o;
           });
-        };
-        if constexpr (RES) {
-          for (int cs = 0; cs < BN; cs += 128) {
-            if (cs > 0) load_r0_batch(cs);
-#pragma unroll
-            for (int ci = 0; ci < 4; ++ci)
-              if (cs + ci * 32 < BN) direct(cs + ci * 32, rb0 + ci * 4);
-          }
-        } else {
-#pragma unroll 1
-          for (int c = 0; c < BN; c += 32) direct(c, rb0);
-        }
       }
       tc_fence_before();
       __syncwarp();
@@ -703,7 +699,8 @@ int Net::tc_prepare() {
       const int all_w_ = cp.ntaps * q.kchunks * btile_;
       const bool resident_ = tc_resident_mode && q.n_nt == 1 && all_w_ <= 112 * 1024;
       const int st_ = (130 * q.KC * 2 + 1023) / 1024 * 1024 + (resident_ ? 0 : 3 * btile_);
-      if ((max_smem - 2048 - 65536 - cp.cout_pad * 4 - (resident_ ? all_w_ + 1024 : 0)) / st_ < 4) halo = false;
+      const int staging_ = 65536 + ((L.res0 >= 0 && q.BN <= 128) ? 65536 : 0);
+      if ((max_smem - 2048 - staging_ - cp.cout_pad * 4 - (resident_ ? all_w_ + 1024 : 0)) / st_ < 3) halo = false;
     }
     if (G > 1 && cp.mode != MODE_1x1 && !halo) {  // the banded issue of a 3-tap row needs the halo tile
       delete plan;
@@ -756,7 +753,10 @@ int Net::tc_prepare() {
       q.cbw = q.BN < 64 ? q.BN : 64;
       q.c_stage_bytes = (128 * q.cbw * 2 + 1023) / 1024 * 1024;
     }
-    const int cstage_total = q.tma_store ? 4 * q.c_stage_bytes : 0;
+    // residual0 is staged through smem only for the memory-bound layers (N tile <= 128): the wide Darknet layers are
+    // tensor-bound and keep their smem for pipeline stages
+    q.res_smem = (L.res0 >= 0 && q.BN <= 128) ? 1 : 0;
+    const int cstage_total = (q.tma_store ? 4 * q.c_stage_bytes : 0) + (q.res_smem ? 65536 : 0);
     // pipeline depth; weights stay resident in smem when the whole layer fits next to >= 4 stages
     q.a_bytes = (q.a_rows * q.KC * 2 + 1023) / 1024 * 1024;
     q.b_tile_bytes = G > 1 ? cp.cout_pad * cin_blk * 2 : q.BN * q.KC * 2;
