@@ -273,16 +273,20 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
   constexpr int TW = 256 / CV;       // columns per CTA (32 or 16)
   constexpr int ROWV = (TW + 6) * CV;  // vectors per staged row
   constexpr int LPT = (ROWV + 255) / 256;
-  __shared__ int4 rowbuf[2][ROWV];
-  __shared__ float w1s[C * R], w2s[R * C], b1s[R], b2s[C];
-  // bank-conflict-free layouts: the CV lanes of a pixel read consecutive words, lanes of other pixels broadcast
-  //   w1s[(k * R + j) * CV + cv] = W1[cv * 8 + k][j],  w2s[(j * 8 + k) * CV + cv] = W2[j][cv * 8 + k],  b2s[k * CV + cv]
+  constexpr int NB = 5, DIST = 3;  // cp.async ring: rows r+1..r+3 in flight while row r is processed
+  __shared__ int4 rowbuf[NB][ROWV];
+  // weights in shared memory, laid out so that a thread fetches its 8 x R squeeze weights / R x 8 excitation weights
+  // with 128-bit loads: per-cv blocks of 8*R floats, padded by 4 floats so that the quarter-warp's 16-byte accesses hit
+  // distinct banks (lanes of another pixel with the same cv broadcast)
+  //   w1s[cv * WS + k * R + j] = W1[cv * 8 + k][j]      w2s[cv * WS + j * 8 + k] = W2[j][cv * 8 + k]
+  constexpr int WS = 8 * R + 4;
+  __shared__ __align__(16) float w1s[CV * WS], w2s[CV * WS], b1s[R], b2s[C];
   for (int i = threadIdx.x; i < C * R; i += 256) {
-    { const int ch = i / R, j = i % R; w1s[((ch % 8) * R + j) * CV + ch / 8] = p.w1[i]; }
-    { const int j = i / C, ch = i % C; w2s[(j * 8 + ch % 8) * CV + ch / 8] = p.w2[i]; }
+    { const int ch = i / R, j = i % R; w1s[(ch / 8) * WS + (ch % 8) * R + j] = p.w1[i]; }
+    { const int j = i / C, ch = i % C; w2s[(ch / 8) * WS + j * 8 + (ch % 8)] = p.w2[i]; }
   }
   for (int i = threadIdx.x; i < R; i += 256) b1s[i] = p.b1[i];
-  for (int i = threadIdx.x; i < C; i += 256) b2s[(i % 8) * CV + i / 8] = p.b2[i];
+  for (int i = threadIdx.x; i < C; i += 256) b2s[i] = p.b2[i];
 
   const int w0 = blockIdx.x * TW;
   const int64_t b = blockIdx.y;
@@ -291,25 +295,25 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
   const int cv = threadIdx.x % CV, c = threadIdx.x / CV;  // this thread's column (0..TW-1) and channel vector
   const int4 NEG = neg_inf8<T>();
 
-  // prefetch registers for the next staged row
-  int4 pre[LPT];
-  auto fetch = [&](int r) {
+  // stage input row r into ring slot r % NB: in-image vectors travel global -> shared with cp.async (no registers,
+  // DIST rows in flight), padding (outside the image) is written as -inf so that it never wins the max
+  auto stage_row = [&](int r) {
+    int4* dst = rowbuf[((r % NB) + NB) % NB];
 #pragma unroll
     for (int k = 0; k < LPT; ++k) {
       const int i = threadIdx.x + k * 256;
-      pre[k] = NEG;
-      if (i < ROWV && r >= 0 && r < H) {
+      if (i < ROWV) {
         const int col = w0 - 3 + i / CV;
-        if (col >= 0 && col < W) pre[k] = __ldg(img + ((int64_t)r * W + col) * CV + (i % CV));
+        if (r >= 0 && r < H && col >= 0 && col < W) {
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + i);
+          const int4* src = img + ((int64_t)r * W + col) * CV + (i % CV);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
+        } else {
+          dst[i] = NEG;
+        }
       }
     }
-  };
-  auto stage = [&](int buf) {
-#pragma unroll
-    for (int k = 0; k < LPT; ++k) {
-      const int i = threadIdx.x + k * 256;
-      if (i < ROWV) rowbuf[buf][i] = pre[k];
-    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
   int4 win[7];   // horizontal maxima of the last seven input rows (oldest first)
@@ -319,13 +323,13 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
 #pragma unroll
   for (int k = 0; k < 4; ++k) xr[k] = NEG;
 
-  fetch(-3 + 3);  // first staged row is input row 0 (rows -3..-1 are padding and already -inf in the window)
-  stage(0);
-  __syncthreads();
+  for (int r = 0; r < DIST; ++r) stage_row(r);  // rows -3..-1 are padding and already -inf in the window
   const bool col_ok = (w0 + c) < W;
   for (int r = 0; r < H + 3; ++r) {          // r = newest input row in the window; output row o = r - 3
-    const int buf = r & 1;
-    if (r + 1 < H + 3) fetch(r + 1);        // rows >= H come back as -inf
+    const int buf = r % NB;
+    stage_row(r + DIST);                     // rows >= H are written as -inf
+    asm volatile("cp.async.wait_group %0;" ::"n"(DIST) : "memory");   // row r has landed (this thread's copies)
+    __syncthreads();                         // ... and everybody else's; also fences the slot reused by stage_row(r + DIST + 1)
     // horizontal 7-max of row r at this column: staged columns c .. c+6 (c+3 is the centre)
     int4 hm = rowbuf[buf][(c + 0) * CV + cv];
 #pragma unroll
@@ -350,11 +354,18 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
       }
       float sq[R];
 #pragma unroll
-      for (int j = 0; j < R; ++j) {
-        float a = 0.0f;
+      for (int j = 0; j < R; ++j) sq[j] = 0.0f;
+      const float4* w1v = reinterpret_cast<const float4*>(w1s + cv * WS);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) a = fmaf(pooled[k], w1s[(k * R + j) * CV + cv], a);
-        sq[j] = a;
+      for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int jj = 0; jj < R / 4; ++jj) {
+          const float4 wv = w1v[k * (R / 4) + jj];
+          sq[jj * 4 + 0] = fmaf(pooled[k], wv.x, sq[jj * 4 + 0]);
+          sq[jj * 4 + 1] = fmaf(pooled[k], wv.y, sq[jj * 4 + 1]);
+          sq[jj * 4 + 2] = fmaf(pooled[k], wv.z, sq[jj * 4 + 2]);
+          sq[jj * 4 + 3] = fmaf(pooled[k], wv.w, sq[jj * 4 + 3]);
+        }
       }
 #pragma unroll
       for (int off = CV / 2; off >= 1; off >>= 1)
@@ -365,18 +376,20 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
       if (col_ok) {
         float x[8];
         unpack8<T>(xr[0], x);
+        const float4* w2v = reinterpret_cast<const float4*>(w2s + cv * WS);
+        const float4 bb0 = *reinterpret_cast<const float4*>(b2s + cv * 8), bb1 = *reinterpret_cast<const float4*>(b2s + cv * 8 + 4);
+        float e[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float e = b2s[k * CV + cv];
-#pragma unroll
-          for (int j = 0; j < R; ++j) e = fmaf(sq[j], w2s[(j * 8 + k) * CV + cv], e);
-          x[k] *= __frcp_rn(1.0f + __expf(-e));
+        for (int j = 0; j < R; ++j) {
+          const float4 wa = w2v[j * 2], wb = w2v[j * 2 + 1];
+          e[0] = fmaf(sq[j], wa.x, e[0]); e[1] = fmaf(sq[j], wa.y, e[1]); e[2] = fmaf(sq[j], wa.z, e[2]); e[3] = fmaf(sq[j], wa.w, e[3]);
+          e[4] = fmaf(sq[j], wb.x, e[4]); e[5] = fmaf(sq[j], wb.y, e[5]); e[6] = fmaf(sq[j], wb.z, e[6]); e[7] = fmaf(sq[j], wb.w, e[7]);
         }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = __fdividef(x[k], 1.0f + __expf(-e[k]));  // sigmoid gate (MUFU ex2 + rcp)
         oimg[((int64_t)o * W + (w0 + c)) * CV + cv] = pack8<T>(x);
       }
     }
-    stage(buf ^ 1);
-    __syncthreads();
   }
 }
 
