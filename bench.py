@@ -279,17 +279,25 @@ def run_ours(args):
     del lid, msk
   e2e_steps = max(3, min(args.steps, 20))
 
-  def e2e_step(i):
+  def e2e_issue(i):
     lidar, mask = host_inputs[i % 2]
-    probabilities, predictions = model([lidar, mask])      # H2D inside
-    return predictions.numpy()                             # D2H (synchronises)
+    probabilities, predictions = model([lidar, mask])      # H2D (copy stream) + forward, asynchronous
+    return predictions
 
-  for i in range(2):
-    e2e_step(i)
+  def e2e_run(n):
+    # the call a user makes, double-buffered: batch i+1 is submitted before batch i's predictions are read back, so
+    # its upload overlaps batch i's kernels; EVERY step's predictions are copied to the host (predictions.numpy())
+    pending = e2e_issue(0)
+    for i in range(1, n):
+      nxt = e2e_issue(i)
+      pending.numpy()                                     # D2H (synchronises on batch i-1)
+      pending = nxt
+    pending.numpy()
+
+  e2e_run(2)
   barrier()
   t0 = time.perf_counter()
-  for i in range(e2e_steps):
-    e2e_step(i)
+  e2e_run(e2e_steps)
   barrier()
   e2e_s = time.perf_counter() - t0
   t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -297,7 +305,7 @@ def run_ours(args):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
   e2e = {"value": world * B * e2e_steps / float(t.item()), "unit": "frames/s",
          "h2d_bytes_per_step": B * H * W * (6 * 4 + 1), "d2h_bytes_per_step": B * H * W * 4,
-         "call": "model([lidar, mask]) -> predictions.numpy(), pinned host inputs, %d steps" % e2e_steps}
+         "call": "model([lidar, mask]) -> predictions.numpy(), pinned host inputs, double-buffered, %d steps" % e2e_steps}
 
   if rank != 0:
     if world > 1:

@@ -173,6 +173,12 @@ struct TcParams {
   const void* res1;
   int res0_channels, res1_channels;
   const float* bias;
+  // fused segmentation head (final conv only): softmax -> argmax -> mask; any of logits/probs may be NULL
+  int head, none_index;
+  const uint8_t* mask;
+  float* probs;
+  int32_t* preds;
+  float* logits;
   unsigned long long* dbg;    // optional [gridDim.x][16] cycle counters (pcls_net_set_option "tc_debug")
 };
 
@@ -241,6 +247,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* bias_s = reinterpret_cast<float*>(smem_raw + (((tmem_slot + 16u + 15u) & ~15u) - smem_u32(smem_raw)));  // [n_nt * BN], 16-byte aligned
   for (int i = threadIdx.x; i < p.n_nt * p.BN; i += blockDim.x) bias_s[i] = p.bias[G > 1 ? i % p.cout_blk : i];
+  float* head_s = bias_s + ((p.n_nt * p.BN + 3) & ~3);  // [8 warps][32][33] staging of the fused head (out_f32 layers)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned long long* const dbg = p.dbg;
@@ -496,19 +503,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (reg_res && cc + 32 < BN) load_r1(cc + 32);
       };
       if (out_f32) {
-        // float32 logits (conv14 / head): cout <= 32 columns of interest, plain stores
-        float* o = reinterpret_cast<float*>(p.out) + pix * out_channels + out_coff;
-        for (int c = 0; c < BN; c += 16) {
-          uint32_t v[16];
-          tmem_ld16(t_row + (uint32_t)c, v);
-          tmem_ld_wait();
-          if (valid) {
+        // float32 logits (conv14 / head layer), cout <= 32.  With the fused head the softmax / argmax / mask of
+        // nets/SegmentationNetwork.py:58-69 run here on the accumulator registers: logits never travel to HBM unless
+        // the caller asks for them.  Each warp stages 32 pixels x cout floats in smem so that global stores are coalesced.
+        float lg[32];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int co = n0 + c + j;
-              if (co < cout) { const float x = __uint_as_float(v[j]) + bias_s[co]; o[co] = fmaxf(x, x * slope); }
-            }
+        for (int c = 0; c < 32; c += 16) {
+          uint32_t v[16];
+          if (c < BN) { tmem_ld16(t_row + (uint32_t)c, v); tmem_ld_wait(); }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x = (c < BN && c + j < cout) ? __uint_as_float(v[j]) + bias_s[n0 + c + j] : 0.0f;
+            lg[c + j] = fmaxf(x, x * slope);
           }
+        }
+        float* stg = head_s + (warp - 2) * (32 * 33);
+        const int64_t pix0 = __shfl_sync(0xffffffffu, pix, 0);      // pixels of a warp are consecutive in memory
+        const int n_valid = __popc(__ballot_sync(0xffffffffu, valid));
+        auto write_rows = [&](float* dst) {                          // lg[] of 32 pixels -> dst[pix0*cout ..] coalesced
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) if (c < cout) stg[lane * 33 + c] = lg[c];
+          __syncwarp();
+          const int n_el = n_valid * cout;
+          int px = lane / cout, cc = lane - px * cout;               // (pixel, class) of element `lane`, advanced by 32
+          const int dpx = 32 / cout, dcc = 32 - dpx * cout;
+          for (int e = lane; e < n_el; e += 32) {
+            dst[pix0 * cout + e] = stg[px * 33 + cc];
+            px += dpx; cc += dcc;
+            if (cc >= cout) { cc -= cout; ++px; }
+          }
+        };
+        if (!p.head) {
+          if (valid) {
+            float* o = reinterpret_cast<float*>(p.out) + pix * out_channels + out_coff;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) if (c < cout) o[c] = lg[c];
+          }
+        } else {
+          if (p.logits) write_rows(p.logits);
+          int best = softmax_argmax<32>(lg, cout);                   // lg[] now holds the probabilities
+          if (valid) {
+            if (p.mask[pix] == 0) best = p.none_index;
+            p.preds[pix] = best;
+          }
+          if (p.probs) write_rows(p.probs);
         }
       } else if (tma_store) {
         // ---- TMEM -> registers -> swizzled smem tile -> TMA bulk tensor store (full lines, edges clipped by TMA) ----
@@ -765,12 +804,12 @@ int Net::tc_prepare() {
     q.bres_bytes = q.b_resident ? (all_w + 1023) / 1024 * 1024 : 0;
     if (G > 1 && !q.b_resident) { delete plan; set_error("internal: pixel-group plan needs resident weights"); return PCLS_ERR_STATE; }
     const int stage_bytes = q.a_bytes + (q.b_resident ? 0 : q.sub * q.b_tile_bytes);
-    int stages = (max_smem - 2048 - cp.cout_pad * 4 - q.bres_bytes - cstage_total) / stage_bytes;
+    int stages = (max_smem - 2048 - cp.cout_pad * 4 - q.bres_bytes - cstage_total - (cp.out_f32 ? 8 * 32 * 33 * 4 : 0)) / stage_bytes;
     if (stages > 12) stages = 12;
     if (stages < 2) { delete plan; continue; }
     q.stages = stages;
     plan->smem_bytes = (size_t)stages * stage_bytes + q.bres_bytes + cstage_total + 1024 /*alignment slack*/ +
-                       (size_t)(2 * stages + 17) * 8 + 48 + (size_t)cp.cout_pad * 4 /*bias*/;
+                       (size_t)(2 * stages + 17) * 8 + 48 + (cp.out_f32 ? 8 * 32 * 33 * 4 : 0) + (size_t)cp.cout_pad * 4 /*bias*/;
     // descriptors
     const uint32_t layout = swz == 128 ? 2u : swz == 64 ? 4u : 6u;  // UMMA LayoutType
     const uint32_t sbo = (uint32_t)(8 * swz) >> 4;                   // 8 rows of one swizzle span
@@ -859,6 +898,9 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
   TcParams prm = plan->prm;
   prm.out = p.out; prm.res0 = p.res0; prm.res1 = p.res1;
   prm.dbg = tc_debug_buf;
+  prm.head = (prm.out_f32 && head_args.head) ? 1 : 0;
+  prm.none_index = head_args.none_index; prm.mask = head_args.mask;
+  prm.probs = head_args.probs; prm.preds = head_args.preds; prm.logits = head_args.logits;
   const int num_tiles = prm.num_tiles * nb;
   if (num_tiles == 0) return PCLS_OK;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();

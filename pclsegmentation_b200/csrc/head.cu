@@ -4,32 +4,12 @@
 // HBM-bound: NC*4 B read + 4 B written per pixel (+ NC*4 B when probabilities are materialised).
 // Each warp stages 32 pixels x NC logits through shared memory so that global loads and the
 // probability stores are fully coalesced 128-byte transactions; one lane then owns one pixel.
-#include "common.cuh"
+#include "nn_kernels.cuh"
 
 namespace pcls {
 
 constexpr int HEAD_MAX_NC = 32;
 constexpr int HEAD_WARPS = 8;
-
-// Shared by the standalone head and the fused conv epilogues: softmax over v[0..nc), argmax over the
-// rounded float32 probabilities (first index wins ties, like tf.argmax), mask fill.
-template <int MAXNC>
-__device__ __forceinline__ int softmax_argmax(float (&v)[MAXNC], int nc) {
-  float m = v[0];
-#pragma unroll
-  for (int c = 1; c < MAXNC; ++c) if (c < nc) m = fmaxf(m, v[c]);
-  float s = 0.0f;
-#pragma unroll
-  for (int c = 0; c < MAXNC; ++c) if (c < nc) { v[c] = expf(v[c] - m); s += v[c]; }
-  int best = 0;
-  float bp = -1.0f;
-#pragma unroll
-  for (int c = 0; c < MAXNC; ++c) if (c < nc) {
-    v[c] = __fdiv_rn(v[c], s);
-    if (v[c] > bp) { bp = v[c]; best = c; }
-  }
-  return best;
-}
 
 __global__ void __launch_bounds__(HEAD_WARPS * 32)
 head_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ mask, int64_t n_pixels, int nc,

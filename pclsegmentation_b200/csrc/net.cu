@@ -414,6 +414,7 @@ int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool ra
   int rc = launch_net_input<T>(lidar, channels, mask, raw, mean5, std5, n_pixels, (T*)tensor_ptr(0, nb), mask_buf, s);
   if (rc) return rc;
   float* logits_buf = logits ? logits : (float*)tensor_ptr(logits_tensor, nb);
+  bool head_done = false;
   for (const OpRef& op : ops) {
     if (ev) cudaEventRecord(ev[evi++], s);
     if (op.type == OP_CONV) {
@@ -424,6 +425,13 @@ int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool ra
       p.res0 = L.res0 >= 0 ? tensor_ptr(L.res0, nb) : nullptr;
       p.res1 = L.res1 >= 0 ? tensor_ptr(L.res1, nb) : nullptr;
       if (conv_impl == 0 && L.tc_ok) {
+        // the final conv can run the segmentation head in its epilogue (every 32-pixel warp row must be contiguous
+        // in memory: full-width tiles of 128 pixels)
+        const bool fuse = fuse_head && L.out == logits_tensor && (W % 128 == 0);
+        head_args.head = fuse ? 1 : 0;
+        head_args.none_index = none_index; head_args.mask = mask_buf;
+        head_args.probs = probs; head_args.preds = preds; head_args.logits = logits;
+        head_done = head_done || fuse;
         if (L.pair_view) {  // same buffers, re-viewed geometry
           ConvParams pv = L.ptc;
           pv.in = p.in; pv.out = p.out; pv.res0 = p.res0; pv.res1 = p.res1;
@@ -456,7 +464,7 @@ int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool ra
     }
   }
   if (ev) cudaEventRecord(ev[evi++], s);
-  rc = launch_head(logits_buf, mask_buf, n_pixels, num_classes, none_index, probs, preds, s);
+  rc = head_done ? PCLS_OK : launch_head(logits_buf, mask_buf, n_pixels, num_classes, none_index, probs, preds, s);
   if (ev) cudaEventRecord(ev[evi++], s);
   return rc;
 }
@@ -732,6 +740,7 @@ extern "C" int pcls_net_set_option(pcls_net* net, const char* name, int value) {
   if (!strcmp(name, "tc_halo")) { tc_halo_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_tma_store")) { tc_tma_store_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_group")) { tc_group_mode = value; return PCLS_OK; }
+  if (!strcmp(name, "fuse_head")) { n->fuse_head = value != 0; n->drop_graphs(); return PCLS_OK; }
   if (!strcmp(name, "tc_debug")) {  // per-role wait-cycle counters of conv_tc_kernel (development aid)
     if (value && !tc_debug_buf) { PCLS_CHECK_CUDA(cudaMalloc(&tc_debug_buf, 148 * 24 * 8)); PCLS_CHECK_CUDA(cudaMemset(tc_debug_buf, 0, 148 * 24 * 8)); }
     if (!value && tc_debug_buf) { cudaFree(tc_debug_buf); tc_debug_buf = nullptr; }

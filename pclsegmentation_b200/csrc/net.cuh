@@ -63,6 +63,8 @@ struct Net {
   // execution knobs
   int conv_impl = 0;
   bool use_graph = true;
+  bool fuse_head = true;   // run softmax/argmax/mask in the epilogue of the final convolution (tcgen05 path)
+  struct HeadArgs { int head = 0, none_index = 0; const uint8_t* mask = nullptr; float* probs = nullptr; int32_t* preds = nullptr; float* logits = nullptr; } head_args;
   int micro_batch = 0;
   // device state
   int frames_per_pass = 0;

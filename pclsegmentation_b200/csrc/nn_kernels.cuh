@@ -55,6 +55,27 @@ template <typename T> int launch_tensor_to_f32(const T* in, float* out, int64_t 
 int launch_head(const float* logits, const uint8_t* mask, int64_t n_pixels, int nc, int none_index, float* probs,
                 int32_t* preds, cudaStream_t s);
 
+// ---- segmentation head arithmetic ----
+// Shared by the standalone head and the fused conv epilogues: softmax over v[0..nc), argmax over the
+// rounded float32 probabilities (first index wins ties, like tf.argmax), mask fill.
+template <int MAXNC>
+__device__ __forceinline__ int softmax_argmax(float (&v)[MAXNC], int nc) {
+  float m = v[0];
+#pragma unroll
+  for (int c = 1; c < MAXNC; ++c) if (c < nc) m = fmaxf(m, v[c]);
+  float s = 0.0f;
+#pragma unroll
+  for (int c = 0; c < MAXNC; ++c) if (c < nc) { v[c] = expf(v[c] - m); s += v[c]; }
+  int best = 0;
+  float bp = -1.0f;
+#pragma unroll
+  for (int c = 0; c < MAXNC; ++c) if (c < nc) {
+    v[c] = __fdiv_rn(v[c], s);
+    if (v[c] > bp) { bp = v[c]; best = c; }
+  }
+  return best;
+}
+
 // 16-bit <-> float helpers
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }

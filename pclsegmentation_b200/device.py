@@ -26,13 +26,34 @@ def stream_handle():
   return torch.cuda.current_stream().cuda_stream
 
 
+_copy_streams = {}
+
+
+def _h2d(t, dev):
+  """Pinned host tensor -> device on a dedicated copy stream; the compute stream only waits on the copy's event, so the
+  upload of batch i+1 overlaps the kernels of batch i when the caller issues model(batch i+1) before reading batch i."""
+  cs = _copy_streams.get(dev.index)
+  if cs is None:
+    cs = _copy_streams[dev.index] = torch.cuda.Stream(device=dev)
+  main = torch.cuda.current_stream(dev)
+  with torch.cuda.stream(cs):
+    d = t.to(dev, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(cs)
+  main.wait_event(ev)
+  d.record_stream(main)
+  _h2d.last_event = ev
+  return d
+
+
 def to_device(x, dtype, pinned_cache=None, key=None):
   """numpy array / torch tensor -> contiguous CUDA tensor of `dtype` (async H2D through pinned memory)."""
   dev = require_cuda()
   if torch.is_tensor(x):
     if x.is_cuda:
       return x.to(dtype).contiguous()
-    return x.to(dtype).contiguous().pin_memory().to(dev, non_blocking=True)
+    x = x.to(dtype).contiguous()
+    return _h2d(x if x.is_pinned() else x.pin_memory(), dev)
   a = np.ascontiguousarray(x)
   t = torch.from_numpy(a)
   if t.dtype != dtype:
@@ -42,20 +63,53 @@ def to_device(x, dtype, pinned_cache=None, key=None):
     if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
       buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
       pinned_cache[key] = buf
+    busy = pinned_cache.get((key, "event"))
+    if busy is not None:
+      busy.synchronize()          # the previous upload out of this staging buffer must have finished
     buf.copy_(t)
-    t = buf
-  else:
-    t = t.pin_memory()
-  return t.to(dev, non_blocking=True)
+    d = _h2d(buf, dev)
+    pinned_cache[(key, "event")] = _h2d.last_event
+    return d
+  t = t.pin_memory()
+  return _h2d(t, dev)
+
+
+_d2h_streams = {}
+_d2h_pinned = {}
 
 
 class DeviceTensor(torch.Tensor):
   """A CUDA tensor whose ``.numpy()`` performs the device->host copy, so reference code written against TF
-  eager tensors (``predictions.numpy()[0]``, inference.py:78) works unchanged."""
+  eager tensors (``predictions.numpy()[0]``, inference.py:78) works unchanged.
+
+  The copy runs on a dedicated D2H stream that waits only for the event recorded after the forward that produced
+  this tensor - not for work queued later on the compute stream - so a caller that submits batch i+1 before reading
+  batch i keeps the GPU busy (upload, kernels and read-back of three consecutive batches overlap)."""
 
   def numpy(self):  # noqa: D401
-    return self.detach().as_subclass(torch.Tensor).cpu().numpy()
+    t = self.detach().as_subclass(torch.Tensor)
+    ev = getattr(self, "_pcls_ready", None)
+    if ev is None or not t.is_cuda:
+      return t.cpu().numpy()
+    dev = t.device
+    ds = _d2h_streams.get(dev.index)
+    if ds is None:
+      ds = _d2h_streams[dev.index] = torch.cuda.Stream(device=dev)
+    key = (dev.index, tuple(t.shape), t.dtype)
+    host = _d2h_pinned.get(key)
+    if host is None:
+      host = _d2h_pinned[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    ds.wait_event(ev)
+    with torch.cuda.stream(ds):
+      host.copy_(t, non_blocking=True)
+      done = torch.cuda.Event()
+      done.record(ds)
+    t.record_stream(ds)
+    done.synchronize()
+    return host.numpy().copy()
 
 
-def wrap(t):
-  return t.as_subclass(DeviceTensor)
+def wrap(t, ready_event=None):
+  w = t.as_subclass(DeviceTensor)
+  w._pcls_ready = ready_event
+  return w

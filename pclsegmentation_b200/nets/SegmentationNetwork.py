@@ -183,7 +183,9 @@ class PCLSegmentationNetwork:
                     else torch.bool, self._pinned, "mask")
       m = m.reshape(lidar.shape[0], lidar.shape[1], lidar.shape[2])  # tf.squeeze(lidar_mask) semantics
     res = self.forward_device(lidar, m)
-    return wrap(res["probabilities"]), wrap(res["predictions"])
+    ready = torch.cuda.Event()
+    ready.record(torch.cuda.current_stream())
+    return wrap(res["probabilities"], ready), wrap(res["predictions"], ready)
 
   def predict_step(self, data):
     (lidar_input, lidar_mask), _, _ = data
