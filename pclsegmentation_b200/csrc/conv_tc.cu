@@ -542,7 +542,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         } else {
           if (p.logits) write_rows(p.logits);
-          int best = softmax_argmax<32>(lg, cout);                   // lg[] now holds the probabilities
+          // softmax with SFU exponentials and one reciprocal (<= 2 ulp from the standalone head's expf / IEEE division),
+          // argmax over the rounded probabilities, first index on ties
+          float mx = lg[0];
+#pragma unroll
+          for (int c = 1; c < 32; ++c) if (c < cout) mx = fmaxf(mx, lg[c]);
+          float sum = 0.0f;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) if (c < cout) { lg[c] = exp2f((lg[c] - mx) * 1.4426950408889634f); sum += lg[c]; }
+          const float inv = __fdividef(1.0f, sum);
+          int best = 0;
+          float bp = -1.0f;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) if (c < cout) { lg[c] *= inv; if (lg[c] > bp) { bp = lg[c]; best = c; } }
           if (valid) {
             if (p.mask[pix] == 0) best = p.none_index;
             p.preds[pix] = best;
