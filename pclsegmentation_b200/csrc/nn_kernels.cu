@@ -204,46 +204,52 @@ __device__ __forceinline__ int4 max8(const int4& a, const int4& b) {
   return r;
 }
 
+template <typename T> __device__ __forceinline__ int4 neg_inf8();
+template <> __device__ __forceinline__ int4 neg_inf8<__half>() { return make_int4(0xFC00FC00, 0xFC00FC00, 0xFC00FC00, 0xFC00FC00); }
+template <> __device__ __forceinline__ int4 neg_inf8<__nv_bfloat16>() { return make_int4(0xFF80FF80, 0xFF80FF80, 0xFF80FF80, 0xFF80FF80); }
+
+// Column-streaming form: a thread owns one output column x 8 channels of one frame and walks down the H rows.  Per
+// input row it takes the horizontal 3-max (three 128-bit loads, two of them shared with the neighbour thread through
+// L1) and keeps the last two row maxima in registers, so every input vector is requested 1.5x instead of 4.5x.
 template <typename T>
 __global__ void __launch_bounds__(256)
-maxpool3x3_s2_kernel(const int4* __restrict__ in, int4* __restrict__ out, int64_t n_vec, int H, int Win, int Wout,
+maxpool3x3_s2_kernel(const int4* __restrict__ in, int4* __restrict__ out, int64_t n_cols, int H, int Win, int Wout,
                      int CV, int pad_left) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
-    const int cv = (int)(i % CV);
-    int64_t r = i / CV;
-    const int wo = (int)(r % Wout); r /= Wout;
-    const int h = (int)(r % H);
-    const int64_t b = r / H;
-    bool have = false;
-    int4 m = make_int4(0, 0, 0, 0);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (frame, wo, cv)
+  if (i >= n_cols) return;
+  const int cv = (int)(i % CV);
+  const int wo = (int)((i / CV) % Wout);
+  const int64_t b = i / ((int64_t)CV * Wout);
+  const int4* img = in + b * H * Win * CV + cv;
+  int4* oimg = out + (b * H * Wout + wo) * CV + cv;
+  const int w_lo = 2 * wo - pad_left;
+  const int4 NEG = neg_inf8<T>();
+  auto hrow = [&](int h) -> int4 {
+    if (h < 0 || h >= H) return NEG;
+    const int4* row = img + (int64_t)h * Win * CV;
+    int4 m = NEG;
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int hi = h + dy;
-      if (hi < 0 || hi >= H) continue;
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int wi = 2 * wo + dx - pad_left;
-        if (wi < 0 || wi >= Win) continue;
-        const int4 v = __ldg(in + ((b * H + hi) * Win + wi) * CV + cv);
-        m = have ? max8<T>(m, v) : v;
-        have = true;
-      }
+    for (int dx = 0; dx < 3; ++dx) {
+      const int wi = w_lo + dx;
+      if (wi >= 0 && wi < Win) m = max8<T>(m, __ldg(row + (int64_t)wi * CV));
     }
-    out[i] = m;
+    return m;
+  };
+  int4 prev = NEG, cur = hrow(0);
+  for (int h = 0; h < H; ++h) {
+    const int4 nxt = hrow(h + 1);
+    oimg[(int64_t)h * Wout * CV] = max8<T>(max8<T>(prev, cur), nxt);
+    prev = cur; cur = nxt;
   }
 }
 
 template <typename T>
 int launch_maxpool3x3_s2(const T* in, T* out, int B, int H, int Win, int Wout, int C, int pad_left, cudaStream_t s) {
   const int CV = C / 8;
-  const int64_t n_vec = (int64_t)B * H * Wout * CV;
-  if (n_vec == 0) return PCLS_OK;
-  int64_t blocks = ceil_div(n_vec, 256);
-  const int64_t cap = (int64_t)sm_count() * 32;
-  if (blocks > cap) blocks = cap;
-  maxpool3x3_s2_kernel<T><<<(int)blocks, 256, 0, s>>>(reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out),
-                                                     n_vec, H, Win, Wout, CV, pad_left);
+  const int64_t n_cols = (int64_t)B * Wout * CV;
+  if (n_cols == 0) return PCLS_OK;
+  maxpool3x3_s2_kernel<T><<<(unsigned)ceil_div(n_cols, 256), 256, 0, s>>>(
+      reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), n_cols, H, Win, Wout, CV, pad_left);
   return check_launch("maxpool3x3_s2_kernel");
 }
 template int launch_maxpool3x3_s2<__half>(const __half*, __half*, int, int, int, int, int, int, cudaStream_t);
@@ -261,10 +267,6 @@ template int launch_maxpool3x3_s2<__nv_bfloat16>(const __nv_bfloat16*, __nv_bflo
 // The two 1x1 convolutions are tiny: partial dot products per 8-channel lane, xor-shuffle reduction over the
 // C/8 lanes of a pixel.
 // --------------------------------------------------------------------------------------------------
-template <typename T> __device__ __forceinline__ int4 neg_inf8();
-template <> __device__ __forceinline__ int4 neg_inf8<__half>() { return make_int4(0xFC00FC00, 0xFC00FC00, 0xFC00FC00, 0xFC00FC00); }
-template <> __device__ __forceinline__ int4 neg_inf8<__nv_bfloat16>() { return make_int4(0xFF80FF80, 0xFF80FF80, 0xFF80FF80, 0xFF80FF80); }
-
 template <typename T, int C>
 __global__ void __launch_bounds__(256)
 cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int H, int W) {
