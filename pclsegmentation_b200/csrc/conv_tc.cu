@@ -101,6 +101,67 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, const int4& v) {
 __device__ __forceinline__ unsigned long long clk() { unsigned long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)); return t; }
 #define DBG_T0 const unsigned long long _t0 = dbg ? clk() : 0ull
 #define DBG_ADD(slot) if (dbg) dbg_acc[slot] += clk() - _t0
+// ---- warp-uniform issue: the WHOLE warp executes these with identical operands, the instruction itself is predicated
+// on elect.sync, so operands stay in uniform registers (issuing from divergent `if (lane == 0)` code makes the compiler
+// wrap every UTCHMMA / UTMALDG in an elect + R2UR loop, ~100 cycles each)
+__device__ __forceinline__ void umma_f16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_elect(uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+      "}" ::"r"(bar), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t"
+      "}" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                                  int c3) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t"
+      "}" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                                  int c3, int c4) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n\t"
+      "}" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -278,19 +339,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int BN = p.BN;
 
   if (warp == 0) {
-    // ===================== TMA producer (one thread) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp, one elected lane issues) =====================
+    {
       if (b_resident) {
         // weight-stationary: every weight tile of the layer once per CTA, laid out in MMA iteration order
         // [phase][group][K chunk][sub] so that the issuer only increments an address
-        mbar_arrive_expect_tx(BRES_BAR, (uint32_t)(n_phase * n_groups * kchunks * SUB) * b_tile_bytes);
+        mbar_arrive_expect_tx_elect(BRES_BAR, (uint32_t)(n_phase * n_groups * kchunks * SUB) * b_tile_bytes);
         uint32_t dst = bres_base;
         for (int ph = 0; ph < n_phase; ++ph)
           for (int g = 0; g < n_groups; ++g)
             for (int kc = 0; kc < kchunks; ++kc)
 #pragma unroll
               for (int u = 0; u < SUB; ++u, dst += b_tile_bytes)
-                tma_load_3d(dst, &map_b, BRES_BAR, kc * KC, 0, p.grp_w[ph][g][u]);
+                tma_load_3d_elect(dst, &map_b, BRES_BAR, kc * KC, 0, p.grp_w[ph][g][u]);
       }
       const uint32_t tx_bytes = (uint32_t)(p.a_rows * KC * 2) + b_stage_bytes;
       const int BW = p.BW, BH = p.BH;
@@ -314,13 +375,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             { DBG_T0; mbar_wait(EMPTY_BAR(stage), phase ^ 1u); DBG_ADD(0); }
             const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
             const uint32_t fb = FULL_BAR(stage);
-            mbar_arrive_expect_tx(fb, tx_bytes);
-            if (is5d) tma_load_5d(a_dst, &map_a, fb, kc * KC, par, ww, hh, b);
-            else tma_load_4d(a_dst, &map_a, fb, kc * KC, ww, hh, b);
+            mbar_arrive_expect_tx_elect(fb, tx_bytes);
+            if (is5d) tma_load_5d_elect(a_dst, &map_a, fb, kc * KC, par, ww, hh, b);
+            else tma_load_4d_elect(a_dst, &map_a, fb, kc * KC, ww, hh, b);
             if (!b_resident) {
 #pragma unroll
               for (int u = 0; u < SUB; ++u)
-                tma_load_3d(a_dst + a_bytes + (uint32_t)u * b_tile_bytes, &map_b, fb, kc * KC, n0, wtap[u]);
+                tma_load_3d_elect(a_dst + a_bytes + (uint32_t)u * b_tile_bytes, &map_b, fb, kc * KC, n0, wtap[u]);
             }
             if (++stage == S) { stage = 0; phase ^= 1u; }
           }
@@ -328,8 +389,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+    {
       const uint32_t desc_hi = p.desc_hi, idesc = p.idesc;
       const uint32_t n_acc = (uint32_t)p.n_acc;
       uint32_t sub_off[SUB];
@@ -360,7 +421,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const uint64_t b_desc = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_addr >> 4) & 0x3FFFu) | 0x10000u);
 #pragma unroll
               for (int j = 0; j < KC / 16; ++j) {  // +32 bytes along K inside the swizzle atom per UMMA_K = 16
-                umma_f16(d_tmem, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j), idesc, accumulate);
+                umma_f16_elect(d_tmem, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j), idesc, accumulate);
                 accumulate = 1u;
               }
               b_addr += b_tile_bytes;
@@ -385,16 +446,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 const uint64_t a_desc = ((uint64_t)desc_hi << 32) | (uint64_t)(((a_start >> 4) & 0x3FFFu) | 0x10000u);
 #pragma unroll
                 for (int j = 0; j < CIN / 16; ++j)
-                  umma_f16(d_tmem + (uint32_t)pp * cout_blk, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j),
+                  umma_f16_elect(d_tmem + (uint32_t)pp * cout_blk, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j),
                            idesc_blk, (k | u | j) != 0 ? 1u : 0u);
               }
             }
           }
           b_res += (uint32_t)SUB * b_tile_bytes;
-          umma_commit(EMPTY_BAR(stage));  // smem slot free once these MMAs have read it
+          umma_commit_elect(EMPTY_BAR(stage));  // smem slot free once these MMAs have read it
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(TFULL_BAR(acc));  // accumulator complete
+        umma_commit_elect(TFULL_BAR(acc));  // accumulator complete
         if (++acc == n_acc) { acc = 0; acc_phase ^= 1u; }
       }
     }
