@@ -194,7 +194,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // kernel parameters
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int TC_MAX_TAPS = 9;
-constexpr int TC_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 epilogue groups (one per accumulator)
+constexpr int TC_NG = 2;                        // epilogue warp-groups (4 warps each); tiles are dealt round-robin
+constexpr int TC_THREADS = 64 + 128 * TC_NG;    // warp 0 TMA producer, warp 1 MMA issuer, then the epilogue groups
 
 struct TcParams {
   // tile geometry
@@ -296,8 +297,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t stage_bytes = a_bytes + b_stage_bytes;
   const uint32_t bres_base = smem_base + (uint32_t)S * stage_bytes;   // resident weights (1024-aligned)
   const uint32_t cstage_base = bres_base + (uint32_t)p.bres_bytes;  // output staging: [group][2] x c_stage_bytes
-  const uint32_t rstage_base = cstage_base + (p.tma_store ? 4u * (uint32_t)p.c_stage_bytes : 0u);  // residual0 staging (RES)
-  const uint32_t bar_base = rstage_base + ((RES && p.res_smem) ? 2u * 32768u : 0u);
+  const uint32_t rstage_base = cstage_base + (p.tma_store ? 2u * (uint32_t)TC_NG * (uint32_t)p.c_stage_bytes : 0u);  // residual0 staging (RES)
+  const uint32_t bar_base = rstage_base + ((RES && p.res_smem) ? (uint32_t)TC_NG * 16384u : 0u);
 #define FULL_BAR(s) (bar_base + 8u * (uint32_t)(s))
 #define EMPTY_BAR(s) (bar_base + 8u * (uint32_t)(S + (s)))
 #define TFULL_BAR(a) (bar_base + 8u * (uint32_t)(2 * S + (a)))
@@ -308,7 +309,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* bias_s = reinterpret_cast<float*>(smem_raw + (((tmem_slot + 16u + 15u) & ~15u) - smem_u32(smem_raw)));  // [n_nt * BN], 16-byte aligned
   for (int i = threadIdx.x; i < p.n_nt * p.BN; i += blockDim.x) bias_s[i] = p.bias[G > 1 ? i % p.cout_blk : i];
-  float* head_s = bias_s + ((p.n_nt * p.BN + 3) & ~3);  // [8 warps][32][33] staging of the fused head (out_f32 layers)
+  float* head_s = bias_s + ((p.n_nt * p.BN + 3) & ~3);  // [4 * TC_NG warps][32][33] staging of the fused head (out_f32 layers)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned long long* const dbg = p.dbg;
@@ -480,9 +481,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     T* const outp = reinterpret_cast<T*>(p.out);
     const bool issuer = (q == 2) && lane == 0;            // first warp of the group (warp 2 or 6) issues the TMA stores
     const int bar_id = 1 + grp;
+    // a group may only ever wait on the CURRENT or NEXT phase of an accumulator barrier (parity waits alias beyond that):
+    // never run more groups than there are accumulators
+    const uint32_t ng = n_acc < (uint32_t)TC_NG ? n_acc : (uint32_t)TC_NG;
     uint32_t tl = 0, blk = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-      if ((int)(tl & 1u) != grp) continue;
+    for (int tile = blockIdx.x; tile < num_tiles && (uint32_t)grp < ng; tile += gridDim.x, ++tl) {
+      if ((int)(tl % ng) != grp) continue;
       int r = tile;
       const int nt = r % n_nt; r /= n_nt;
       const int ph = r % n_phase; r /= n_phase;
@@ -505,14 +509,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // (16 bytes per vector, thread-private slots, zero-fill for out-of-range rows) BEFORE waiting for the accumulator:
       // no registers are held, the DRAM latency overlaps the MMAs of this tile and the chunk loop stays compact.
       // The second residual (Darknet decoder only, compute-bound layers) is fetched one chunk ahead.
-      const uint32_t rslot = rstage_base + (uint32_t)grp * 32768u + (uint32_t)(m & 127) * 16u;  // + i * 2048 per vector
+      const uint32_t rslot = rstage_base + (uint32_t)grp * 16384u + (uint32_t)(m & 127) * 16u;  // + i * 2048 per vector
       int4 r0[4], r1[4];
       const bool res_smem = RES && p.res_smem != 0 && has_r0;
       auto prefetch_r0 = [&](int cs) {
         if constexpr (RES) {
           if (res_smem) {
 #pragma unroll 4
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 0; i < 8; ++i) {
               const int64_t o = (cs + i * 8 < BN) ? elem_off(n0 + cs + i * 8, res0_channels) : (int64_t)-1;
               cp_async16(rslot + (uint32_t)i * 2048u, res0 + (o >= 0 ? o : 0), o >= 0);
             }
@@ -553,12 +557,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         tmem_ld_wait();
         if constexpr (RES) {
-          if (res_smem && cc > 0 && (cc & 127) == 0) { prefetch_r0(cc); cp_async_wait_all(); }  // next 128-column batch
+          if (res_smem && cc > 0 && (cc & 63) == 0) { prefetch_r0(cc); cp_async_wait_all(); }  // next 64-column batch
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           int4 r0v = make_int4(0, 0, 0, 0);
-          if constexpr (RES) { r0v = res_smem ? ld_shared_v4(rslot + (uint32_t)(((cc & 127) >> 3) + g) * 2048u) : r0[g]; }
+          if constexpr (RES) { r0v = res_smem ? ld_shared_v4(rslot + (uint32_t)(((cc & 63) >> 3) + g) * 2048u) : r0[g]; }
           sink(g, epilogue_vec8<T>(v + g * 8, bias_s + n0 + cc + g * 8, slope, RES && has_r0, r0v, RES && has_r1, r1[g]));
         }
         if (reg_res && cc + 32 < BN) load_r1(cc + 32);
@@ -626,6 +630,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ---- TMEM -> registers -> swizzled smem tile -> TMA bulk tensor store (full lines, edges clipped by TMA) ----
         // blocks of 64 channels (128-byte rows, SWIZZLE_128B)
         for (int cb = 0; cb < BN; cb += 64, ++blk) {
+          // two staging buffers per group: block k is written while the TMA store of block k-1 drains the other one
           const uint32_t buf = cstage_base + (uint32_t)(grp * 2 + (int)(blk & 1u)) * c_stage_bytes;
           const uint32_t row_addr = buf + (uint32_t)(m * 128);
 #pragma unroll 1
@@ -633,7 +638,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             chunk(cb + ci * 32, [&](int g, const int4& o) {
               st_shared_v4(row_addr + (uint32_t)(((ci * 4 + g) ^ (m & 7)) << 4), o); });
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> visible to the TMA engine
-          { DBG_T0; if (issuer) bulk_wait_read0(); DBG_ADD(4); }   // previous store of this group finished reading the OTHER buffer
+          { DBG_T0; if (issuer) bulk_wait_read0(); DBG_ADD(4); }   // store k-1 has finished reading the OTHER buffer
           { DBG_T0; group_barrier(bar_id); DBG_ADD(5); }
           if (issuer) {
             const int pp = G > 1 ? (n0 + cb) >> blk_shift : 0;
@@ -752,13 +757,12 @@ static bool tc_eligible(const ConvParams& p) {
   return true;
 }
 
-int Net::tc_prepare() {
+int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
   const int max_smem = 227 * 1024;
-  static bool attr_set = false;
-  for (auto& L : convs) {
     ConvParams& cp = L.pair_view ? L.ptc : L.p;
     L.tc_ok = false;
-    if (!tc_eligible(cp)) continue;
+    *retry = false;
+    if (!tc_eligible(cp)) return PCLS_OK;
     TcPlan* plan = new TcPlan();
     memset(plan, 0, sizeof(TcPlan));
     TcParams& q = plan->prm;
@@ -772,7 +776,7 @@ int Net::tc_prepare() {
     // width, so G adjacent pixels are viewed as ONE row of G*Cin channels (<= 128 bytes) and the MMAs are issued
     // banded (kernel comment).  Needs the whole tensor row to be contiguous (Cin == tensor channels).
     int G = 1;
-    if (tc_group_mode && tc_resident_mode && (cp.mode == MODE_1x1 || cp.mode == MODE_3x3_S1 || cp.mode == MODE_ROW3) &&
+    if (allow_group && tc_group_mode && tc_resident_mode && (cp.mode == MODE_1x1 || cp.mode == MODE_3x3_S1 || cp.mode == MODE_ROW3) &&
         (cp.cin_pad == 16 || cp.cin_pad == 32) && cp.in_channels == cp.cin_pad && cp.cout == cp.cout_pad && !cp.out_f32 &&
         cp.Wout == cp.Win) {
       for (int g = 64 / cp.cin_pad; g >= 2; g /= 2)
@@ -811,13 +815,13 @@ int Net::tc_prepare() {
       const int all_w_ = cp.ntaps * q.kchunks * btile_;
       const bool resident_ = tc_resident_mode && q.n_nt == 1 && all_w_ <= 112 * 1024;
       const int st_ = (130 * q.KC * 2 + 1023) / 1024 * 1024 + (resident_ ? 0 : 3 * btile_);
-      const int staging_ = 65536 + ((L.res0 >= 0 && q.BN <= 128) ? 65536 : 0);
+      const int staging_ = 2 * TC_NG * 16384 + ((L.res0 >= 0 && q.BN <= 128) ? TC_NG * 16384 : 0);
       if ((max_smem - 2048 - staging_ - cp.cout_pad * 4 - (resident_ ? all_w_ + 1024 : 0)) / st_ < 3) halo = false;
     }
-    if (G > 1 && cp.mode != MODE_1x1 && !halo) {  // the banded issue of a 3-tap row needs the halo tile
+    if (G > 1 && cp.mode != MODE_1x1 && !halo) {  // the banded issue of a 3-tap row needs the halo tile: plan again ungrouped
       delete plan;
-      set_error("internal: pixel-group plan without halo tile");
-      return PCLS_ERR_STATE;
+      *retry = true;
+      return PCLS_OK;
     }
     if (cp.mode == MODE_1x1) {
       q.n_groups = 1;
@@ -868,21 +872,21 @@ int Net::tc_prepare() {
     // residual0 is staged through smem only for the memory-bound layers (N tile <= 128): the wide Darknet layers are
     // tensor-bound and keep their smem for pipeline stages
     q.res_smem = (L.res0 >= 0 && q.BN <= 128) ? 1 : 0;
-    const int cstage_total = (q.tma_store ? 4 * q.c_stage_bytes : 0) + (q.res_smem ? 65536 : 0);
+    const int cstage_total = (q.tma_store ? 2 * TC_NG * q.c_stage_bytes : 0) + (q.res_smem ? TC_NG * 16384 : 0);
     // pipeline depth; weights stay resident in smem when the whole layer fits next to >= 4 stages
     q.a_bytes = (q.a_rows * q.KC * 2 + 1023) / 1024 * 1024;
     q.b_tile_bytes = G > 1 ? cp.cout_pad * cin_blk * 2 : q.BN * q.KC * 2;
     const int all_w = q.n_phase * q.n_groups * q.kchunks * q.sub * q.b_tile_bytes;
     q.b_resident = (tc_resident_mode && q.n_nt == 1 && all_w <= 112 * 1024) ? 1 : 0;
     q.bres_bytes = q.b_resident ? (all_w + 1023) / 1024 * 1024 : 0;
-    if (G > 1 && !q.b_resident) { delete plan; set_error("internal: pixel-group plan needs resident weights"); return PCLS_ERR_STATE; }
+    if (G > 1 && !q.b_resident) { delete plan; *retry = true; return PCLS_OK; }
     const int stage_bytes = q.a_bytes + (q.b_resident ? 0 : q.sub * q.b_tile_bytes);
-    int stages = (max_smem - 2048 - cp.cout_pad * 4 - q.bres_bytes - cstage_total - (cp.out_f32 ? 8 * 32 * 33 * 4 : 0)) / stage_bytes;
+    int stages = (max_smem - 2048 - cp.cout_pad * 4 - q.bres_bytes - cstage_total - (cp.out_f32 ? 4 * TC_NG * 32 * 33 * 4 : 0)) / stage_bytes;
     if (stages > 12) stages = 12;
-    if (stages < 2) { delete plan; continue; }
+    if (stages < 2) { delete plan; *retry = G > 1; return PCLS_OK; }
     q.stages = stages;
     plan->smem_bytes = (size_t)stages * stage_bytes + q.bres_bytes + cstage_total + 1024 /*alignment slack*/ +
-                       (size_t)(2 * stages + 17) * 8 + 48 + (cp.out_f32 ? 8 * 32 * 33 * 4 : 0) + (size_t)cp.cout_pad * 4 /*bias*/;
+                       (size_t)(2 * stages + 17) * 8 + 48 + (cp.out_f32 ? 4 * TC_NG * 32 * 33 * 4 : 0) + (size_t)cp.cout_pad * 4 /*bias*/;
     // descriptors
     const uint32_t layout = swz == 128 ? 2u : swz == 64 ? 4u : 6u;  // UMMA LayoutType
     const uint32_t sbo = (uint32_t)(8 * swz) >> 4;                   // 8 rows of one swizzle span
@@ -951,6 +955,17 @@ int Net::tc_prepare() {
     }
     L.tc = plan;
     L.tc_ok = true;
+  return PCLS_OK;
+}
+
+int Net::tc_prepare() {
+  const int max_smem = 227 * 1024;
+  static bool attr_set = false;
+  for (auto& L : convs) {
+    bool retry = false;
+    int rc = tc_plan_layer(L, true, &retry);
+    if (rc == PCLS_OK && retry) rc = tc_plan_layer(L, false, &retry);  // pixel-group view did not fit: plan ungrouped
+    if (rc) return rc;
   }
   if (!attr_set) {
     for (int kc = 16; kc <= 64; kc *= 2)

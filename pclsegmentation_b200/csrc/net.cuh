@@ -104,6 +104,7 @@ struct Net {
 
   // tcgen05 implicit-GEMM path (conv_tc.cu)
   int tc_prepare();
+  int tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry);
   int tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s);
   void tc_release();
 };
