@@ -46,6 +46,7 @@ class Graph:
     self.variables = {}     # name -> np.float32 array (Keras layout)
     self.program = []       # ops in execution order
     self.rng = np.random.default_rng(0)
+    self.merge_expand = True  # fuse Fire expand1x1 || expand3x3 into one convolution (see concat)
     self.input = Sym(self, W, 8, is_input=True)
 
   # ---- variables ---------------------------------------------------------------------------------
@@ -115,9 +116,29 @@ class Graph:
     return a
 
   def concat(self, parts):
-    """tf.concat(axis=3) of fresh convolution outputs: they write channel slices of one tensor."""
+    """tf.concat(axis=3) of fresh convolution outputs: they write channel slices of one tensor.
+
+    Fire expand pairs (expand1x1 || expand3x3 on the same squeeze output, nets/SqueezeSegV2.py:124-127, 196-199) are
+    MERGED into one 3x3 convolution with N = E1 + E3 output channels whose first E1 channels carry the 1x1 weights in
+    the centre tap: the squeeze tensor is read once, every output pixel row (and every residual row) is touched by ONE
+    kernel as a full contiguous line instead of two half lines, and a launch disappears.  Done when N <= 256."""
     assert all(len(p.producers) == 1 and not p.consumed for p in parts)
     out = Sym(self, parts[0].width, sum(p.channels for p in parts))
+    ops = [p.producers[0] for p in parts]
+    if (self.merge_expand and len(ops) == 2 and all(o["op"] == "conv" and o["kind"] == _lib.KIND_CONV for o in ops) and
+        ops[0]["src"] is ops[1]["src"] and (ops[0]["kh"], ops[0]["kw"]) == (1, 1) and (ops[1]["kh"], ops[1]["kw"]) == (3, 3) and
+        ops[0]["stride_w"] == 1 and ops[1]["stride_w"] == 1 and ops[0]["act"] == ops[1]["act"] and
+        (ops[0]["bn"] is None) == (ops[1]["bn"] is None) and (ops[0]["bias"] is None) == (ops[1]["bias"] is None) and
+        not ops[0]["res"] and not ops[1]["res"] and out.channels <= 256):
+      a, b = ops
+      merged = dict(op="conv", kind=_lib.KIND_CONV, kh=3, kw=3, stride_w=1, cin=a["cin"], cout=out.channels,
+                    kernel=None, bias=None, bn=None, merge=(a, b), act=a["act"], src=a["src"], dst=out, off=0, res=[],
+                    stage=max(a["stage"], b["stage"]))
+      i = self.program.index(a)
+      self.program.remove(b)
+      self.program[i] = merged
+      out.producers.append(merged)
+      return out
     off = 0
     for p in parts:
       assert p.width == out.width
@@ -126,6 +147,19 @@ class Graph:
       out.producers.append(op)
       off += p.channels
     return out
+
+  def _merged_arrays(self, op):
+    """(kernel [3,3,Cin,E1+E3], bias, gamma, beta, mean, var) of a merged Fire expand pair, from the current variables."""
+    a, b = op["merge"]
+    v = self.variables
+    k1, k3 = v[a["kernel"]], v[b["kernel"]]
+    kernel = np.zeros((3, 3, k3.shape[2], k1.shape[3] + k3.shape[3]), np.float32)
+    kernel[1, 1, :, :k1.shape[3]] = k1[0, 0]
+    kernel[:, :, :, k1.shape[3]:] = k3
+    cat = lambda x, y: np.concatenate([v[x], v[y]]).astype(np.float32)
+    bias = cat(a["bias"], b["bias"]) if a["bias"] else None
+    bn = [cat(a["bn"] + s, b["bn"] + s) for s in ("/gamma", "/beta", "/moving_mean", "/moving_variance")] if a["bn"] else [None] * 4
+    return [kernel, bias] + bn
 
   def max_pool_3x3_s2(self, x):
     self._consume(x)
@@ -164,6 +198,13 @@ class Graph:
         keep.append(a)
         return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
 
+      def aptr(a):
+        if a is None:
+          return None
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        keep.append(a)
+        return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
       def tid(sym):
         if sym.tid is None:
           sym.tid = _lib.check(lib.pcls_net_tensor(handle, sym.width, sym.channels, 1 if sym.logits else 0),
@@ -178,18 +219,22 @@ class Graph:
         if op["op"] == "conv":
           d = _lib.ConvDesc()
           d.kind, d.kh, d.kw, d.stride_w, d.cin, d.cout = op["kind"], op["kh"], op["kw"], op["stride_w"], op["cin"], op["cout"]
-          d.h_kernel, d.h_bias = fptr(op["kernel"]), fptr(op["bias"])
-          bn = op["bn"]
-          d.h_bn_gamma = fptr(bn + "/gamma" if bn else None)
-          d.h_bn_beta = fptr(bn + "/beta" if bn else None)
-          d.h_bn_mean = fptr(bn + "/moving_mean" if bn else None)
-          d.h_bn_var = fptr(bn + "/moving_variance" if bn else None)
+          if op.get("merge"):
+            arrs = [aptr(x) for x in self._merged_arrays(op)]
+            d.h_kernel, d.h_bias, d.h_bn_gamma, d.h_bn_beta, d.h_bn_mean, d.h_bn_var = arrs
+          else:
+            d.h_kernel, d.h_bias = fptr(op["kernel"]), fptr(op["bias"])
+            bn = op["bn"]
+            d.h_bn_gamma = fptr(bn + "/gamma" if bn else None)
+            d.h_bn_beta = fptr(bn + "/beta" if bn else None)
+            d.h_bn_mean = fptr(bn + "/moving_mean" if bn else None)
+            d.h_bn_var = fptr(bn + "/moving_variance" if bn else None)
           d.bn_eps, d.act = BN_EPS, op["act"]
           d.in_tensor, d.out_tensor, d.out_channel_offset = tid(op["src"]), tid(op["dst"]), op["off"]
           res = [tid(r) for r in op["res"]] + [-1, -1]
           d.residual0, d.residual1 = res[0], res[1]
           d.out_is_logits = 1 if op["dst"].logits else 0
-          _lib.check(lib.pcls_net_conv(handle, ctypes.byref(d)), "pcls_net_conv(%s)" % op["kernel"])
+          _lib.check(lib.pcls_net_conv(handle, ctypes.byref(d)), "pcls_net_conv(%s)" % (op["kernel"] or op["merge"][1]["kernel"]))
         elif op["op"] == "pool":
           _lib.check(lib.pcls_net_maxpool3x3_s2(handle, tid(op["src"]), tid(op["dst"])), "pcls_net_maxpool3x3_s2")
         else:

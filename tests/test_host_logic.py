@@ -59,12 +59,25 @@ def test_squeezesegv2_trace_matches_weight_inventory():
       assert v[f"fire{n}/upconv/kernel"].shape == (1, 4, s, s) and f"fire{n}/upconv_bn/gamma" not in v
   assert v["conv14/kernel"].shape == (3, 3, 64, 20)
   prog = model._graph.program
-  assert sum(o["op"] == "conv" for o in prog) == 43 and sum(o["op"] == "cam" for o in prog) == 3
-  assert sum(o["op"] == "pool" for o in prog) == 3
-  # every tf.add skip was folded into the two expand convs of its FireDeconv
+  # 43 Keras convolutions; the expand1x1 || expand3x3 pairs of fire2-5 and fire10-13 (N <= 256) are merged into one op
+  merged = [o for o in prog if o["op"] == "conv" and o.get("merge")]
+  assert sum(o["op"] == "conv" for o in prog) == 43 - 8 and len(merged) == 8
+  assert sum(o["op"] == "cam" for o in prog) == 3 and sum(o["op"] == "pool" for o in prog) == 3
+  for o in merged:
+    a, b = o["merge"]
+    assert a["kernel"].endswith("expand1x1/kernel") and b["kernel"].endswith("expand3x3/kernel")
+    assert o["cout"] == a["cout"] + b["cout"] and (o["kh"], o["kw"]) == (3, 3)
+    k = model._graph._merged_arrays(o)[0]
+    assert k.shape == (3, 3, a["cin"], o["cout"]) and np.array_equal(k[1, 1, :, :a["cout"]], model.variables[a["kernel"]][0, 0])
+    assert not k[0, 0, :, :a["cout"]].any() and np.array_equal(k[..., a["cout"]:], model.variables[b["kernel"]])
+  # every tf.add skip was folded into the (merged) expand convolution of its FireDeconv
   for n in (10, 11, 12, 13):
-    ops = [o for o in prog if o["op"] == "conv" and o["kernel"].startswith(f"fire{n}/expand")]
-    assert len(ops) == 2 and all(len(o["res"]) == 1 for o in ops) and sorted(o["off"] for o in ops) == [0, ops[0]["cout"]]
+    ops = [o for o in merged if o["merge"][0]["kernel"].startswith(f"fire{n}/")]
+    assert len(ops) == 1 and len(ops[0]["res"]) == 1 and ops[0]["off"] == 0
+  # fire6-9 (N = 384 / 512) keep two convolutions writing channel slices of the concat tensor
+  for n in (6, 7, 8, 9):
+    ops = [o for o in prog if o["op"] == "conv" and (o["kernel"] or "").startswith(f"fire{n}/expand")]
+    assert len(ops) == 2 and sorted(o["off"] for o in ops) == [0, ops[0]["cout"]]
   skip = [o for o in prog if o["op"] == "conv" and o["kernel"] == "conv1_skip/kernel"][0]
   assert skip["act"] == _lib.ACT_NONE and skip["bn"] == "bn1_skip"
 
