@@ -123,7 +123,7 @@ def cpu_reference_forward(model_name, mc, model, lidar, mask):
                      num_layers=getattr(mc, "NUM_LAYERS", 53), output_stride=getattr(mc, "OUTPUT_STRIDE", 16))
 
 
-def time_cpu_baseline(model_name, mc, model, raw, budget_s=12.0, max_frames=8):
+def time_cpu_baseline(model_name, mc, model, raw, budget_s=12.0, max_frames=256):
   """Oracle port (torch-CPU fp32 restatement of the reference graph incl. input stage + head) on all host cores."""
   import torch
   from oracle import nn as onn
@@ -361,8 +361,15 @@ def run_ours(args):
     roof = {"bound": "tensor", "achieved": top["TFLOP/s"], "peak": peaks["tflops_sustained"], "unit": "TFLOP/s"}
   else:
     roof = {"bound": "hbm", "achieved": top["GB/s"], "peak": peaks["hbm_gbs"], "unit": "GB/s"}
-  roof.update(frac=roof["achieved"] / roof["peak"], traffic=None, kernel=top["op"], share_of_step=top["share"],
-              peak_source=peaks["source"], batch_profiled=pb)
+  traffic = None
+  tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
+  if os.path.exists(tpath):  # DRAM bytes per launch of this kernel from the committed ncu --set full capture (same batch)
+    t = json.load(open(tpath)).get(top["op"])
+    if t and t.get("batch") == pb:
+      traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
+  roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, kernel=top["op"], share_of_step=top["share"],
+              peak_source=peaks["source"], batch_profiled=pb,
+              algorithmic_bytes_per_launch=roof["achieved"] * 1e9 * top["ms"] / 1e3 if roof["unit"] == "GB/s" else None)
   # whole-step view: algorithmic bytes and flops of all ops over the measured step time
   tot_by = tot_fl = 0
   for i in range(n_ops):
