@@ -208,13 +208,16 @@ void Net::build_pair_view(ConvLayer& L) {
                 L.w_tc[((size_t)(dh * 3 + dw + 1) * q.cout_pad + px * co_n + co) * 16 + par * 8 + ci] = wf(dh * 3 + kx, co, ci);
           }
   } else {
-    q.mode = MODE_PAIR6; q.ntaps = 6;
-    L.w_tc.assign((size_t)6 * q.cout_pad * 16, 0.0f);
+    // 3x3 s[1,2] on pairs: kx = 0,1 live in pair wo (dw = 0), kx = 2 in pair wo + 1 (dw = +1).  Expressed as a 3x3
+    // stride-1 convolution on the pair tensor whose dw = -1 taps are zero, so that it takes the halo / pixel-group
+    // path of the tensor-core kernel (128-byte TMA rows) instead of six 32-byte-row loads per tile.
+    q.mode = MODE_3x3_S1; q.ntaps = 9;
+    L.w_tc.assign((size_t)9 * q.cout_pad * 16, 0.0f);
     for (int dh = 0; dh < 3; ++dh)
       for (int kx = 0; kx < 3; ++kx)
         for (int co = 0; co < co_n; ++co)
           for (int ci = 0; ci < p.cin; ++ci)
-            L.w_tc[((size_t)(dh * 2 + (kx >> 1)) * q.cout_pad + co) * 16 + (kx & 1) * 8 + ci] = wf(dh * 3 + kx, co, ci);
+            L.w_tc[((size_t)(dh * 3 + 1 + (kx >> 1)) * q.cout_pad + co) * 16 + (kx & 1) * 8 + ci] = wf(dh * 3 + kx, co, ci);
   }
   L.bias_tc.assign(q.cout_pad, 0.0f);
   for (int n = 0; n < q.cout; ++n) L.bias_tc[n] = L.bias_f32[n % co_n];
