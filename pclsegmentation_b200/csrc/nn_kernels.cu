@@ -259,59 +259,102 @@ template int launch_maxpool3x3_s2<__nv_bfloat16>(const __nv_bfloat16*, __nv_bflo
 // --------------------------------------------------------------------------------------------------
 // CAM (nets/SqueezeSegV2.py:66-70), one row-streaming kernel:
 //   pool = maxpool7x7_SAME(x); s = relu(W1^T pool + b1); e = sigmoid(W2^T s + b2); out = x * e
-// A CTA owns a strip of TW columns of one frame and walks down the H rows.  Each input row is staged ONCE in
-// shared memory (TW + 6 columns, double buffered, next row prefetched into registers while the current one is
-// processed); a thread owns 8 channels of one column, takes the horizontal 7-max from the staged row and keeps the
-// last seven horizontal maxima plus the last four inputs in registers, so the vertical 7-max and the gate of row
-// h - 3 need no further memory traffic.  HBM traffic: (TW + 6) / TW reads + 1 write of the tensor.
-// The two 1x1 convolutions are tiny: partial dot products per 8-channel lane, xor-shuffle reduction over the
-// C/8 lanes of a pixel.
+// A CTA owns a strip of TW columns of one frame and walks down the H rows, three pipeline phases per iteration with
+// ONE __syncthreads:
+//   stage   input row r+3 travels global -> smem ring with cp.async (TW + 6 columns; padding written as -inf)
+//   phase A (thread = column x 8 channels) horizontal 7-max of row r from the ring, the last seven horizontal maxima stay
+//           in registers -> vertical 7-max of output row r-3 -> pooled tile P (fp16) in smem
+//   phase B (warp = 16 pixels x 16 channels) the two 1x1 convolutions of row r-4 on tensor cores (mma.sync m16n8k16,
+//           fp32 accumulate): squeeze P[16 x C] . W1[C x R], bias + ReLU in the accumulator fragment, which IS the A
+//           fragment of the excitation [16 x 16] . W2[16 x 8]; sigmoid (SFU), gate x from the ring, result tile O in smem
+//   phase C (thread = column x 8 channels) O of row r-5 -> global, 16-byte coalesced stores
+// HBM traffic: (TW + 6) / TW reads + 1 write of the tensor.  Weights live in registers as MMA B fragments.
 // --------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]);
+template <> __device__ __forceinline__ void mma16816<__half>(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <> __device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  T h[2] = {from_f32<T>(lo), from_f32<T>(hi)};
+  return *reinterpret_cast<uint32_t*>(h);
+}
+template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t v) {
+  const T* h = reinterpret_cast<const T*>(&v);
+  return make_float2(to_f32<T>(h[0]), to_f32<T>(h[1]));
+}
+
 template <typename T, int C>
 __global__ void __launch_bounds__(256)
 cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int H, int W) {
-  constexpr int CV = C / 8;          // 16-byte vectors per pixel (8 or 16)
-  constexpr int R = C / 16;          // reduced channels (4 or 8)
-  constexpr int TW = 256 / CV;       // columns per CTA (32 or 16)
-  constexpr int ROWV = (TW + 6) * CV;  // vectors per staged row
-  constexpr int LPT = (ROWV + 255) / 256;
-  constexpr int NB = 5, DIST = 3;  // cp.async ring: rows r+1..r+3 in flight while row r is processed
-  __shared__ int4 rowbuf[NB][ROWV];
-  // weights in shared memory, laid out so that a thread fetches its 8 x R squeeze weights / R x 8 excitation weights
-  // with 128-bit loads: per-cv blocks of 8*R floats, padded by 4 floats so that the quarter-warp's 16-byte accesses hit
-  // distinct banks (lanes of another pixel with the same cv broadcast)
-  //   w1s[cv * WS + k * R + j] = W1[cv * 8 + k][j]      w2s[cv * WS + j * 8 + k] = W2[j][cv * 8 + k]
-  constexpr int WS = 8 * R + 4;
-  __shared__ __align__(16) float w1s[CV * WS], w2s[CV * WS], b1s[R], b2s[C];
-  for (int i = threadIdx.x; i < C * R; i += 256) {
-    { const int ch = i / R, j = i % R; w1s[(ch / 8) * WS + (ch % 8) * R + j] = p.w1[i]; }
-    { const int j = i / C, ch = i % C; w2s[(ch / 8) * WS + j * 8 + (ch % 8)] = p.w2[i]; }
-  }
-  for (int i = threadIdx.x; i < R; i += 256) b1s[i] = p.b1[i];
-  for (int i = threadIdx.x; i < C; i += 256) b2s[i] = p.b2[i];
+  constexpr int CV = C / 8;            // 16-byte vectors per pixel (8 or 16)
+  constexpr int R = C / 16;            // reduced channels (4 or 8)
+  constexpr int TW = 256 / CV;         // columns per CTA (32 or 16)
+  constexpr int PV = CV + 1;           // ring pixel pitch in vectors (+1: the gate's 4-byte reads of x hit 32 banks)
+  constexpr int ROWV = (TW + 6) * PV;  // vectors per staged row
+  constexpr int LPT = ((TW + 6) * CV + 255) / 256;
+  constexpr int NB = 9, DIST = 3;      // ring: rows r-5 .. r+3 resident
+  constexpr int PITCH = C * 2 + 16;    // bytes per pixel row of the P / O tiles (+16: conflict-free ldmatrix)
+  constexpr int KS = C / 16;           // k-steps of the squeeze
+  constexpr int MT = TW / 16;          // 16-pixel M tiles per row (1 or 2)
+  extern __shared__ int4 cam_smem[];    // ring [NB][ROWV] | P tiles [2][TW * PITCH] | O tiles [2][TW * PITCH]
+  int4 (*rowbuf)[ROWV] = reinterpret_cast<int4 (*)[ROWV]>(cam_smem);
+  unsigned char (*Pt)[TW * PITCH] = reinterpret_cast<unsigned char (*)[TW * PITCH]>(cam_smem + NB * ROWV);
+  unsigned char (*Ot)[TW * PITCH] = Pt + 2;
 
   const int w0 = blockIdx.x * TW;
   const int64_t b = blockIdx.y;
   const int4* img = in + b * H * W * CV;
   int4* oimg = out + b * H * W * CV;
-  const int cv = threadIdx.x % CV, c = threadIdx.x / CV;  // this thread's column (0..TW-1) and channel vector
+  const int cv = threadIdx.x % CV, c = threadIdx.x / CV;  // phase A / C mapping: column (0..TW-1), channel vector
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int mt = MT == 1 ? 0 : warp / 4;                  // phase B mapping: M tile and two 8-channel N tiles per warp
+  const int nt0 = MT == 1 ? warp * 2 : (warp % 4) * 2;
   const int4 NEG = neg_inf8<T>();
 
-  // stage input row r into ring slot r % NB: in-image vectors travel global -> shared with cp.async (no registers,
-  // DIST rows in flight), padding (outside the image) is written as -inf so that it never wins the max
+  // ---- weights as MMA B fragments in registers (b0: k = 2t, 2t+1; b1: k = 2t+8, 2t+9; n = g) ----
+  uint32_t w1f[KS][2];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int k0 = ks * 16 + 2 * t;
+    auto w1 = [&](int ch) { return g < R ? p.w1[ch * R + g] : 0.0f; };   // W1[ch][j = g]
+    w1f[ks][0] = pack2<T>(w1(k0), w1(k0 + 1));
+    w1f[ks][1] = pack2<T>(w1(k0 + 8), w1(k0 + 9));
+  }
+  uint32_t w2f[2][2];
+  float b2v[2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int ch = (nt0 + i) * 8 + g;                                      // n = g
+    auto w2 = [&](int j) { return j < R ? p.w2[j * C + ch] : 0.0f; };      // W2[j = k][ch]
+    w2f[i][0] = pack2<T>(w2(2 * t), w2(2 * t + 1));
+    w2f[i][1] = 0u;                                                        // k >= 8: zero rows
+    b2v[i][0] = p.b2[(nt0 + i) * 8 + 2 * t];
+    b2v[i][1] = p.b2[(nt0 + i) * 8 + 2 * t + 1];
+  }
+  const float b1a = (2 * t < R) ? p.b1[2 * t] : 0.0f, b1b = (2 * t + 1 < R) ? p.b1[2 * t + 1] : 0.0f;
+
+  // stage input row r into ring slot r mod NB
   auto stage_row = [&](int r) {
     int4* dst = rowbuf[((r % NB) + NB) % NB];
 #pragma unroll
     for (int k = 0; k < LPT; ++k) {
       const int i = threadIdx.x + k * 256;
-      if (i < ROWV) {
+      if (i < (TW + 6) * CV) {
         const int col = w0 - 3 + i / CV;
+        int4* d = dst + (i / CV) * PV + (i % CV);
         if (r >= 0 && r < H && col >= 0 && col < W) {
-          const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + i);
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
           const int4* src = img + ((int64_t)r * W + col) * CV + (i % CV);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
         } else {
-          dst[i] = NEG;
+          *d = NEG;
         }
       }
     }
@@ -319,79 +362,76 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
   };
 
   int4 win[7];   // horizontal maxima of the last seven input rows (oldest first)
-  int4 xr[4];    // inputs of the last four rows at this thread's pixel (oldest first)
 #pragma unroll
   for (int k = 0; k < 7; ++k) win[k] = NEG;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) xr[k] = NEG;
 
-  for (int r = 0; r < DIST; ++r) stage_row(r);  // rows -3..-1 are padding and already -inf in the window
+  for (int r = 0; r < DIST; ++r) stage_row(r);
   const bool col_ok = (w0 + c) < W;
-  for (int r = 0; r < H + 3; ++r) {          // r = newest input row in the window; output row o = r - 3
-    const int buf = r % NB;
-    stage_row(r + DIST);                     // rows >= H are written as -inf
-    asm volatile("cp.async.wait_group %0;" ::"n"(DIST) : "memory");   // row r has landed (this thread's copies)
-    __syncthreads();                         // ... and everybody else's; also fences the slot reused by stage_row(r + DIST + 1)
-    // horizontal 7-max of row r at this column: staged columns c .. c+6 (c+3 is the centre)
-    int4 hm = rowbuf[buf][(c + 0) * CV + cv];
+  for (int r = 0; r < H + 5; ++r) {
+    stage_row(r + DIST);                                                  // rows >= H are written as -inf
+    asm volatile("cp.async.wait_group %0;" ::"n"(DIST) : "memory");     // row r has landed (this thread's copies)
+    __syncthreads();
+
+    // ---------------- phase A: pooled row oA = r - 3 ----------------
+    const int oA = r - 3;
+    if (r < H + 3) {
+      const int buf = r % NB;
+      int4 hm = rowbuf[buf][(c + 0) * PV + cv];
 #pragma unroll
-    for (int d = 1; d < 7; ++d) hm = max8<T>(hm, rowbuf[buf][(c + d) * CV + cv]);
-    const int4 centre = rowbuf[buf][(c + 3) * CV + cv];
+      for (int d = 1; d < 7; ++d) hm = max8<T>(hm, rowbuf[buf][(c + d) * PV + cv]);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) win[k] = win[k + 1];
-    win[6] = hm;
+      for (int k = 0; k < 6; ++k) win[k] = win[k + 1];
+      win[6] = hm;
+      if (oA >= 0) {
+        int4 vm = win[0];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) xr[k] = xr[k + 1];
-    xr[3] = centre;
-    const int o = r - 3;
-    if (o >= 0) {  // uniform across the CTA
-      int4 vm = win[0];
-#pragma unroll
-      for (int k = 1; k < 7; ++k) vm = max8<T>(vm, win[k]);
-      float pooled[8];
-      unpack8<T>(vm, pooled);
-      if (!col_ok) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) pooled[k] = 0.0f;
-      }
-      float sq[R];
-#pragma unroll
-      for (int j = 0; j < R; ++j) sq[j] = 0.0f;
-      const float4* w1v = reinterpret_cast<const float4*>(w1s + cv * WS);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-#pragma unroll
-        for (int jj = 0; jj < R / 4; ++jj) {
-          const float4 wv = w1v[k * (R / 4) + jj];
-          sq[jj * 4 + 0] = fmaf(pooled[k], wv.x, sq[jj * 4 + 0]);
-          sq[jj * 4 + 1] = fmaf(pooled[k], wv.y, sq[jj * 4 + 1]);
-          sq[jj * 4 + 2] = fmaf(pooled[k], wv.z, sq[jj * 4 + 2]);
-          sq[jj * 4 + 3] = fmaf(pooled[k], wv.w, sq[jj * 4 + 3]);
-        }
-      }
-#pragma unroll
-      for (int off = CV / 2; off >= 1; off >>= 1)
-#pragma unroll
-        for (int j = 0; j < R; ++j) sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], off);
-#pragma unroll
-      for (int j = 0; j < R; ++j) sq[j] = fmaxf(sq[j] + b1s[j], 0.0f);
-      if (col_ok) {
-        float x[8];
-        unpack8<T>(xr[0], x);
-        const float4* w2v = reinterpret_cast<const float4*>(w2s + cv * WS);
-        const float4 bb0 = *reinterpret_cast<const float4*>(b2s + cv * 8), bb1 = *reinterpret_cast<const float4*>(b2s + cv * 8 + 4);
-        float e[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const float4 wa = w2v[j * 2], wb = w2v[j * 2 + 1];
-          e[0] = fmaf(sq[j], wa.x, e[0]); e[1] = fmaf(sq[j], wa.y, e[1]); e[2] = fmaf(sq[j], wa.z, e[2]); e[3] = fmaf(sq[j], wa.w, e[3]);
-          e[4] = fmaf(sq[j], wb.x, e[4]); e[5] = fmaf(sq[j], wb.y, e[5]); e[6] = fmaf(sq[j], wb.z, e[6]); e[7] = fmaf(sq[j], wb.w, e[7]);
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = __fdividef(x[k], 1.0f + __expf(-e[k]));  // sigmoid gate (MUFU ex2 + rcp)
-        oimg[((int64_t)o * W + (w0 + c)) * CV + cv] = pack8<T>(x);
+        for (int k = 1; k < 7; ++k) vm = max8<T>(vm, win[k]);
+        if (!col_ok) vm = make_int4(0, 0, 0, 0);                          // columns right of the image: keep the MMA finite
+        *reinterpret_cast<int4*>(&Pt[oA & 1][c * PITCH + cv * 16]) = vm;
       }
     }
+
+    // ---------------- phase B: gate of row oB = r - 4 on tensor cores ----------------
+    const int oB = r - 4;
+    if (oB >= 0 && oB < H) {
+      const unsigned char* P = Pt[oB & 1] + mt * 16 * PITCH;
+      float sacc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        // ldmatrix.x4: lanes 0-15 address rows 0-15 at k 0-7, lanes 16-31 rows 0-15 at k 8-15 of this k-step
+        const unsigned addr = (unsigned)__cvta_generic_to_shared(P + (lane & 15) * PITCH + ks * 32 + (lane >> 4) * 16);
+        uint32_t a[4];
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
+        mma16816<T>(sacc, a, w1f[ks]);
+      }
+      // bias + ReLU; the accumulator fragment (rows g / g+8, cols 2t, 2t+1) is the A fragment of the next MMA (k < 8)
+      uint32_t sa[4];
+      sa[0] = pack2<T>(fmaxf(sacc[0] + b1a, 0.0f), fmaxf(sacc[1] + b1b, 0.0f));
+      sa[1] = pack2<T>(fmaxf(sacc[2] + b1a, 0.0f), fmaxf(sacc[3] + b1b, 0.0f));
+      sa[2] = 0u; sa[3] = 0u;
+      const unsigned char* xrow = reinterpret_cast<const unsigned char*>(rowbuf[oB % NB]);  // ring slot of input row oB
+      unsigned char* O = Ot[oB & 1] + mt * 16 * PITCH;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float e[4] = {b2v[i][0], b2v[i][1], b2v[i][0], b2v[i][1]};
+        mma16816<T>(e, sa, w2f[i]);
+        const int chb = ((nt0 + i) * 8 + 2 * t) * 2;                       // byte offset of channel pair inside a pixel
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {                                   // rows g and g + 8
+          const int px = mt * 16 + g + h2 * 8;
+          const float2 x = unpack2<T>(*reinterpret_cast<const uint32_t*>(xrow + (px + 3) * (PV * 16) + chb));
+          const float g0 = __fdividef(x.x, 1.0f + __expf(-e[h2 * 2 + 0]));
+          const float g1 = __fdividef(x.y, 1.0f + __expf(-e[h2 * 2 + 1]));
+          *reinterpret_cast<uint32_t*>(O + (g + h2 * 8) * PITCH + chb) = pack2<T>(g0, g1);
+        }
+      }
+    }
+
+    // ---------------- phase C: store row oC = r - 5 ----------------
+    const int oC = r - 5;
+    if (oC >= 0 && col_ok)
+      oimg[((int64_t)oC * W + (w0 + c)) * CV + cv] = *reinterpret_cast<const int4*>(&Ot[oC & 1][c * PITCH + cv * 16]);
   }
 }
 
@@ -402,10 +442,14 @@ int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, cud
   PCLS_REQUIRE(p.R == p.C / 16, "CAM: reduced channels must be C/16");
   const int TW = 256 / (p.C / 8);
   dim3 grid((unsigned)ceil_div(W, TW), (unsigned)B);
-  if (p.C == 64)
-    cam_kernel<T, 64><<<grid, 256, 0, s>>>(reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), p, H, W);
-  else
-    cam_kernel<T, 128><<<grid, 256, 0, s>>>(reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), p, H, W);
+  const int smem = (9 * (TW + 6) + 4 * TW) * (p.C * 2 + 16);   // ring + P/O tiles, see cam_kernel
+  auto kern = p.C == 64 ? cam_kernel<T, 64> : cam_kernel<T, 128>;
+  static bool configured[2] = {false, false};
+  if (!configured[p.C == 128]) {
+    PCLS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured[p.C == 128] = true;
+  }
+  kern<<<grid, 256, smem, s>>>(reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), p, H, W);
   return check_launch("cam_kernel");
 }
 template int launch_cam<__half>(const __half*, __half*, const CamParams&, int, int, int, cudaStream_t);
