@@ -259,15 +259,17 @@ template int launch_maxpool3x3_s2<__nv_bfloat16>(const __nv_bfloat16*, __nv_bflo
 // --------------------------------------------------------------------------------------------------
 // CAM (nets/SqueezeSegV2.py:66-70), one row-streaming kernel:
 //   pool = maxpool7x7_SAME(x); s = relu(W1^T pool + b1); e = sigmoid(W2^T s + b2); out = x * e
-// A CTA owns a strip of TW columns of one frame and walks down the H rows, three pipeline phases per iteration with
-// ONE __syncthreads:
-//   stage   input row r+3 travels global -> smem ring with cp.async (TW + 6 columns; padding written as -inf)
-//   phase A (thread = column x 8 channels) horizontal 7-max of row r from the ring, the last seven horizontal maxima stay
-//           in registers -> vertical 7-max of output row r-3 -> pooled tile P (fp16) in smem
-//   phase B (warp = 16 pixels x 16 channels) the two 1x1 convolutions of row r-4 on tensor cores (mma.sync m16n8k16,
-//           fp32 accumulate): squeeze P[16 x C] . W1[C x R], bias + ReLU in the accumulator fragment, which IS the A
-//           fragment of the excitation [16 x 16] . W2[16 x 8]; sigmoid (SFU), gate x from the ring, result tile O in smem
-//   phase C (thread = column x 8 channels) O of row r-5 -> global, 16-byte coalesced stores
+// A CTA owns a strip of TW columns of one frame and walks down the H rows; a thread owns one pixel x 8 channels of the
+// strip.  Per iteration, ONE __syncthreads:
+//   stage   input row r+3 travels global -> smem ring with cp.async (TW + 6 columns; -inf outside the image)
+//   phase A horizontal 7-max of row r from the ring; the last seven horizontal maxima stay in registers -> vertical
+//           7-max = pooled row r-3, still in registers.  They ARE the A fragment of the squeeze MMA (mma.sync m16n8k16,
+//           fp32 accumulate; the K order is a free permutation of the channels, chosen so that lane (g, t) holds pixel g,
+//           channels 8 cv .. 8 cv + 7, cv = 4 cvg + t; fragment rows 8-15 are unused).  A warp covers 8 pixels x 32
+//           channels and leaves its partial sums in its own [TW][8] fp32 tile.
+//   phase B (row r-4) sum of the C/32 partial tiles -> bias + ReLU -> A fragment of the excitation MMAs, whose N order is
+//           permuted so that lane (g, t) receives exactly its own 8 channels (b2 rides along as two extra K rows, split
+//           hi + lo); sigmoid on the SFU, gate x (16 bytes from the ring), one coalesced 16-byte global store.
 // HBM traffic: (TW + 6) / TW reads + 1 write of the tensor.  Weights live in registers as MMA B fragments.
 // --------------------------------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]);
@@ -289,149 +291,172 @@ template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t v) {
   const T* h = reinterpret_cast<const T*>(&v);
   return make_float2(to_f32<T>(h[0]), to_f32<T>(h[1]));
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int C> struct CamGeom {
+  static constexpr int CV = C / 8;              // 16-byte vectors per pixel (8 or 16)
+  static constexpr int TW = 256 / CV;           // columns per CTA (32 or 16)
+  static constexpr int PITCH = C * 2 + 64;      // bytes per ring pixel; = 64 mod 128: the (pixel, 4 vectors) reads of a
+                                                // quarter warp (2 pixels x 64 bytes) fall on disjoint banks
+  static constexpr int ROWB = (TW + 6) * PITCH; // bytes per ring slot
+  static constexpr int NB = 9, DIST = 3;        // ring: rows r-5 .. r+3 resident
+  static constexpr int SMEM = NB * ROWB + 2 * (CV / 4) * TW * 8 * 4;
+};
 
 template <typename T, int C>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int H, int W) {
-  constexpr int CV = C / 8;            // 16-byte vectors per pixel (8 or 16)
-  constexpr int R = C / 16;            // reduced channels (4 or 8)
-  constexpr int TW = 256 / CV;         // columns per CTA (32 or 16)
-  constexpr int PV = CV + 1;           // ring pixel pitch in vectors (+1: the gate's 4-byte reads of x hit 32 banks)
-  constexpr int ROWV = (TW + 6) * PV;  // vectors per staged row
-  constexpr int LPT = ((TW + 6) * CV + 255) / 256;
-  constexpr int NB = 9, DIST = 3;      // ring: rows r-5 .. r+3 resident
-  constexpr int PITCH = C * 2 + 16;    // bytes per pixel row of the P / O tiles (+16: conflict-free ldmatrix)
-  constexpr int KS = C / 16;           // k-steps of the squeeze
-  constexpr int MT = TW / 16;          // 16-pixel M tiles per row (1 or 2)
-  extern __shared__ int4 cam_smem[];    // ring [NB][ROWV] | P tiles [2][TW * PITCH] | O tiles [2][TW * PITCH]
-  int4 (*rowbuf)[ROWV] = reinterpret_cast<int4 (*)[ROWV]>(cam_smem);
-  unsigned char (*Pt)[TW * PITCH] = reinterpret_cast<unsigned char (*)[TW * PITCH]>(cam_smem + NB * ROWV);
-  unsigned char (*Ot)[TW * PITCH] = Pt + 2;
+  using G = CamGeom<C>;
+  constexpr int CV = G::CV, TW = G::TW, PITCH = G::PITCH, ROWB = G::ROWB, NB = G::NB, DIST = G::DIST;
+  constexpr int R = C / 16;                // reduced channels (4 or 8)
+  constexpr int NSTG = (TW + 6) * CV;      // 16-byte copies per staged row
+  constexpr int LPT = (NSTG + 255) / 256;
+  constexpr int CVG = CV / 4;              // warps per pixel group (2 or 4)
+  constexpr int STILE = TW * 8 * 4;        // bytes of one partial squeeze tile [TW][8] fp32
+  extern __shared__ int4 cam_smem[];       // ring [NB][ROWB] | squeeze tiles [2][CVG][TW][8] fp32
+  unsigned char* const ring = reinterpret_cast<unsigned char*>(cam_smem);
+  unsigned char* const St = ring + NB * ROWB;
 
   const int w0 = blockIdx.x * TW;
   const int64_t b = blockIdx.y;
-  const int4* img = in + b * H * W * CV;
-  int4* oimg = out + b * H * W * CV;
-  const int cv = threadIdx.x % CV, c = threadIdx.x / CV;  // phase A / C mapping: column (0..TW-1), channel vector
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int mt = MT == 1 ? 0 : warp / 4;                  // phase B mapping: M tile and two 8-channel N tiles per warp
-  const int nt0 = MT == 1 ? warp * 2 : (warp % 4) * 2;
+  const int cvg = warp % CVG, pg = warp / CVG;
+  const int c = pg * 8 + g, cv = cvg * 4 + t;              // this thread's pixel (column in the strip) and channel vector
   const int4 NEG = neg_inf8<T>();
+  const int64_t rowv = (int64_t)W * CV;                    // vectors per image row
 
-  // ---- weights as MMA B fragments in registers (b0: k = 2t, 2t+1; b1: k = 2t+8, 2t+9; n = g) ----
-  uint32_t w1f[KS][2];
+  // ---- squeeze weights: B fragments of the two k-steps.  K slot (2t', 2t'+1 | +8) <-> channels 8 cv(t') + 4u + {0,1 | 2,3}
+  uint32_t w1f[2][2];
 #pragma unroll
-  for (int ks = 0; ks < KS; ++ks) {
-    const int k0 = ks * 16 + 2 * t;
-    auto w1 = [&](int ch) { return g < R ? p.w1[ch * R + g] : 0.0f; };   // W1[ch][j = g]
-    w1f[ks][0] = pack2<T>(w1(k0), w1(k0 + 1));
-    w1f[ks][1] = pack2<T>(w1(k0 + 8), w1(k0 + 9));
+  for (int u = 0; u < 2; ++u) {
+    const int ch = cv * 8 + 4 * u;
+    auto w1 = [&](int k) { return g < R ? p.w1[(ch + k) * R + g] : 0.0f; };   // W1[channel][j = g]
+    w1f[u][0] = pack2<T>(w1(0), w1(1));
+    w1f[u][1] = pack2<T>(w1(2), w1(3));
   }
-  uint32_t w2f[2][2];
-  float b2v[2][2];
+  // ---- excitation weights: N slot n of tile q <-> channel 8 (4 cvg + n / 2) + 2q + n % 2, so that the accumulator of
+  // lane (g, t) (columns 2t, 2t+1) is channel pair q of its own vector.  sigmoid(e) = 1 / (1 + 2^(-log2(e) e)): the factor
+  // is folded into W2 and b2.
+  constexpr float NL2E = -1.4426950408889634f;
+  uint32_t w2f[4][2];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int ch = (nt0 + i) * 8 + g;                                      // n = g
-    auto w2 = [&](int j) { return j < R ? p.w2[j * C + ch] : 0.0f; };      // W2[j = k][ch]
-    w2f[i][0] = pack2<T>(w2(2 * t), w2(2 * t + 1));
-    w2f[i][1] = 0u;                                                        // k >= 8: zero rows
-    b2v[i][0] = p.b2[(nt0 + i) * 8 + 2 * t];
-    b2v[i][1] = p.b2[(nt0 + i) * 8 + 2 * t + 1];
+  for (int q = 0; q < 4; ++q) {
+    const int chn = (cvg * 4 + (g >> 1)) * 8 + 2 * q + (g & 1);
+    auto w2 = [&](int j) { return j < R ? NL2E * p.w2[j * C + chn] : 0.0f; };  // W2[j = k][channel]
+    w2f[q][0] = pack2<T>(w2(2 * t), w2(2 * t + 1));
+    // K rows 8 and 9 carry the bias (A holds 1.0 there), as hi + lo so that it keeps fp32 accuracy
+    const float bias = NL2E * p.b2[chn];
+    const float hi = to_f32<T>(from_f32<T>(bias));
+    w2f[q][1] = t == 0 ? pack2<T>(hi, bias - hi) : 0u;
   }
+  const uint32_t one2 = t == 0 ? pack2<T>(1.0f, 1.0f) : 0u;
   const float b1a = (2 * t < R) ? p.b1[2 * t] : 0.0f, b1b = (2 * t + 1 < R) ? p.b1[2 * t + 1] : 0.0f;
 
-  // stage input row r into ring slot r mod NB
-  auto stage_row = [&](int r) {
-    int4* dst = rowbuf[((r % NB) + NB) % NB];
+  // ---- staging: this thread's copies of a row (fixed columns, the source advances one image row per call) ----
+  const int4* const fin = in + b * H * rowv;                 // this frame (CTA-uniform); per-thread offsets stay 32-bit
+  int4* const fout = out + b * H * rowv;
+  unsigned sptr[LPT];
+  unsigned soff[LPT];
+  bool sok[LPT];
 #pragma unroll
-    for (int k = 0; k < LPT; ++k) {
-      const int i = threadIdx.x + k * 256;
-      if (i < (TW + 6) * CV) {
-        const int col = w0 - 3 + i / CV;
-        int4* d = dst + (i / CV) * PV + (i % CV);
-        if (r >= 0 && r < H && col >= 0 && col < W) {
-          const unsigned sa = (unsigned)__cvta_generic_to_shared(d);
-          const int4* src = img + ((int64_t)r * W + col) * CV + (i % CV);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
-        } else {
-          *d = NEG;
-        }
+  for (int k = 0; k < LPT; ++k) {
+    const int i = threadIdx.x + k * 256;
+    const int col = w0 - 3 + i / CV;
+    sok[k] = i < NSTG && col >= 0 && col < W;
+    soff[k] = (unsigned)__cvta_generic_to_shared(ring) + (i / CV) * PITCH + (i % CV) * 16;
+    sptr[k] = (unsigned)(col * CV + (i % CV));
+    if (i < NSTG && !sok[k])                                               // columns outside the image: -inf, written once
+      for (int sl = 0; sl < NB; ++sl) *reinterpret_cast<int4*>(ring + sl * ROWB + (i / CV) * PITCH + (i % CV) * 16) = NEG;
+  }
+  auto stage_row = [&](int r, int slot) {
+    if (r < H) {
+#pragma unroll
+      for (int k = 0; k < LPT; ++k) {
+        if (sok[k]) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(soff[k] + slot * ROWB), "l"(fin + sptr[k]) : "memory");
+        sptr[k] += (unsigned)rowv;
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  int4 win[7];   // horizontal maxima of the last seven input rows (oldest first)
+  // ---- per-thread offsets ----
+  const unsigned a_off = c * PITCH + cv * 16;                              // ring: pixel c - 3 (+ d * PITCH), this vector
+  const unsigned s_off = (c * 8 + 2 * t) * 4;                              // squeeze tile: pixel c, columns 2t, 2t+1
+  const bool col_ok = (w0 + c) < W;
+  unsigned optr = (unsigned)((w0 + c) * CV + cv);
+
+  int4 win[7];   // horizontal maxima of the last seven input rows (slot = row mod 7)
 #pragma unroll
   for (int k = 0; k < 7; ++k) win[k] = NEG;
 
-  for (int r = 0; r < DIST; ++r) stage_row(r);
-  const bool col_ok = (w0 + c) < W;
-  for (int r = 0; r < H + 5; ++r) {
-    stage_row(r + DIST);                                                  // rows >= H are written as -inf
-    asm volatile("cp.async.wait_group %0;" ::"n"(DIST) : "memory");     // row r has landed (this thread's copies)
-    __syncthreads();
+  for (int r = 0; r < DIST; ++r) stage_row(r, r);
+  int sc = 0;                                                              // ring slot of row r (r mod NB)
+  for (int r0 = 0; r0 < H + 4; r0 += 7) {
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int r = r0 + j;
+      if (r >= H + 4) break;
+      stage_row(r + DIST, sc + DIST >= NB ? sc + DIST - NB : sc + DIST);
+      asm volatile("cp.async.wait_group %0;" ::"n"(DIST) : "memory");    // row r has landed (this thread's copies)
+      __syncthreads();
 
-    // ---------------- phase A: pooled row oA = r - 3 ----------------
-    const int oA = r - 3;
-    if (r < H + 3) {
-      const int buf = r % NB;
-      int4 hm = rowbuf[buf][(c + 0) * PV + cv];
+      // ---------------- phase A: pooled row r - 3, squeeze partial sums -> tiles [r & 1] ----------------
+      if (r < H + 3) {
+        int4 hm = NEG;                                                     // rows below the image pad with -inf
+        if (r < H) {
+          const unsigned char* src = ring + sc * ROWB + a_off;
+          hm = *reinterpret_cast<const int4*>(src);
 #pragma unroll
-      for (int d = 1; d < 7; ++d) hm = max8<T>(hm, rowbuf[buf][(c + d) * PV + cv]);
+          for (int d = 1; d < 7; ++d) hm = max8<T>(hm, *reinterpret_cast<const int4*>(src + d * PITCH));
+        }
+        win[j] = hm;
+        if (r >= 3) {
+          int4 vm = win[0];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) win[k] = win[k + 1];
-      win[6] = hm;
-      if (oA >= 0) {
-        int4 vm = win[0];
-#pragma unroll
-        for (int k = 1; k < 7; ++k) vm = max8<T>(vm, win[k]);
-        if (!col_ok) vm = make_int4(0, 0, 0, 0);                          // columns right of the image: keep the MMA finite
-        *reinterpret_cast<int4*>(&Pt[oA & 1][c * PITCH + cv * 16]) = vm;
-      }
-    }
-
-    // ---------------- phase B: gate of row oB = r - 4 on tensor cores ----------------
-    const int oB = r - 4;
-    if (oB >= 0 && oB < H) {
-      const unsigned char* P = Pt[oB & 1] + mt * 16 * PITCH;
-      float sacc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        // ldmatrix.x4: lanes 0-15 address rows 0-15 at k 0-7, lanes 16-31 rows 0-15 at k 8-15 of this k-step
-        const unsigned addr = (unsigned)__cvta_generic_to_shared(P + (lane & 15) * PITCH + ks * 32 + (lane >> 4) * 16);
-        uint32_t a[4];
-        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
-        mma16816<T>(sacc, a, w1f[ks]);
-      }
-      // bias + ReLU; the accumulator fragment (rows g / g+8, cols 2t, 2t+1) is the A fragment of the next MMA (k < 8)
-      uint32_t sa[4];
-      sa[0] = pack2<T>(fmaxf(sacc[0] + b1a, 0.0f), fmaxf(sacc[1] + b1b, 0.0f));
-      sa[1] = pack2<T>(fmaxf(sacc[2] + b1a, 0.0f), fmaxf(sacc[3] + b1b, 0.0f));
-      sa[2] = 0u; sa[3] = 0u;
-      const unsigned char* xrow = reinterpret_cast<const unsigned char*>(rowbuf[oB % NB]);  // ring slot of input row oB
-      unsigned char* O = Ot[oB & 1] + mt * 16 * PITCH;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        float e[4] = {b2v[i][0], b2v[i][1], b2v[i][0], b2v[i][1]};
-        mma16816<T>(e, sa, w2f[i]);
-        const int chb = ((nt0 + i) * 8 + 2 * t) * 2;                       // byte offset of channel pair inside a pixel
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {                                   // rows g and g + 8
-          const int px = mt * 16 + g + h2 * 8;
-          const float2 x = unpack2<T>(*reinterpret_cast<const uint32_t*>(xrow + (px + 3) * (PV * 16) + chb));
-          const float g0 = __fdividef(x.x, 1.0f + __expf(-e[h2 * 2 + 0]));
-          const float g1 = __fdividef(x.y, 1.0f + __expf(-e[h2 * 2 + 1]));
-          *reinterpret_cast<uint32_t*>(O + (g + h2 * 8) * PITCH + chb) = pack2<T>(g0, g1);
+          for (int k = 1; k < 7; ++k) vm = max8<T>(vm, win[k]);
+          float sq[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // (columns right of the image carry -inf: their rows are never stored)
+          const uint32_t a0[4] = {(uint32_t)vm.x, 0u, (uint32_t)vm.y, 0u};
+          const uint32_t a1[4] = {(uint32_t)vm.z, 0u, (uint32_t)vm.w, 0u};
+          mma16816<T>(sq, a0, w1f[0]);
+          mma16816<T>(sq, a1, w1f[1]);
+          *reinterpret_cast<float2*>(St + ((r & 1) * CVG + cvg) * STILE + s_off) = make_float2(sq[0], sq[1]);
         }
       }
-    }
 
-    // ---------------- phase C: store row oC = r - 5 ----------------
-    const int oC = r - 5;
-    if (oC >= 0 && col_ok)
-      oimg[((int64_t)oC * W + (w0 + c)) * CV + cv] = *reinterpret_cast<const int4*>(&Ot[oC & 1][c * PITCH + cv * 16]);
+      // ---------------- phase B: gate and store row r - 4 (tiles [(r - 1) & 1]) ----------------
+      if (r >= 4) {
+        float2 sv = make_float2(b1a, b1b);
+#pragma unroll
+        for (int k = 0; k < CVG; ++k) {
+          const float2 part = *reinterpret_cast<const float2*>(St + (((r - 1) & 1) * CVG + k) * STILE + s_off);
+          sv.x += part.x; sv.y += part.y;
+        }
+        const uint32_t sa[4] = {pack2<T>(fmaxf(sv.x, 0.0f), fmaxf(sv.y, 0.0f)), 0u, one2, 0u};
+        const int sb = sc + 5 >= NB ? sc + 5 - NB : sc + 5;                // ring slot of input row r - 4
+        const int4 xv = *reinterpret_cast<const int4*>(ring + sb * ROWB + a_off + 3 * PITCH);
+        const uint32_t xw[4] = {(uint32_t)xv.x, (uint32_t)xv.y, (uint32_t)xv.z, (uint32_t)xv.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float e[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          mma16816<T>(e, sa, w2f[q]);
+          const float2 x = unpack2<T>(xw[q]);
+          o[q] = pack2<T>(x.x * rcp_approx(1.0f + ex2_approx(e[0])), x.y * rcp_approx(1.0f + ex2_approx(e[1])));
+        }
+        if (col_ok) fout[optr] = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
+        optr += (unsigned)rowv;
+      }
+      sc = sc + 1 == NB ? 0 : sc + 1;
+    }
   }
 }
 
@@ -442,11 +467,12 @@ int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, cud
   PCLS_REQUIRE(p.R == p.C / 16, "CAM: reduced channels must be C/16");
   const int TW = 256 / (p.C / 8);
   dim3 grid((unsigned)ceil_div(W, TW), (unsigned)B);
-  const int smem = (9 * (TW + 6) + 4 * TW) * (p.C * 2 + 16);   // ring + P/O tiles, see cam_kernel
+  const int smem = p.C == 64 ? CamGeom<64>::SMEM : CamGeom<128>::SMEM;   // ring + P/O tiles, see cam_kernel
   auto kern = p.C == 64 ? cam_kernel<T, 64> : cam_kernel<T, 128>;
   static bool configured[2] = {false, false};
   if (!configured[p.C == 128]) {
     PCLS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PCLS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured[p.C == 128] = true;
   }
   kern<<<grid, 256, smem, s>>>(reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), p, H, W);
