@@ -309,11 +309,11 @@ template <int C> struct CamGeom {
                                                 // quarter warp (2 pixels x 64 bytes) fall on disjoint banks
   static constexpr int ROWB = (TW + 6) * PITCH; // bytes per ring slot
   static constexpr int NB = 9, DIST = 3;        // ring: rows r-5 .. r+3 resident
-  static constexpr int SMEM = NB * ROWB + 2 * (CV / 4) * TW * 8 * 4;
+  static constexpr int SMEM = NB * ROWB + (2 * (CV / 4) + 1) * TW * 8 * 4;
 };
 
 template <typename T, int C>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int H, int W) {
   using G = CamGeom<C>;
   constexpr int CV = G::CV, TW = G::TW, PITCH = G::PITCH, ROWB = G::ROWB, NB = G::NB, DIST = G::DIST;
@@ -322,7 +322,7 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
   constexpr int LPT = (NSTG + 255) / 256;
   constexpr int CVG = CV / 4;              // warps per pixel group (2 or 4)
   constexpr int STILE = TW * 8 * 4;        // bytes of one partial squeeze tile [TW][8] fp32
-  extern __shared__ int4 cam_smem[];       // ring [NB][ROWB] | squeeze tiles [2][CVG][TW][8] fp32
+  extern __shared__ int4 cam_smem[];       // ring [NB][ROWB] | squeeze tiles [2][CVG][TW][8] fp32 | b1 tile [TW][8] fp32
   unsigned char* const ring = reinterpret_cast<unsigned char*>(cam_smem);
   unsigned char* const St = ring + NB * ROWB;
 
@@ -347,43 +347,49 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
   // lane (g, t) (columns 2t, 2t+1) is channel pair q of its own vector.  sigmoid(e) = 1 / (1 + 2^(-log2(e) e)): the factor
   // is folded into W2 and b2.
   constexpr float NL2E = -1.4426950408889634f;
-  uint32_t w2f[4][2];
+  uint32_t w2f[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int chn = (cvg * 4 + (g >> 1)) * 8 + 2 * q + (g & 1);
     auto w2 = [&](int j) { return j < R ? NL2E * p.w2[j * C + chn] : 0.0f; };  // W2[j = k][channel]
-    w2f[q][0] = pack2<T>(w2(2 * t), w2(2 * t + 1));
-    // K rows 8 and 9 carry the bias (A holds 1.0 there), as hi + lo so that it keeps fp32 accuracy
-    const float bias = NL2E * p.b2[chn];
-    const float hi = to_f32<T>(from_f32<T>(bias));
-    w2f[q][1] = t == 0 ? pack2<T>(hi, bias - hi) : 0u;
+    w2f[q] = pack2<T>(w2(2 * t), w2(2 * t + 1));
   }
-  const uint32_t one2 = t == 0 ? pack2<T>(1.0f, 1.0f) : 0u;
-  const float b1a = (2 * t < R) ? p.b1[2 * t] : 0.0f, b1b = (2 * t + 1 < R) ? p.b1[2 * t + 1] : 0.0f;
+  // b2 rides in K rows 8 + 2q, 9 + 2q of tile q (hi + lo: fp32 accuracy), where A holds 1.0 for that tile only; the other
+  // rows >= 8 meet zeros in A, so ONE register (lane t' holds the rows of tile q = t') serves all four tiles
+  uint32_t w2b;
+  {
+    const float bias = NL2E * p.b2[(cvg * 4 + (g >> 1)) * 8 + 2 * t + (g & 1)];
+    const float hi = to_f32<T>(from_f32<T>(bias));
+    w2b = pack2<T>(hi, bias - hi);
+  }
+  const uint32_t one2 = pack2<T>(1.0f, 1.0f);
 
   // ---- staging: this thread's copies of a row (fixed columns, the source advances one image row per call) ----
   const int4* const fin = in + b * H * rowv;                 // this frame (CTA-uniform); per-thread offsets stay 32-bit
   int4* const fout = out + b * H * rowv;
-  unsigned sptr[LPT];
-  unsigned soff[LPT];
+  static_assert(LPT == 2, "two copies per thread and row");
+  // copy k = 0: column w0 - 3 + tid / CV, vector tid % CV; copy k = 1: 256 / CV columns further right
+  unsigned sptr = (unsigned)((w0 - 3 + (int)threadIdx.x / CV) * CV + threadIdx.x % CV);
+  const unsigned soff = (unsigned)__cvta_generic_to_shared(ring) + (threadIdx.x / CV) * PITCH + (threadIdx.x % CV) * 16;
   bool sok[LPT];
 #pragma unroll
   for (int k = 0; k < LPT; ++k) {
     const int i = threadIdx.x + k * 256;
     const int col = w0 - 3 + i / CV;
     sok[k] = i < NSTG && col >= 0 && col < W;
-    soff[k] = (unsigned)__cvta_generic_to_shared(ring) + (i / CV) * PITCH + (i % CV) * 16;
-    sptr[k] = (unsigned)(col * CV + (i % CV));
     if (i < NSTG && !sok[k])                                               // columns outside the image: -inf, written once
       for (int sl = 0; sl < NB; ++sl) *reinterpret_cast<int4*>(ring + sl * ROWB + (i / CV) * PITCH + (i % CV) * 16) = NEG;
   }
+  for (int i = threadIdx.x; i < TW * 8; i += 256)                          // b1, replicated per pixel (zero beyond R)
+    reinterpret_cast<float*>(St + 2 * CVG * STILE)[i] = (i % 8) < R ? p.b1[i % 8] : 0.0f;
   auto stage_row = [&](int r, int slot) {
     if (r < H) {
 #pragma unroll
-      for (int k = 0; k < LPT; ++k) {
-        if (sok[k]) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(soff[k] + slot * ROWB), "l"(fin + sptr[k]) : "memory");
-        sptr[k] += (unsigned)rowv;
-      }
+      for (int k = 0; k < LPT; ++k)
+        if (sok[k])
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(soff + k * (256 / CV) * PITCH + slot * ROWB),
+                       "l"(fin + (unsigned)(sptr + k * 256)) : "memory");   // 32-bit wrap: sptr is "negative" left of the image
+      sptr += (unsigned)rowv;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -416,7 +422,10 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
           const unsigned char* src = ring + sc * ROWB + a_off;
           hm = *reinterpret_cast<const int4*>(src);
 #pragma unroll
-          for (int d = 1; d < 7; ++d) hm = max8<T>(hm, *reinterpret_cast<const int4*>(src + d * PITCH));
+          for (int d = 1; d < 4; ++d) hm = max8<T>(hm, *reinterpret_cast<const int4*>(src + d * PITCH));
+          __syncwarp();   // two batches of loads: seven 16-byte values in flight at once cost 12 more registers (spills)
+#pragma unroll
+          for (int d = 4; d < 7; ++d) hm = max8<T>(hm, *reinterpret_cast<const int4*>(src + d * PITCH));
         }
         win[j] = hm;
         if (r >= 3) {
@@ -434,13 +443,13 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
 
       // ---------------- phase B: gate and store row r - 4 (tiles [(r - 1) & 1]) ----------------
       if (r >= 4) {
-        float2 sv = make_float2(b1a, b1b);
+        float2 sv = *reinterpret_cast<const float2*>(St + 2 * CVG * STILE + s_off);   // b1
 #pragma unroll
         for (int k = 0; k < CVG; ++k) {
           const float2 part = *reinterpret_cast<const float2*>(St + (((r - 1) & 1) * CVG + k) * STILE + s_off);
           sv.x += part.x; sv.y += part.y;
         }
-        const uint32_t sa[4] = {pack2<T>(fmaxf(sv.x, 0.0f), fmaxf(sv.y, 0.0f)), 0u, one2, 0u};
+        uint32_t sa[4] = {pack2<T>(fmaxf(sv.x, 0.0f), fmaxf(sv.y, 0.0f)), 0u, 0u, 0u};
         const int sb = sc + 5 >= NB ? sc + 5 - NB : sc + 5;                // ring slot of input row r - 4
         const int4 xv = *reinterpret_cast<const int4*>(ring + sb * ROWB + a_off + 3 * PITCH);
         const uint32_t xw[4] = {(uint32_t)xv.x, (uint32_t)xv.y, (uint32_t)xv.z, (uint32_t)xv.w};
@@ -448,7 +457,9 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float e[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-          mma16816<T>(e, sa, w2f[q]);
+          const uint32_t bq[2] = {w2f[q], w2b};
+          sa[2] = t == q ? one2 : 0u;
+          mma16816<T>(e, sa, bq);
           const float2 x = unpack2<T>(xw[q]);
           o[q] = pack2<T>(x.x * rcp_approx(1.0f + ex2_approx(e[0])), x.y * rcp_approx(1.0f + ex2_approx(e[1])));
         }
