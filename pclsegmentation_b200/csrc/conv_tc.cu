@@ -82,6 +82,7 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void group_barrier(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
@@ -227,6 +228,9 @@ struct TcParams {
   // to pixel p of the group.  cout_blk = 1 << 30 when G == 1.
   int G, cout_blk, cout_blk_shift;
   int res_smem;               // RES kernels: 1 = residual0 staged through smem with cp.async, 0 = per-chunk LDG
+  int res_tma;                // RES kernels with the TMA-store epilogue: residual0 blocks are TMA-loaded INTO the output
+                              // staging buffers one block ahead (three buffers per group), added in place, stored by TMA
+  int n_cbuf;                 // output staging buffers per epilogue group (2, or 3 with res_tma)
   uint32_t desc_hi_b, idesc_blk;
   // epilogue
   int cout, out_channels, out_coff, act, out_f32, is_bf16;
@@ -286,7 +290,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 template <typename T, int KC, int SUB, int G, bool RES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ TcParams p, const int num_tiles) {
+               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
+               const __grid_constant__ TcParams p, const int num_tiles) {
   extern __shared__ uint8_t smem_raw[];
   // carve: [stages x (A tile | B tiles)] 1024-aligned, resident weights, barriers, TMEM base slot, bias
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -296,15 +301,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t b_stage_bytes = b_resident ? 0u : (uint32_t)SUB * b_tile_bytes;
   const uint32_t stage_bytes = a_bytes + b_stage_bytes;
   const uint32_t bres_base = smem_base + (uint32_t)S * stage_bytes;   // resident weights (1024-aligned)
-  const uint32_t cstage_base = bres_base + (uint32_t)p.bres_bytes;  // output staging: [group][2] x c_stage_bytes
-  const uint32_t rstage_base = cstage_base + (p.tma_store ? 2u * (uint32_t)TC_NG * (uint32_t)p.c_stage_bytes : 0u);  // residual0 staging (RES)
+  const uint32_t cstage_base = bres_base + (uint32_t)p.bres_bytes;  // output staging: [group][n_cbuf] x c_stage_bytes
+  const uint32_t rstage_base = cstage_base + (p.tma_store ? (uint32_t)(p.n_cbuf * TC_NG) * (uint32_t)p.c_stage_bytes : 0u);  // residual0 staging (RES)
   const uint32_t bar_base = rstage_base + ((RES && p.res_smem) ? (uint32_t)TC_NG * 16384u : 0u);
 #define FULL_BAR(s) (bar_base + 8u * (uint32_t)(s))
 #define EMPTY_BAR(s) (bar_base + 8u * (uint32_t)(S + (s)))
 #define TFULL_BAR(a) (bar_base + 8u * (uint32_t)(2 * S + (a)))
 #define TEMPTY_BAR(a) (bar_base + 8u * (uint32_t)(2 * S + 8 + (a)))
 #define BRES_BAR (bar_base + 8u * (uint32_t)(2 * S + 16))
-  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * S + 17);
+#define RFULL_BAR(i) (bar_base + 8u * (uint32_t)(2 * S + 17 + (i)))   // [group][3]: residual block landed in staging buffer
+  const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * S + 17 + 3 * TC_NG);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* bias_s = reinterpret_cast<float*>(smem_raw + (((tmem_slot + 16u + 15u) & ~15u) - smem_u32(smem_raw)));  // [n_nt * BN], 16-byte aligned
@@ -320,6 +326,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+    if (RES && p.res_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r) : "memory");
+    for (int i = 0; i < 3 * TC_NG; ++i) mbar_init(RFULL_BAR(i), 1);
     for (int s = 0; s < S; ++s) { mbar_init(FULL_BAR(s), 1); mbar_init(EMPTY_BAR(s), 1); }
     for (int a = 0; a < 8; ++a) { mbar_init(TFULL_BAR(a), 1); mbar_init(TEMPTY_BAR(a), 4); }
     mbar_init(BRES_BAR, 1);
@@ -485,6 +493,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // never run more groups than there are accumulators
     const uint32_t ng = n_acc < (uint32_t)TC_NG ? n_acc : (uint32_t)TC_NG;
     uint32_t tl = 0, blk = 0;
+    // res_tma: TMA load of the residual block (tile, channel block cb) into staging buffer `bi` of this group
+    auto issue_res = [&](int rtile, int rcb, uint32_t bi) {
+      int r2 = rtile;
+      const int nt2 = r2 % n_nt; r2 /= n_nt;
+      const int ph2 = r2 % n_phase; r2 /= n_phase;
+      const int wt2 = r2 % n_wt; r2 /= n_wt;
+      const int ht2 = r2 % n_ht;
+      const int b2 = r2 / n_ht;
+      const uint32_t dst = cstage_base + (uint32_t)(grp * 3 + (int)bi) * c_stage_bytes;
+      const uint32_t bar = RFULL_BAR(grp * 3 + (int)bi);
+      const int pp2 = G > 1 ? (nt2 * BN + rcb) >> blk_shift : 0;
+      const int c02 = out_coff + ((nt2 * BN + rcb) & blk_mask);
+      mbar_arrive_expect_tx(bar, 128u * 64u * 2u);
+      if (c_is_5d) tma_load_5d(dst, &map_r, bar, c02, G > 1 ? pp2 : ph2, wt2 * BW, ht2 * BH, b2);
+      else tma_load_4d(dst, &map_r, bar, c02, wt2 * BW, ht2 * BH, b2);
+    };
+    if (RES && p.res_tma != 0 && has_r0 && issuer && (uint32_t)grp < ng && (int)(blockIdx.x + grp * gridDim.x) < num_tiles)
+      issue_res((int)(blockIdx.x + grp * gridDim.x), 0, 0u);
     for (int tile = blockIdx.x; tile < num_tiles && (uint32_t)grp < ng; tile += gridDim.x, ++tl) {
       if ((int)(tl % ng) != grp) continue;
       int r = tile;
@@ -512,6 +538,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t rslot = rstage_base + (uint32_t)grp * 16384u + (uint32_t)(m & 127) * 16u;  // + i * 2048 per vector
       int4 r0[4], r1[4];
       const bool res_smem = RES && p.res_smem != 0 && has_r0;
+      const bool res_tma = RES && p.res_tma != 0 && has_r0;
+      uint32_t res_row = 0;     // res_tma: this thread's row of the staging buffer that holds the residual block
       auto prefetch_r0 = [&](int cs) {
         if constexpr (RES) {
           if (res_smem) {
@@ -530,14 +558,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int g = 0; g < 4; ++g) {
             const int64_t o = has_r1 ? elem_off(n0 + c + g * 8, res1_channels) : (int64_t)-1;
             r1[g] = o >= 0 ? __ldg(reinterpret_cast<const int4*>(res1 + o)) : make_int4(0, 0, 0, 0);
-            if (has_r0 && !res_smem) {
+            if (has_r0 && !res_smem && !res_tma) {
               const int64_t o0 = elem_off(n0 + c + g * 8, res0_channels);
               r0[g] = o0 >= 0 ? __ldg(reinterpret_cast<const int4*>(res0 + o0)) : make_int4(0, 0, 0, 0);
             }
           }
         }
       };
-      const bool reg_res = RES && (has_r1 || (has_r0 && !res_smem));
+      const bool reg_res = RES && (has_r1 || (has_r0 && !res_smem && !res_tma));
       prefetch_r0(0);
       if (reg_res) load_r1(0);
       { DBG_T0; mbar_wait(TFULL_BAR(acc), acc_parity); DBG_ADD(3); }
@@ -562,7 +590,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           int4 r0v = make_int4(0, 0, 0, 0);
-          if constexpr (RES) { r0v = res_smem ? ld_shared_v4(rslot + (uint32_t)(((cc & 63) >> 3) + g) * 2048u) : r0[g]; }
+          if constexpr (RES) {
+            r0v = res_tma ? ld_shared_v4(res_row + (uint32_t)(((((cc & 63) >> 3) + g) ^ (m & 7)) << 4))
+                : res_smem ? ld_shared_v4(rslot + (uint32_t)(((cc & 63) >> 3) + g) * 2048u) : r0[g];
+          }
           sink(g, epilogue_vec8<T>(v + g * 8, bias_s + n0 + cc + g * 8, slope, RES && has_r0, r0v, RES && has_r1, r1[g]));
         }
         if (reg_res && cc + 32 < BN) load_r1(cc + 32);
@@ -630,15 +661,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ---- TMEM -> registers -> swizzled smem tile -> TMA bulk tensor store (full lines, edges clipped by TMA) ----
         // blocks of 64 channels (128-byte rows, SWIZZLE_128B)
         for (int cb = 0; cb < BN; cb += 64, ++blk) {
-          // two staging buffers per group: block k is written while the TMA store of block k-1 drains the other one
-          const uint32_t buf = cstage_base + (uint32_t)(grp * 2 + (int)(blk & 1u)) * c_stage_bytes;
+          uint32_t buf;
+          if (res_tma) {
+            // three staging buffers per group.  Block k+1's residual is TMA-loaded into buffer (k+1) % 3 while block k is
+            // computed: the buffer is free once the store of block k-2 has read it (stores k-2 .. k-1 may be pending).
+            if (issuer) {
+              int ntile = tile, ncb = cb + 64;
+              if (ncb >= BN) { ncb = 0; ntile = tile + (int)ng * (int)gridDim.x; }
+              if (ntile < num_tiles) {
+                bulk_wait_read1();
+                issue_res(ntile, ncb, (blk + 1u) % 3u);
+              }
+            }
+            buf = cstage_base + (uint32_t)(grp * 3 + (int)(blk % 3u)) * c_stage_bytes;
+            { DBG_T0; mbar_wait(RFULL_BAR(grp * 3 + (int)(blk % 3u)), (blk / 3u) & 1u); DBG_ADD(4); }
+          } else {
+            // two staging buffers per group: block k is written while the TMA store of block k-1 drains the other one
+            buf = cstage_base + (uint32_t)(grp * 2 + (int)(blk & 1u)) * c_stage_bytes;
+          }
           const uint32_t row_addr = buf + (uint32_t)(m * 128);
+          res_row = row_addr;
 #pragma unroll 1
           for (int ci = 0; ci < 2; ++ci)
             chunk(cb + ci * 32, [&](int g, const int4& o) {
               st_shared_v4(row_addr + (uint32_t)(((ci * 4 + g) ^ (m & 7)) << 4), o); });
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> visible to the TMA engine
-          { DBG_T0; if (issuer) bulk_wait_read0(); DBG_ADD(4); }   // store k-1 has finished reading the OTHER buffer
+          if (!res_tma) { DBG_T0; if (issuer) bulk_wait_read0(); DBG_ADD(4); }   // store k-1 has finished reading the OTHER buffer
           { DBG_T0; group_barrier(bar_id); DBG_ADD(5); }
           if (issuer) {
             const int pp = G > 1 ? (n0 + cb) >> blk_shift : 0;
@@ -685,9 +733,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #undef TFULL_BAR
 #undef TEMPTY_BAR
 #undef BRES_BAR
+#undef RFULL_BAR
 }
 
-typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const int);
+typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const int);
 template <typename T, bool RES>
 static TcKernelFn tc_kernel_for_t(int KC, int SUB, int G) {
   if (G == 4) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 4, RES> : conv_tc_kernel<T, 64, 1, 4, RES>;
@@ -704,7 +753,7 @@ static TcKernelFn tc_kernel_for(int KC, int SUB, int G, int is_bf16, int res) {
 }
 
 struct TcPlan {
-  CUtensorMap map_a, map_b, map_c;
+  CUtensorMap map_a, map_b, map_c, map_r;
   TcParams prm;
   size_t smem_bytes;
 };
@@ -744,7 +793,7 @@ static int make_map(CUtensorMap* map, bool bf16, void* base, int rank, const uin
 }
 
 // A/B switches for measurement (pcls_net_set_option before finalize): halo reuse, resident weights, base offset
-int tc_tma_store_mode = 1, tc_group_mode = 1;
+int tc_tma_store_mode = 1, tc_group_mode = 1, tc_res_tma_mode = 1;
 unsigned long long* tc_debug_buf = nullptr;  // [148][24] counters of the most recent launch when enabled
 int tc_halo_mode = 1, tc_resident_mode = 1, tc_base_offset_mode = 0;  // measured: UMMA swizzles on absolute smem address bits, a row-shifted start needs NO base offset
 
@@ -815,7 +864,7 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
       const int all_w_ = cp.ntaps * q.kchunks * btile_;
       const bool resident_ = tc_resident_mode && q.n_nt == 1 && all_w_ <= 112 * 1024;
       const int st_ = (130 * q.KC * 2 + 1023) / 1024 * 1024 + (resident_ ? 0 : 3 * btile_);
-      const int staging_ = 2 * TC_NG * 16384 + ((L.res0 >= 0 && q.BN <= 128) ? TC_NG * 16384 : 0);
+      const int staging_ = 2 * TC_NG * 16384 + ((L.res0 >= 0 && (q.BN <= 128 || resident_)) ? TC_NG * 16384 : 0);
       if ((max_smem - 2048 - staging_ - cp.cout_pad * 4 - (resident_ ? all_w_ + 1024 : 0)) / st_ < 3) halo = false;
     }
     if (G > 1 && cp.mode != MODE_1x1 && !halo) {  // the banded issue of a 3-tap row needs the halo tile: plan again ungrouped
@@ -871,14 +920,18 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
     }
     // residual0 is staged through smem only for the memory-bound layers (N tile <= 128): the wide Darknet layers are
     // tensor-bound and keep their smem for pipeline stages
-    q.res_smem = (L.res0 >= 0 && q.BN <= 128) ? 1 : 0;
-    const int cstage_total = (q.tma_store ? 2 * TC_NG * q.c_stage_bytes : 0) + (q.res_smem ? TC_NG * 16384 : 0);
     // pipeline depth; weights stay resident in smem when the whole layer fits next to >= 4 stages
     q.a_bytes = (q.a_rows * q.KC * 2 + 1023) / 1024 * 1024;
     q.b_tile_bytes = G > 1 ? cp.cout_pad * cin_blk * 2 : q.BN * q.KC * 2;
     const int all_w = q.n_phase * q.n_groups * q.kchunks * q.sub * q.b_tile_bytes;
     q.b_resident = (tc_resident_mode && q.n_nt == 1 && all_w <= 112 * 1024) ? 1 : 0;
     q.bres_bytes = q.b_resident ? (all_w + 1023) / 1024 * 1024 : 0;
+    // residual0 of the memory-bound layers (resident weights) with the TMA-store epilogue: TMA-loaded into a third
+    // staging buffer and added in place (no per-thread address arithmetic, a whole block of latency hiding)
+    q.res_tma = (tc_res_tma_mode && L.res0 >= 0 && q.tma_store && q.cbw == 64 && q.b_resident && (cp.res0_channels * 2) % 16 == 0) ? 1 : 0;
+    q.n_cbuf = q.res_tma ? 3 : 2;
+    q.res_smem = (!q.res_tma && L.res0 >= 0 && q.BN <= 128) ? 1 : 0;
+    const int cstage_total = (q.tma_store ? q.n_cbuf * TC_NG * q.c_stage_bytes : 0) + (q.res_smem ? TC_NG * 16384 : 0);
     if (G > 1 && !q.b_resident) { delete plan; *retry = true; return PCLS_OK; }
     const int stage_bytes = q.a_bytes + (q.b_resident ? 0 : q.sub * q.b_tile_bytes);
     int stages = (max_smem - 2048 - cp.cout_pad * 4 - q.bres_bytes - cstage_total - (cp.out_f32 ? 4 * TC_NG * 32 * 33 * 4 : 0)) / stage_bytes;
@@ -886,7 +939,7 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
     if (stages < 2) { delete plan; *retry = G > 1; return PCLS_OK; }
     q.stages = stages;
     plan->smem_bytes = (size_t)stages * stage_bytes + q.bres_bytes + cstage_total + 1024 /*alignment slack*/ +
-                       (size_t)(2 * stages + 17) * 8 + 48 + (cp.out_f32 ? 4 * TC_NG * 32 * 33 * 4 : 0) + (size_t)cp.cout_pad * 4 /*bias*/;
+                       (size_t)(2 * stages + 17 + 3 * TC_NG) * 8 + 48 + (cp.out_f32 ? 4 * TC_NG * 32 * 33 * 4 : 0) + (size_t)cp.cout_pad * 4 /*bias*/;
     // descriptors
     const uint32_t layout = swz == 128 ? 2u : swz == 64 ? 4u : 6u;  // UMMA LayoutType
     const uint32_t sbo = (uint32_t)(8 * swz) >> 4;                   // 8 rows of one swizzle span
@@ -953,6 +1006,24 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
     } else {
       plan->map_c = plan->map_a;  // unused
     }
+    plan->map_r = plan->map_c;
+    if (q.res_tma) {  // R: the residual tensor, same view as C
+      char* r_base = (char*)tensor_ptr(L.res0, frames_per_pass);
+      const uint64_t Co = (uint64_t)cp.res0_channels, Wo = (uint64_t)cp.Wout;
+      if (q.c_is_5d) {
+        const uint64_t gg = G > 1 ? (uint64_t)G : 2;
+        const uint64_t dims[5] = {Co, gg, Wo / gg, Hh, F};
+        const uint64_t str[4] = {Co * 2, Co * 2 * gg, Wo * Co * 2, Hh * Wo * Co * 2};
+        const uint32_t box[5] = {(uint32_t)q.cbw, 1, (uint32_t)q.BW, (uint32_t)q.BH, 1};
+        rc = make_map(&plan->map_r, bf16, r_base, 5, dims, str, box, 128);
+      } else {
+        const uint64_t dims[4] = {Co, Wo, Hh, F};
+        const uint64_t str[3] = {Co * 2, Wo * Co * 2, Hh * Wo * Co * 2};
+        const uint32_t box[4] = {(uint32_t)q.cbw, (uint32_t)q.BW, (uint32_t)q.BH, 1};
+        rc = make_map(&plan->map_r, bf16, r_base, 4, dims, str, box, 128);
+      }
+      if (rc) { delete plan; return rc; }
+    }
     L.tc = plan;
     L.tc_ok = true;
   return PCLS_OK;
@@ -992,7 +1063,7 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
   const int num_tiles = prm.num_tiles * nb;
   if (num_tiles == 0) return PCLS_OK;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0)<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, prm, num_tiles);
+  tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0)<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, plan->map_r, prm, num_tiles);
   return check_launch("conv_tc_kernel");
 }
 
