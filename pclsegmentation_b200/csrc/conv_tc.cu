@@ -80,6 +80,14 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
+__device__ __forceinline__ void bulk_store_1d(void* dst, uint32_t src, uint32_t bytes) {   // bytes % 16 == 0
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -568,6 +576,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool reg_res = RES && (has_r1 || (has_r0 && !res_smem && !res_tma));
       prefetch_r0(0);
       if (reg_res) load_r1(0);
+      uint8_t head_mask = 1;                                       // fused head: the mask byte travels during the MMAs
+      if (out_f32 && p.head && valid) head_mask = p.mask[pix];
       { DBG_T0; mbar_wait(TFULL_BAR(acc), acc_parity); DBG_ADD(3); }
       const unsigned long long _te = dbg ? clk() : 0ull;
       tc_fence_after();
@@ -603,20 +613,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // nets/SegmentationNetwork.py:58-69 run here on the accumulator registers: logits never travel to HBM unless
         // the caller asks for them.  Each warp stages 32 pixels x cout floats in smem so that global stores are coalesced.
         float lg[32];
+        {
+          uint32_t v[32];
+          if (BN >= 32) {
+            tmem_ld32(t_row, v);
+          } else {
+            uint32_t v16[16];
+            tmem_ld16(t_row, v16);
 #pragma unroll
-        for (int c = 0; c < 32; c += 16) {
-          uint32_t v[16];
-          if (c < BN) { tmem_ld16(t_row + (uint32_t)c, v); tmem_ld_wait(); }
+            for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0u; }
+          }
+          tmem_ld_wait();
+          // columns >= cout (padding up to the next multiple of 4) become -inf: the loops below run in uniform blocks
+          // of four classes without per-class range checks
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float x = (c < BN && c + j < cout) ? __uint_as_float(v[j]) + bias_s[n0 + c + j] : 0.0f;
-            lg[c + j] = fmaxf(x, x * slope);
+          for (int c4 = 0; c4 < 32; c4 += 4) {
+            if (c4 < cout) {
+#pragma unroll
+              for (int j = c4; j < c4 + 4; ++j) {
+                const float x = __uint_as_float(v[j]) + bias_s[n0 + j];
+                lg[j] = (j < cout) ? fmaxf(x, x * slope) : -INFINITY;
+              }
+            }
           }
         }
         float* stg = head_s + (warp - 2) * (32 * 33);
         const int64_t pix0 = __shfl_sync(0xffffffffu, pix, 0);      // pixels of a warp are consecutive in memory
         const int n_valid = __popc(__ballot_sync(0xffffffffu, valid));
         auto write_rows = [&](float* dst) {                          // lg[] of 32 pixels -> dst[pix0*cout ..] coalesced
+          if ((cout & 3) == 0) {
+            // the warp's rows form ONE contiguous span of the output: stage them in that layout, one bulk copy
+            if (lane == 0) bulk_wait_read0();                        // the previous copy has finished reading the rows
+            __syncwarp();
+#pragma unroll
+            for (int c4 = 0; c4 < 32; c4 += 4)
+              if (c4 < cout) *reinterpret_cast<float4*>(stg + lane * cout + c4) = make_float4(lg[c4], lg[c4 + 1], lg[c4 + 2], lg[c4 + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && n_valid > 0) {
+              bulk_store_1d(dst + pix0 * cout, smem_u32(stg), (uint32_t)(n_valid * cout * 4));
+              bulk_commit();
+            }
+            return;
+          }
           __syncwarp();
 #pragma unroll
           for (int c = 0; c < 32; ++c) if (c < cout) stg[lane * 33 + c] = lg[c];
@@ -642,17 +681,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // argmax over the rounded probabilities, first index on ties
           float mx = lg[0];
 #pragma unroll
-          for (int c = 1; c < 32; ++c) if (c < cout) mx = fmaxf(mx, lg[c]);
+          for (int c4 = 0; c4 < 32; c4 += 4)
+            if (c4 < cout) mx = fmaxf(fmaxf(mx, fmaxf(lg[c4], lg[c4 + 1])), fmaxf(lg[c4 + 2], lg[c4 + 3]));
           float sum = 0.0f;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) if (c < cout) { lg[c] = exp2f((lg[c] - mx) * 1.4426950408889634f); sum += lg[c]; }
+          for (int c4 = 0; c4 < 32; c4 += 4)
+            if (c4 < cout) {
+#pragma unroll
+              for (int j = c4; j < c4 + 4; ++j) { lg[j] = ex2_ftz((lg[j] - mx) * 1.4426950408889634f); sum += lg[j]; }
+            }
           const float inv = __fdividef(1.0f, sum);
           int best = 0;
           float bp = -1.0f;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) if (c < cout) { lg[c] *= inv; if (lg[c] > bp) { bp = lg[c]; best = c; } }
+          for (int c4 = 0; c4 < 32; c4 += 4)
+            if (c4 < cout) {
+#pragma unroll
+              for (int j = c4; j < c4 + 4; ++j) { lg[j] *= inv; if (lg[j] > bp) { bp = lg[j]; best = j; } }
+            }
           if (valid) {
-            if (p.mask[pix] == 0) best = p.none_index;
+            if (head_mask == 0) best = p.none_index;
             p.preds[pix] = best;
           }
           if (p.probs) write_rows(p.probs);
@@ -711,6 +759,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (dbg) { dbg_acc[6] += clk() - _te; dbg_acc[7] += 1; }
     }
     if (p.tma_store && q == 2 && lane == 0) bulk_wait_all();  // smem must outlive the last stores
+    if (out_f32 && lane == 0) bulk_wait_all();                 // (fused head: every warp issues its own bulk copies)
   }
 
   if (dbg && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 6)) {
