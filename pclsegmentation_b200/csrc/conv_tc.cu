@@ -239,6 +239,10 @@ struct TcParams {
   int res_tma;                // RES kernels with the TMA-store epilogue: residual0 blocks are TMA-loaded INTO the output
                               // staging buffers one block ahead (three buffers per group), added in place, stored by TMA
   int n_cbuf;                 // output staging buffers per epilogue group (2, or 3 with res_tma)
+  // split-N (merged Fire expand1x1 || expand3x3, nets/SqueezeSegV2.py:30-40): output channels [0, n1) have a non-zero
+  // kernel only at the centre tap.  The other eight taps then load and multiply only the weight rows [n1, BN).
+  int n1, b_small_bytes, bres_tx;
+  uint32_t idesc_small, idesc_lo;
   uint32_t desc_hi_b, idesc_blk;
   // epilogue
   int cout, out_channels, out_coff, act, out_f32, is_bf16;
@@ -299,7 +303,7 @@ template <typename T, int KC, int SUB, int G, bool RES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
-               const __grid_constant__ TcParams p, const int num_tiles) {
+               const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ TcParams p, const int num_tiles) {
   extern __shared__ uint8_t smem_raw[];
   // carve: [stages x (A tile | B tiles)] 1024-aligned, resident weights, barriers, TMEM base slot, bias
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -333,6 +337,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    if (p.n1 > 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b2) : "memory");
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     if (RES && p.res_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r) : "memory");
     for (int i = 0; i < 3 * TC_NG; ++i) mbar_init(RFULL_BAR(i), 1);
@@ -361,16 +366,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (b_resident) {
         // weight-stationary: every weight tile of the layer once per CTA, laid out in MMA iteration order
         // [phase][group][K chunk][sub] so that the issuer only increments an address
-        mbar_arrive_expect_tx_elect(BRES_BAR, (uint32_t)(n_phase * n_groups * kchunks * SUB) * b_tile_bytes);
+        mbar_arrive_expect_tx_elect(BRES_BAR, (uint32_t)p.bres_tx);
         uint32_t dst = bres_base;
         for (int ph = 0; ph < n_phase; ++ph)
           for (int g = 0; g < n_groups; ++g)
             for (int kc = 0; kc < kchunks; ++kc)
 #pragma unroll
-              for (int u = 0; u < SUB; ++u, dst += b_tile_bytes)
-                tma_load_3d_elect(dst, &map_b, BRES_BAR, kc * KC, 0, p.grp_w[ph][g][u]);
+              for (int u = 0; u < SUB; ++u) {
+                const int tap = p.grp_w[ph][g][u];
+                if (p.n1 > 0 && tap != 4) {   // rows [n1, BN) only
+                  tma_load_3d_elect(dst, &map_b2, BRES_BAR, kc * KC, p.n1, tap);
+                  dst += (uint32_t)p.b_small_bytes;
+                } else {
+                  tma_load_3d_elect(dst, &map_b, BRES_BAR, kc * KC, 0, tap);
+                  dst += b_tile_bytes;
+                }
+              }
       }
-      const uint32_t tx_bytes = (uint32_t)(p.a_rows * KC * 2) + b_stage_bytes;
+      const uint32_t a_tx_bytes = (uint32_t)(p.a_rows * KC * 2);
       const int BW = p.BW, BH = p.BH;
       const bool is5d = p.a_is_5d != 0;
       int stage = 0;
@@ -392,13 +405,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             { DBG_T0; mbar_wait(EMPTY_BAR(stage), phase ^ 1u); DBG_ADD(0); }
             const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
             const uint32_t fb = FULL_BAR(stage);
+            uint32_t tx_bytes = a_tx_bytes;
+            if (!b_resident) {
+#pragma unroll
+              for (int u = 0; u < SUB; ++u) tx_bytes += (p.n1 > 0 && wtap[u] != 4) ? (uint32_t)p.b_small_bytes : b_tile_bytes;
+            }
             mbar_arrive_expect_tx_elect(fb, tx_bytes);
             if (is5d) tma_load_5d_elect(a_dst, &map_a, fb, kc * KC, par, ww, hh, b);
             else tma_load_4d_elect(a_dst, &map_a, fb, kc * KC, ww, hh, b);
             if (!b_resident) {
 #pragma unroll
-              for (int u = 0; u < SUB; ++u)
-                tma_load_3d_elect(a_dst + a_bytes + (uint32_t)u * b_tile_bytes, &map_b, fb, kc * KC, n0, wtap[u]);
+              for (int u = 0; u < SUB; ++u) {
+                if (p.n1 > 0 && wtap[u] != 4)
+                  tma_load_3d_elect(a_dst + a_bytes + (uint32_t)u * b_tile_bytes, &map_b2, fb, kc * KC, p.n1, wtap[u]);
+                else
+                  tma_load_3d_elect(a_dst + a_bytes + (uint32_t)u * b_tile_bytes, &map_b, fb, kc * KC, n0, wtap[u]);
+              }
             }
             if (++stage == S) { stage = 0; phase ^= 1u; }
           }
@@ -423,26 +445,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)BN;
         uint32_t b_res = bres_base + (n_phase > 1 ? (uint32_t)((tile / n_nt) % n_phase) * bres_phase_bytes : 0u);
-        uint32_t accumulate = 0u;
+        uint32_t accumulate = 0u, acc_lo = 0u;
+        int kc_i = 0, g_i = 0;   // K chunk and A-load group of iteration k
         for (int k = 0; k < k_iters; ++k) {
           { DBG_T0; mbar_wait(FULL_BAR(stage), phase); DBG_ADD(2); }
           tc_fence_after();
           const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
           if constexpr (G == 1) {
             uint32_t b_addr = b_resident ? b_res : a_addr + a_bytes;
+            const uint32_t n1 = (uint32_t)p.n1;
 #pragma unroll
             for (int u = 0; u < SUB; ++u) {
               // descriptors: start address (>>4) | LBO = 1 in the low word; SBO / version / swizzle mode in the high word.
               // A row-shifted start (halo taps) needs no base offset: the swizzle is a function of absolute smem address bits.
               const uint64_t a_desc = ((uint64_t)desc_hi << 32) | (uint64_t)((((a_addr + sub_off[u]) >> 4) & 0x3FFFu) | 0x10000u);
               const uint64_t b_desc = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_addr >> 4) & 0x3FFFu) | 0x10000u);
+              if (n1 == 0u) {
 #pragma unroll
-              for (int j = 0; j < KC / 16; ++j) {  // +32 bytes along K inside the swizzle atom per UMMA_K = 16
-                umma_f16_elect(d_tmem, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j), idesc, accumulate);
-                accumulate = 1u;
+                for (int j = 0; j < KC / 16; ++j) {  // +32 bytes along K inside the swizzle atom per UMMA_K = 16
+                  umma_f16_elect(d_tmem, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j), idesc, accumulate);
+                  accumulate = 1u;
+                }
+                b_addr += b_tile_bytes;
+              } else if (p.grp_w[0][g_i][u] != 4) {
+                // split-N, outer tap: the tile holds weight rows [n1, BN) only -> accumulator columns [n1, BN)
+#pragma unroll
+                for (int j = 0; j < KC / 16; ++j) {
+                  umma_f16_elect(d_tmem + n1, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j), p.idesc_small, accumulate);
+                  accumulate = 1u;
+                }
+                b_addr += b_resident ? (uint32_t)p.b_small_bytes : b_tile_bytes;
+              } else {
+                // split-N, centre tap: full tile; columns [0, n1) see only this tap, columns [n1, BN) continue to accumulate
+                const uint32_t b_hi = b_addr + n1 * (uint32_t)(KC * 2);
+                const uint64_t b_desc_hi = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_hi >> 4) & 0x3FFFu) | 0x10000u);
+#pragma unroll
+                for (int j = 0; j < KC / 16; ++j) {
+                  umma_f16_elect(d_tmem, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j), p.idesc_lo, acc_lo);
+                  umma_f16_elect(d_tmem + n1, a_desc + (uint64_t)(2 * j), b_desc_hi + (uint64_t)(2 * j), p.idesc_small, accumulate);
+                  acc_lo = 1u; accumulate = 1u;
+                }
+                b_addr += b_tile_bytes;
               }
-              b_addr += b_tile_bytes;
             }
+            if (b_resident) b_res = b_addr;
           } else {
             // pixel-group view, banded issue: output pixel p of the group and horizontal tap u read input pixel
             // t = p + u - 1, i.e. group dq = floor(t / G) (row offset dq + 1 in the halo tile) and K offset (t mod G) * Cin;
@@ -468,7 +514,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
           }
-          b_res += (uint32_t)SUB * b_tile_bytes;
+          if constexpr (G > 1) b_res += (uint32_t)SUB * b_tile_bytes;
+          if (++kc_i == kchunks) { kc_i = 0; ++g_i; }
           umma_commit_elect(EMPTY_BAR(stage));  // smem slot free once these MMAs have read it
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
@@ -785,7 +832,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #undef RFULL_BAR
 }
 
-typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const int);
+typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const int);
 template <typename T, bool RES>
 static TcKernelFn tc_kernel_for_t(int KC, int SUB, int G) {
   if (G == 4) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 4, RES> : conv_tc_kernel<T, 64, 1, 4, RES>;
@@ -802,7 +849,7 @@ static TcKernelFn tc_kernel_for(int KC, int SUB, int G, int is_bf16, int res) {
 }
 
 struct TcPlan {
-  CUtensorMap map_a, map_b, map_c, map_r;
+  CUtensorMap map_a, map_b, map_c, map_r, map_b2;
   TcParams prm;
   size_t smem_bytes;
 };
@@ -842,7 +889,7 @@ static int make_map(CUtensorMap* map, bool bf16, void* base, int rank, const uin
 }
 
 // A/B switches for measurement (pcls_net_set_option before finalize): halo reuse, resident weights, base offset
-int tc_tma_store_mode = 1, tc_group_mode = 1, tc_res_tma_mode = 1;
+int tc_tma_store_mode = 1, tc_group_mode = 1, tc_res_tma_mode = 1, tc_split_mode = 1;
 unsigned long long* tc_debug_buf = nullptr;  // [148][24] counters of the most recent launch when enabled
 int tc_halo_mode = 1, tc_resident_mode = 1, tc_base_offset_mode = 0;  // measured: UMMA swizzles on absolute smem address bits, a row-shifted start needs NO base offset
 
@@ -887,6 +934,24 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
     if (G > 1) { q.KC = G * cin_blk; q.kchunks = 1; q.BN = G * cp.cout_pad; q.n_nt = 1; }
     const int swz = q.KC * 2;
     const int swz_b = G > 1 ? cin_blk * 2 : swz;
+    // split-N: leading output channels whose kernel is zero outside the centre tap (the expand1x1 half of a merged Fire
+    // expand layer).  Multiples of 16 channels on both sides (UMMA N granularity at M = 128).
+    q.n1 = 0;
+    if (tc_split_mode && G == 1 && cp.mode == MODE_3x3_S1 && q.n_nt == 1 && !L.pair_view) {
+      int z = 0;
+      for (; z < cp.cout_pad; ++z) {
+        bool zero = true;
+        for (int t = 0; t < 9 && zero; ++t) {
+          if (t == 4) continue;
+          const float* wr = &L.w_f32[((size_t)t * cp.cout_pad + z) * cp.cin_pad];
+          for (int ci = 0; ci < cp.cin_pad; ++ci) if (wr[ci] != 0.0f) { zero = false; break; }
+        }
+        if (!zero) break;
+      }
+      z = z / 16 * 16;
+      if (z >= 16 && q.BN - z >= 16) q.n1 = z;
+    }
+    q.b_small_bytes = (q.BN - q.n1) * q.KC * 2;
     // pixel grid tiled by BW x BH = 128
     const bool deconv = cp.mode == MODE_DECONV;  // (two-phase form; MODE_ROW3 is the single-pass form)
     q.Hgrid = cp.H;
@@ -910,7 +975,7 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
     bool halo = (cp.mode == MODE_3x3_S1 || cp.mode == MODE_ROW3) && q.BW == 128 && tc_halo_mode;
     if (halo) {
       const int btile_ = G > 1 ? cp.cout_pad * cin_blk * 2 : q.BN * q.KC * 2;
-      const int all_w_ = cp.ntaps * q.kchunks * btile_;
+      const int all_w_ = q.n1 > 0 ? q.kchunks * (btile_ + (cp.ntaps - 1) * q.b_small_bytes) : cp.ntaps * q.kchunks * btile_;
       const bool resident_ = tc_resident_mode && q.n_nt == 1 && all_w_ <= 112 * 1024;
       const int st_ = (130 * q.KC * 2 + 1023) / 1024 * 1024 + (resident_ ? 0 : 3 * btile_);
       const int staging_ = 2 * TC_NG * 16384 + ((L.res0 >= 0 && (q.BN <= 128 || resident_)) ? TC_NG * 16384 : 0);
@@ -972,7 +1037,9 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
     // pipeline depth; weights stay resident in smem when the whole layer fits next to >= 4 stages
     q.a_bytes = (q.a_rows * q.KC * 2 + 1023) / 1024 * 1024;
     q.b_tile_bytes = G > 1 ? cp.cout_pad * cin_blk * 2 : q.BN * q.KC * 2;
-    const int all_w = q.n_phase * q.n_groups * q.kchunks * q.sub * q.b_tile_bytes;
+    const int all_w = q.n1 > 0 ? q.kchunks * (q.b_tile_bytes + 8 * q.b_small_bytes)
+                               : q.n_phase * q.n_groups * q.kchunks * q.sub * q.b_tile_bytes;
+    q.bres_tx = all_w;
     q.b_resident = (tc_resident_mode && q.n_nt == 1 && all_w <= 112 * 1024) ? 1 : 0;
     q.bres_bytes = q.b_resident ? (all_w + 1023) / 1024 * 1024 : 0;
     // residual0 of the memory-bound layers (resident weights) with the TMA-store epilogue: TMA-loaded into a third
@@ -1001,6 +1068,8 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
     }
     q.idesc = (1u << 4) /*D = f32*/ | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) |
               ((uint32_t)(q.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    q.idesc_small = (q.idesc & ~(0x3Fu << 17)) | ((uint32_t)((q.BN - q.n1) >> 3) << 17);
+    q.idesc_lo = (q.idesc & ~(0x3Fu << 17)) | ((uint32_t)(q.n1 >> 3) << 17);
     q.n_acc = 2;
     while (q.n_acc < 8 && q.n_acc * 2 * q.BN <= 512) q.n_acc *= 2;
     uint32_t cols = 32;
@@ -1035,6 +1104,14 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
       rc = make_map(&plan->map_b, bf16, const_cast<void*>(cp.w), 3, dims, str, box, swz_b);
     }
     if (rc) { delete plan; return rc; }
+    plan->map_b2 = plan->map_b;
+    if (q.n1 > 0) {  // weight rows [n1, BN) of one tap
+      const uint64_t dims[3] = {(uint64_t)cp.cin_pad, (uint64_t)cp.cout_pad, (uint64_t)cp.ntaps};
+      const uint64_t str[2] = {(uint64_t)cp.cin_pad * 2, (uint64_t)cp.cin_pad * cp.cout_pad * 2};
+      const uint32_t box[3] = {(uint32_t)q.KC, (uint32_t)(q.BN - q.n1), 1};
+      rc = make_map(&plan->map_b2, bf16, const_cast<void*>(cp.w), 3, dims, str, box, swz_b);
+      if (rc) { delete plan; return rc; }
+    }
     if (q.tma_store) {  // C: the output tensor (or its re-viewed form) inside the arena
       char* c_base = (char*)tensor_ptr(L.out, frames_per_pass);
       const uint64_t Co = (uint64_t)cp.out_channels, Wo = (uint64_t)cp.Wout;
@@ -1112,7 +1189,7 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
   const int num_tiles = prm.num_tiles * nb;
   if (num_tiles == 0) return PCLS_OK;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0)<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, plan->map_r, prm, num_tiles);
+  tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0)<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, plan->map_r, plan->map_b2, prm, num_tiles);
   return check_launch("conv_tc_kernel");
 }
 
