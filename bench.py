@@ -220,6 +220,9 @@ def run_ours(args):
   for k, v in (("conv_impl", args.conv_impl), ("use_graph", args.use_graph), ("micro_batch", args.micro_batch)):
     if v is not None:
       model.set_option(k, v)
+  for kv in args.opt:                      # A/B switches of the library (pcls_net_set_option), e.g. --opt tc_vstream=1
+    k, v = kv.split("=")
+    model.set_option(k, int(v))
   lib = _lib.load()
 
   # ---- inputs: NBUF distinct raw batches resident in HBM (rotated, so consecutive steps never see the same input) ----
@@ -489,6 +492,7 @@ def main():
   ap.add_argument("--conv-impl", type=int, default=None)
   ap.add_argument("--use-graph", type=int, default=None)
   ap.add_argument("--micro-batch", type=int, default=None)
+  ap.add_argument("--opt", action="append", default=[], help="library A/B switch name=value (repeatable)")
   ap.add_argument("--op-table", default=None, help="write the per-op roofline table (JSON) here")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--ref-frames", type=int, default=2, help="--impl reference: frames per step (bounded sample)")

@@ -243,6 +243,10 @@ struct TcParams {
   // kernel only at the centre tap.  The other eight taps then load and multiply only the weight rows [n1, BN).
   int n1, b_small_bytes, bres_tx;
   uint32_t idesc_small, idesc_lo;
+  // vertical streaming (3x3 stride-1 layers with the halo tile and resident weights): a CTA walks R consecutive output
+  // rows of one 128-pixel column strip; every input row travels to smem ONCE per strip and serves the three output rows
+  // around it (R + 2 row loads per R tiles instead of 3 R).  R is chosen per launch (R = 1: plain tiles).
+  int vstream, R, n_hseg;
   uint32_t desc_hi_b, idesc_blk;
   // epilogue
   int cout, out_channels, out_coff, act, out_f32, is_bf16;
@@ -388,6 +392,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool is5d = p.a_is_5d != 0;
       int stage = 0;
       uint32_t phase = 0;
+      if (p.vstream) {
+        const int R = p.R, n_hseg = p.n_hseg, num_units = num_tiles / R;
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+          const int wt = unit % n_wt, hseg = (unit / n_wt) % n_hseg, b = unit / (n_wt * n_hseg);
+          const int ww = wt * BW - 1;
+          for (int hh = hseg * R - 1; hh <= hseg * R + R; ++hh)   // rows outside the image are zero-filled by TMA
+            for (int kc = 0; kc < kchunks; ++kc) {
+              { DBG_T0; mbar_wait(EMPTY_BAR(stage), phase ^ 1u); DBG_ADD(0); }
+              const uint32_t fb = FULL_BAR(stage);
+              mbar_arrive_expect_tx_elect(fb, a_tx_bytes);
+              tma_load_4d_elect(smem_base + (uint32_t)stage * stage_bytes, &map_a, fb, kc * KC, ww, hh, b);
+              if (++stage == S) { stage = 0; phase ^= 1u; }
+            }
+        }
+      } else
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int r = tile;
         const int nt = r % n_nt; r /= n_nt;
@@ -440,7 +459,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0, acc = 0, acc_phase = 0;
       if (b_resident) mbar_wait(BRES_BAR, 0u);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // vertical streaming: ring position of load (input row h - 1, K chunk 0) of the current output row h; loads are
+      // numbered in the producer's order, [0, vs_waited) have been waited for
+      const bool vs = p.vstream != 0;
+      const int vs_R = vs ? p.R : 1;
+      const int my_tiles = vs ? ((num_tiles / vs_R - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * vs_R
+                              : (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      uint32_t vs_slot = 0, vs_phase = 0, vs_idx = 0, vs_waited = 0;
+      int vs_row = 0;
+      auto vs_release = [&](int n) {   // the n oldest loads are no longer needed once the MMAs issued so far have completed
+        for (int i = 0; i < n; ++i) {
+          umma_commit_elect(EMPTY_BAR(vs_slot));
+          if (++vs_slot == (uint32_t)S) { vs_slot = 0; vs_phase ^= 1u; }
+        }
+        vs_idx += (uint32_t)n;
+      };
+      for (int seq = 0; seq < my_tiles; ++seq) {
+        const int tile = blockIdx.x + seq * gridDim.x;   // (only the transposed-conv phase below reads it; not vstream)
         { DBG_T0; mbar_wait(TEMPTY_BAR(acc), acc_phase ^ 1u); DBG_ADD(1); }  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)BN;
@@ -448,9 +483,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint32_t accumulate = 0u, acc_lo = 0u;
         int kc_i = 0, g_i = 0;   // K chunk and A-load group of iteration k
         for (int k = 0; k < k_iters; ++k) {
-          { DBG_T0; mbar_wait(FULL_BAR(stage), phase); DBG_ADD(2); }
+          uint32_t a_addr;
+          if (vs) {
+            uint32_t sl = vs_slot + (uint32_t)k, par = vs_phase;
+            if (sl >= (uint32_t)S) { sl -= (uint32_t)S; par ^= 1u; }
+            if (vs_idx + (uint32_t)k >= vs_waited) {
+              { DBG_T0; mbar_wait(FULL_BAR(sl), par); DBG_ADD(2); }
+              vs_waited = vs_idx + (uint32_t)k + 1u;
+            }
+            a_addr = smem_base + sl * stage_bytes;
+          } else {
+            { DBG_T0; mbar_wait(FULL_BAR(stage), phase); DBG_ADD(2); }
+            a_addr = smem_base + (uint32_t)stage * stage_bytes;
+          }
           tc_fence_after();
-          const uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
           if constexpr (G == 1) {
             uint32_t b_addr = b_resident ? b_res : a_addr + a_bytes;
             const uint32_t n1 = (uint32_t)p.n1;
@@ -516,8 +562,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           if constexpr (G > 1) b_res += (uint32_t)SUB * b_tile_bytes;
           if (++kc_i == kchunks) { kc_i = 0; ++g_i; }
-          umma_commit_elect(EMPTY_BAR(stage));  // smem slot free once these MMAs have read it
-          if (++stage == S) { stage = 0; phase ^= 1u; }
+          if (!vs) {
+            umma_commit_elect(EMPTY_BAR(stage));  // smem slot free once these MMAs have read it
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+          }
+        }
+        if (vs) {  // input row h - 1 is done; the last output row of the strip also retires rows h and h + 1
+          if (++vs_row == vs_R) { vs_row = 0; vs_release(3 * kchunks); }
+          else vs_release(kchunks);
         }
         umma_commit_elect(TFULL_BAR(acc));  // accumulator complete
         if (++acc == n_acc) { acc = 0; acc_phase ^= 1u; }
@@ -564,9 +616,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (c_is_5d) tma_load_5d(dst, &map_r, bar, c02, G > 1 ? pp2 : ph2, wt2 * BW, ht2 * BH, b2);
       else tma_load_4d(dst, &map_r, bar, c02, wt2 * BW, ht2 * BH, b2);
     };
-    if (RES && p.res_tma != 0 && has_r0 && issuer && (uint32_t)grp < ng && (int)(blockIdx.x + grp * gridDim.x) < num_tiles)
-      issue_res((int)(blockIdx.x + grp * gridDim.x), 0, 0u);
-    for (int tile = blockIdx.x; tile < num_tiles && (uint32_t)grp < ng; tile += gridDim.x, ++tl) {
+    // the CTA's seq-th tile as a flat index of the plain (nt, phase, wt, ht, b) encoding, or -1 past the end
+    const bool vs = p.vstream != 0;
+    const int vs_R = vs ? p.R : 1, vs_hseg = p.n_hseg;
+    auto tile_at = [&](uint32_t seq) -> int {
+      if (!vs) {
+        const long long t = (long long)blockIdx.x + (long long)seq * gridDim.x;
+        return t < num_tiles ? (int)t : -1;
+      }
+      const int unit = (int)blockIdx.x + (int)(seq / (uint32_t)vs_R) * (int)gridDim.x;
+      if (unit >= num_tiles / vs_R) return -1;
+      const int i = (int)(seq % (uint32_t)vs_R);
+      const int uwt = unit % n_wt, hseg = (unit / n_wt) % vs_hseg, ub = unit / (n_wt * vs_hseg);
+      return (ub * n_ht + hseg * vs_R + i) * n_wt + uwt;   // n_nt = n_phase = 1 in this mode
+    };
+    if (RES && p.res_tma != 0 && has_r0 && issuer && (uint32_t)grp < ng && tile_at((uint32_t)grp) >= 0)
+      issue_res(tile_at((uint32_t)grp), 0, 0u);
+    for (; (uint32_t)grp < ng; ++tl) {
+      const int tile = tile_at(tl);
+      if (tile < 0) break;
       if ((int)(tl % ng) != grp) continue;
       int r = tile;
       const int nt = r % n_nt; r /= n_nt;
@@ -762,8 +830,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // computed: the buffer is free once the store of block k-2 has read it (stores k-2 .. k-1 may be pending).
             if (issuer) {
               int ntile = tile, ncb = cb + 64;
-              if (ncb >= BN) { ncb = 0; ntile = tile + (int)ng * (int)gridDim.x; }
-              if (ntile < num_tiles) {
+              if (ncb >= BN) { ncb = 0; ntile = tile_at(tl + ng); }
+              if (ntile >= 0) {
                 bulk_wait_read1();
                 issue_res(ntile, ncb, (blk + 1u) % 3u);
               }
@@ -889,7 +957,7 @@ static int make_map(CUtensorMap* map, bool bf16, void* base, int rank, const uin
 }
 
 // A/B switches for measurement (pcls_net_set_option before finalize): halo reuse, resident weights, base offset
-int tc_tma_store_mode = 1, tc_group_mode = 1, tc_res_tma_mode = 1, tc_split_mode = 1;
+int tc_tma_store_mode = 1, tc_group_mode = 1, tc_res_tma_mode = 1, tc_split_mode = 1, tc_vstream_mode = 0;
 unsigned long long* tc_debug_buf = nullptr;  // [148][24] counters of the most recent launch when enabled
 int tc_halo_mode = 1, tc_resident_mode = 1, tc_base_offset_mode = 0;  // measured: UMMA swizzles on absolute smem address bits, a row-shifted start needs NO base offset
 
@@ -1054,6 +1122,8 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
     if (stages > 12) stages = 12;
     if (stages < 2) { delete plan; *retry = G > 1; return PCLS_OK; }
     q.stages = stages;
+    q.vstream = (tc_vstream_mode && halo && cp.mode == MODE_3x3_S1 && q.b_resident && stages >= 3 * q.kchunks + 1) ? 1 : 0;
+    q.R = 1; q.n_hseg = q.Hgrid;
     plan->smem_bytes = (size_t)stages * stage_bytes + q.bres_bytes + cstage_total + 1024 /*alignment slack*/ +
                        (size_t)(2 * stages + 17 + 3 * TC_NG) * 8 + 48 + (cp.out_f32 ? 4 * TC_NG * 32 * 33 * 4 : 0) + (size_t)cp.cout_pad * 4 /*bias*/;
     // descriptors
@@ -1188,7 +1258,16 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
   prm.probs = head_args.probs; prm.preds = head_args.preds; prm.logits = head_args.logits;
   const int num_tiles = prm.num_tiles * nb;
   if (num_tiles == 0) return PCLS_OK;
-  const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  int work = num_tiles;
+  if (prm.vstream) {
+    // rows per strip: the longest run that still leaves >= 6 strips per SM (wave quantisation), R | H
+    int R = 1;
+    for (int r = 32; r > 1; r /= 2)
+      if (prm.Hgrid % r == 0 && (long long)nb * prm.n_wt * (prm.Hgrid / r) >= 6LL * sm_count()) { R = r; break; }
+    prm.R = R; prm.n_hseg = prm.Hgrid / R;
+    work = num_tiles / R;
+  }
+  const int grid = work < sm_count() ? work : sm_count();
   tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0)<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, plan->map_r, plan->map_b2, prm, num_tiles);
   return check_launch("conv_tc_kernel");
 }

@@ -745,6 +745,7 @@ extern "C" int pcls_net_set_option(pcls_net* net, const char* name, int value) {
   if (!strcmp(name, "tc_group")) { tc_group_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_res_tma")) { tc_res_tma_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_split")) { tc_split_mode = value; return PCLS_OK; }
+  if (!strcmp(name, "tc_vstream")) { tc_vstream_mode = value; return PCLS_OK; }
   if (!strcmp(name, "fuse_head")) { n->fuse_head = value != 0; n->drop_graphs(); return PCLS_OK; }
   if (!strcmp(name, "tc_debug")) {  // per-role wait-cycle counters of conv_tc_kernel (development aid)
     if (value && !tc_debug_buf) { PCLS_CHECK_CUDA(cudaMalloc(&tc_debug_buf, 148 * 24 * 8)); PCLS_CHECK_CUDA(cudaMemset(tc_debug_buf, 0, 148 * 24 * 8)); }
