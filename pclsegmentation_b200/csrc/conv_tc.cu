@@ -203,6 +203,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // kernel parameters
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int TC_MAX_TAPS = 9;
+// Vertical streaming of input rows (see TcParams::vstream) is compiled out by default: measured -0.7 % on SqueezeSegV2
+// (the 3x3 layers it applies to are bound by the epilogue or by the tensor pipe's A-operand reads, not by TMA), and its
+// code in the issuer loop costs the tensor-bound Darknet layers instruction-cache room.  -DPCLS_TC_VSTREAM=1 enables it.
+#ifndef PCLS_TC_VSTREAM
+#define PCLS_TC_VSTREAM 0
+#endif
 constexpr int TC_NG = 2;                        // epilogue warp-groups (4 warps each); tiles are dealt round-robin
 constexpr int TC_THREADS = 64 + 128 * TC_NG;    // warp 0 TMA producer, warp 1 MMA issuer, then the epilogue groups
 
@@ -392,7 +398,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool is5d = p.a_is_5d != 0;
       int stage = 0;
       uint32_t phase = 0;
-      if (p.vstream) {
+      if (PCLS_TC_VSTREAM && p.vstream) {
         const int R = p.R, n_hseg = p.n_hseg, num_units = num_tiles / R;
         for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
           const int wt = unit % n_wt, hseg = (unit / n_wt) % n_hseg, b = unit / (n_wt * n_hseg);
@@ -461,7 +467,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (b_resident) mbar_wait(BRES_BAR, 0u);
       // vertical streaming: ring position of load (input row h - 1, K chunk 0) of the current output row h; loads are
       // numbered in the producer's order, [0, vs_waited) have been waited for
-      const bool vs = p.vstream != 0;
+      const bool vs = PCLS_TC_VSTREAM && p.vstream != 0;
       const int vs_R = vs ? p.R : 1;
       const int my_tiles = vs ? ((num_tiles / vs_R - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * vs_R
                               : (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -617,7 +623,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       else tma_load_4d(dst, &map_r, bar, c02, wt2 * BW, ht2 * BH, b2);
     };
     // the CTA's seq-th tile as a flat index of the plain (nt, phase, wt, ht, b) encoding, or -1 past the end
-    const bool vs = p.vstream != 0;
+    const bool vs = PCLS_TC_VSTREAM && p.vstream != 0;
     const int vs_R = vs ? p.R : 1, vs_hseg = p.n_hseg;
     auto tile_at = [&](uint32_t seq) -> int {
       if (!vs) {
@@ -1122,7 +1128,7 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
     if (stages > 12) stages = 12;
     if (stages < 2) { delete plan; *retry = G > 1; return PCLS_OK; }
     q.stages = stages;
-    q.vstream = (tc_vstream_mode && halo && cp.mode == MODE_3x3_S1 && q.b_resident && stages >= 3 * q.kchunks + 1) ? 1 : 0;
+    q.vstream = (PCLS_TC_VSTREAM && tc_vstream_mode && halo && cp.mode == MODE_3x3_S1 && q.b_resident && stages >= 3 * q.kchunks + 1) ? 1 : 0;
     q.R = 1; q.n_hseg = q.Hgrid;
     plan->smem_bytes = (size_t)stages * stage_bytes + q.bres_bytes + cstage_total + 1024 /*alignment slack*/ +
                        (size_t)(2 * stages + 17 + 3 * TC_NG) * 8 + 48 + (cp.out_f32 ? 4 * TC_NG * 32 * 33 * 4 : 0) + (size_t)cp.cout_pad * 4 /*bias*/;
