@@ -19,6 +19,8 @@ SOURCES = ["error.cu", "projection.cu", "head.cu", "input_stage.cu", "confusion.
            "net.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
+# development builds, e.g. PCLS_NVCC_FLAGS="-DPCLS_TC_DEBUG=1" (wait-cycle counters) or "-DPCLS_TC_VSTREAM=1"
+NVCC_FLAGS += os.environ.get("PCLS_NVCC_FLAGS", "").split()
 
 
 def _nvcc():

@@ -108,6 +108,9 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, const int4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ unsigned long long clk() { unsigned long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)); return t; }
+#ifndef PCLS_TC_DEBUG
+#define PCLS_TC_DEBUG 0
+#endif
 #define DBG_T0 const unsigned long long _t0 = dbg ? clk() : 0ull
 #define DBG_ADD(slot) if (dbg) dbg_acc[slot] += clk() - _t0
 // ---- warp-uniform issue: the WHOLE warp executes these with identical operands, the instruction itself is predicated
@@ -340,7 +343,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   float* head_s = bias_s + ((p.n_nt * p.BN + 3) & ~3);  // [4 * TC_NG warps][32][33] staging of the fused head (out_f32 layers)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned long long* const dbg = p.dbg;
+  // wait-cycle counters (tools/tc_debug_run.py): compiled in only with -DPCLS_TC_DEBUG=1, the `if (dbg)` tests and the
+  // sixteen counter registers are measurable in the epilogue loops
+  unsigned long long* const dbg = PCLS_TC_DEBUG ? p.dbg : nullptr;
   unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const unsigned long long dbg_start = dbg ? clk() : 0ull;
 
@@ -964,6 +969,7 @@ static int make_map(CUtensorMap* map, bool bf16, void* base, int rank, const uin
 
 // A/B switches for measurement (pcls_net_set_option before finalize): halo reuse, resident weights, base offset
 int tc_tma_store_mode = 1, tc_group_mode = 1, tc_res_tma_mode = 1, tc_split_mode = 1, tc_vstream_mode = 0;
+const int tc_debug_compiled = PCLS_TC_DEBUG;
 unsigned long long* tc_debug_buf = nullptr;  // [148][24] counters of the most recent launch when enabled
 int tc_halo_mode = 1, tc_resident_mode = 1, tc_base_offset_mode = 0;  // measured: UMMA swizzles on absolute smem address bits, a row-shifted start needs NO base offset
 

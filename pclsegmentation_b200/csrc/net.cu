@@ -748,6 +748,7 @@ extern "C" int pcls_net_set_option(pcls_net* net, const char* name, int value) {
   if (!strcmp(name, "tc_vstream")) { tc_vstream_mode = value; return PCLS_OK; }
   if (!strcmp(name, "fuse_head")) { n->fuse_head = value != 0; n->drop_graphs(); return PCLS_OK; }
   if (!strcmp(name, "tc_debug")) {  // per-role wait-cycle counters of conv_tc_kernel (development aid)
+    PCLS_REQUIRE(!value || tc_debug_compiled, "tc_debug needs a library built with PCLS_NVCC_FLAGS=-DPCLS_TC_DEBUG=1");
     if (value && !tc_debug_buf) { PCLS_CHECK_CUDA(cudaMalloc(&tc_debug_buf, 148 * 24 * 8)); PCLS_CHECK_CUDA(cudaMemset(tc_debug_buf, 0, 148 * 24 * 8)); }
     if (!value && tc_debug_buf) { cudaFree(tc_debug_buf); tc_debug_buf = nullptr; }
     return PCLS_OK;

@@ -15,6 +15,7 @@ struct TensorInfo {
 
 struct TcPlan;  // tcgen05 launch plan of one conv layer (conv_tc.cu)
 extern int tc_halo_mode, tc_resident_mode, tc_base_offset_mode, tc_tma_store_mode, tc_group_mode, tc_res_tma_mode, tc_split_mode, tc_vstream_mode;
+extern const int tc_debug_compiled;
 extern unsigned long long* tc_debug_buf;  // A/B measurement switches (process-wide)
 
 struct ConvLayer {
