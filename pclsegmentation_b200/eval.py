@@ -32,7 +32,7 @@ def evaluation(arg):
   config, model = load_model_config(arg.model, arg.config)
   config.DATA_AUGMENTATION = False
   if arg.path_to_model and os.path.exists(arg.path_to_model):
-    model.load_weights_npz(arg.path_to_model)
+    model.load_weights(arg.path_to_model)
   elif rank == 0:
     print("No weight file given/found: using the Keras-default initialisation")
 
@@ -64,7 +64,7 @@ def main(argv=None):
   parser.add_argument('-d', '--data_path', type=str, help='Absolute path to the dataset')
   parser.add_argument('-i', '--image_set', type=str, default="val", help='Default: `val`. But can also be train, val or test')
   parser.add_argument('-t', '--eval_dir', type=str, help="Kept for CLI compatibility (the reference writes nothing there)")
-  parser.add_argument('-p', '--path_to_model', type=str, help='Path to the model weights (.npz)')
+  parser.add_argument('-p', '--path_to_model', type=str, help='Path to the model: Keras SavedModel dir / checkpoint prefix (read without TensorFlow) or .npz')
   parser.add_argument('-m', '--model', type=str, help='Model name either `squeezesegv2`, `darknet53`, `darknet21`')
   parser.add_argument('-n', '--config', type=str, default='squeezesegv2',
                       help='Which configuration `squeezesegv2`, `squeezesegv2kitti`, `squeezesegv2nuscenes`, '

@@ -3,8 +3,9 @@ matched by --input_path it writes ``pred_<name>.npy`` (int32 [H,W] class ids) pl
 
     python -m pclsegmentation_b200.inference -d './samples/*.npy' -m squeezesegv2 -t ./out -p weights.npz
 
-Differences, all documented in DESIGN.md: --path_to_model takes the ``.npz`` weight container (Keras attribute paths;
-absent -> Keras-default initialisation, as a freshly constructed reference model); --config selects the ``mc`` factory
+Differences, all documented in DESIGN.md: --path_to_model takes the reference's SavedModel directory / checkpoint prefix
+(its TensorBundle is read without TensorFlow, utils/tensor_bundle.py) or an ``.npz`` container keyed by Keras attribute
+paths (absent -> Keras-default initialisation, as a freshly constructed reference model); --config selects the ``mc`` factory
 (the reference hard-codes SqueezeSegV2Config, inference.py:37 - that is the default here); the normalise / mask stage
 (inference.py:50-62) runs fused on the GPU; --batch frames go through the network per call.
 """
@@ -22,7 +23,7 @@ def inference(arg):
   import torch
   config, model = load_model_config(arg.model or "squeezesegv2", arg.config)
   if arg.path_to_model and os.path.exists(arg.path_to_model):
-    model.load_weights_npz(arg.path_to_model)
+    model.load_weights(arg.path_to_model)
   else:
     print("No weight file given/found: using the Keras-default initialisation")
 
@@ -62,7 +63,7 @@ def main(argv=None):
   parser.add_argument('-m', '--model', type=str, help='Model name either `squeezesegv2`, `darknet53`, `darknet21`')
   parser.add_argument('-t', '--output_dir', type=str,
                       help="Directory where to write the model predictions and visualizations")
-  parser.add_argument('-p', '--path_to_model', type=str, help='Path to the model weights (.npz)')
+  parser.add_argument('-p', '--path_to_model', type=str, help='Path to the model: Keras SavedModel dir / checkpoint prefix (read without TensorFlow) or .npz')
   parser.add_argument('-n', '--config', type=str, default='squeezesegv2', help='Which `mc` configuration to use')
   parser.add_argument('-b', '--batch', type=int, default=8, help='frames per forward call')
   parser.add_argument('--no_plots', action='store_true', help='only write pred_*.npy')

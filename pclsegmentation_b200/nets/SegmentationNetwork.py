@@ -87,6 +87,27 @@ class PCLSegmentationNetwork:
     with np.load(path) as f:
       self.set_weights_dict({k: f[k] for k in f.files})
 
+  def load_weights(self, path):
+    """`--path_to_model` of inference.py:128 / eval.py:73.  Accepts what the reference's training writes - a Keras
+    SavedModel directory (`train.py:60`) or a checkpoint prefix (`train.py:42`), read without TensorFlow by
+    utils/tensor_bundle.py - or the neutral `.npz` container keyed by Keras attribute paths.  Every variable of the
+    network must be present (metrics / optimizer entries of the checkpoint are ignored)."""
+    if str(path).endswith(".npz"):
+      return self.load_weights_npz(path)
+    from ..utils import tensor_bundle
+    found = tensor_bundle.load_keras_variables(path)
+    mine = {k: v for k, v in found.items() if k in self._graph.variables}
+    missing = sorted(set(self._graph.variables) - set(mine))
+    if missing:
+      raise KeyError("%s: %d of %d network variables are missing (first: %s); the checkpoint holds %d variables, e.g. %s"
+                     % (path, len(missing), len(self._graph.variables), missing[:3], len(found), sorted(found)[:3]))
+    self.set_weights_dict(mine)
+
+  def save_weights_bundle(self, prefix):
+    """Writes the variables as a TensorBundle (checkpoint prefix) under their Keras object-graph keys."""
+    from ..utils import tensor_bundle
+    tensor_bundle.write_bundle(prefix, {k + "/.ATTRIBUTES/VARIABLE_VALUE": v for k, v in self._graph.variables.items()})
+
   def randomize_batch_norm(self, seed=0):
     """Random BN statistics / affine (mu ~ N(0,0.1), var ~ U(0.5,1.5), gamma ~ U(0.8,1.2), beta ~ N(0,0.1)) so that
     the BN folding is exercised; random biases ~ N(0, 0.05) likewise."""
