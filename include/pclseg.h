@@ -238,7 +238,13 @@ int64_t pcls_net_workspace_bytes(const pcls_net* net);
 /* Execution knobs (all CUDA; for A/B measurement and debugging):
  *   "conv_impl"  0 = tcgen05 implicit-GEMM where the shape allows (default), 1 = CUDA-core direct kernel
  *   "use_graph"  1 = replay the forward as a CUDA graph (default), 0 = plain launches
- *   "micro_batch" frames per pass through the graph (0 = whole batch) */
+ *   "micro_batch" frames per pass through the graph (0 = whole batch)
+ *   "fuse_head"  1 = softmax / argmax / mask in the epilogue of the final convolution (default), 0 = separate kernel
+ * planning switches of the tcgen05 path, process-wide, to be set BEFORE pcls_net_finalize (all default 1):
+ *   "tc_halo" (one 130-pixel tile serves three horizontal taps), "tc_resident" (weights stay in smem), "tc_group"
+ *   (pixel-group view for 16 / 32-channel inputs), "tc_tma_store" (TMA-store epilogue), "tc_res_tma" (residual blocks
+ *   TMA-loaded into the output staging buffers), "tc_split" (outer taps skip the expand1x1 half of merged Fire expands)
+ * "tc_debug" (wait-cycle counters) needs a library built with PCLS_NVCC_FLAGS=-DPCLS_TC_DEBUG=1. */
 int pcls_net_set_option(pcls_net* net, const char* name, int value);
 
 #ifdef __cplusplus

@@ -275,6 +275,37 @@ def test_whole_net_logits_and_labels(impl, name, cfg, H, W, B):
   assert np.array_equal(y2.numpy(), preds.numpy())
 
 
+@pytest.mark.parametrize("name,cfg,H,W,B", [("squeezesegv2", "squeezesegv2nuscenes", 32, 1024, 2),
+                                            ("darknet21", "darknet21", 32, 240, 2)])
+def test_whole_net_bf16_storage(name, cfg, H, W, B):
+  """The bf16 instantiation of every kernel (PCLS_BF16: bf16 storage, fp32 accumulation).  bf16 keeps 8 mantissa bits
+  against fp16's 11, so the logits tolerance is 8x the fp16 one; labels must agree wherever the oracle's two best
+  logits are further apart than twice that tolerance."""
+  from pclsegmentation_b200 import _lib
+  mc, model = _model(name, cfg, H, W)
+  model.precision = _lib.PCLS_BF16
+  model._release()
+  rng = np.random.default_rng(77)
+  raw = synth_range_images(rng, B, H, W, valid_rate=0.78, num_classes=mc.NUM_CLASS)
+  lidar, mask = _prep(mc, raw)
+  lg_ref, pr_ref, pd_ref = _oracle(mc, model, name, lidar, mask)
+  res = model.forward_device(torch.from_numpy(lidar).cuda(), torch.from_numpy(mask).cuda(), want_logits=True)
+  lg = res["logits"].cpu().numpy()
+  scale = max(1.0, float(np.abs(lg_ref).max()) / 4.0)
+  tol = 8 * LOGIT_TOL * scale
+  err = np.abs(lg - lg_ref).max()
+  assert err <= tol, "max abs logit error %g (tolerance %g)" % (err, tol)
+  assert np.abs(res["probabilities"].cpu().numpy() - pr_ref).max() <= err + 1e-6
+  same = res["predictions"].cpu().numpy() == pd_ref
+  top2 = np.sort(lg_ref, axis=-1)[..., -2:]
+  decidable = mask & ((top2[..., 1] - top2[..., 0]) > 2 * tol)
+  assert decidable.sum() > 0.3 * mask.sum()
+  assert same[decidable].mean() >= 0.999, same[decidable].mean()
+  assert same[mask].mean() >= 0.98, same[mask].mean()
+  _report(name + "/bf16", cfg, H, W, B, 0, err, float(np.abs(lg_ref).max()), float(same[mask].mean()),
+          float(same[decidable].mean()))
+
+
 def test_micro_batch_and_graph_replay_are_equivalent():
   mc, model = _model("squeezesegv2", "squeezesegv2", 32, 240)
   rng = np.random.default_rng(2)
