@@ -19,6 +19,7 @@ class MeanIoU:
     self.num_classes = int(num_classes)
     self.name = name
     self._cm = None
+    self._cmw = None      # float64 matrix of weighted updates (test_step); None until the first weighted update
     self._dropped = None
 
   def _ensure(self):
@@ -30,20 +31,34 @@ class MeanIoU:
 
   def update_state(self, y_true, y_pred, sample_weight=None):
     """cm[label, pred] += 1 over every element (eval.py passes no weights: masked pixels count as None/None)."""
-    if sample_weight is not None:
-      raise NotImplementedError("weighted MeanIoU is only used by train/test_step (training side)")
     cm = self._ensure()
     label = to_device(y_true, torch.int32).reshape(-1)
     pred = to_device(y_pred, torch.int32).reshape(-1)
     if label.numel() != pred.numel():
       raise ValueError("label and prediction sizes differ: %d vs %d" % (label.numel(), pred.numel()))
+    if sample_weight is not None:
+      # test_step (nets/SegmentationNetwork.py:129): tf.math.confusion_matrix(..., weights=w) sums the weights per cell.
+      # Not on the inference hot path: float64 accumulation with torch.bincount on the device.
+      w = to_device(sample_weight, torch.float32).reshape(-1).to(torch.float64)
+      if w.numel() != label.numel():
+        raise ValueError("weights and label sizes differ: %d vs %d" % (w.numel(), label.numel()))
+      nc = self.num_classes
+      ok = (label >= 0) & (label < nc) & (pred >= 0) & (pred < nc)
+      idx = label.to(torch.int64) * nc + pred.to(torch.int64)
+      if self._cmw is None:
+        self._cmw = torch.zeros((nc, nc), dtype=torch.float64, device=cm.device)
+      self._cmw += torch.bincount(idx[ok], weights=w[ok], minlength=nc * nc).reshape(nc, nc)
+      self._dropped += (~ok).sum()
+      return
     _lib.check(_lib.load().pcls_confusion_update(ptr(label), ptr(pred), label.numel(), self.num_classes, ptr(cm),
                                                  ptr(self._dropped), stream_handle()), "pcls_confusion_update")
 
   @property
   def total_cm(self):
-    """[NC,NC] int64 CUDA tensor, rows = label, cols = prediction (tf.math.confusion_matrix layout)."""
-    return self._ensure()
+    """[NC,NC] CUDA tensor, rows = label, cols = prediction (tf.math.confusion_matrix layout): int64 counts, or
+    float64 once weighted updates have been made."""
+    cm = self._ensure()
+    return cm if self._cmw is None else cm.to(torch.float64) + self._cmw
 
   @property
   def dropped(self):
@@ -55,7 +70,7 @@ class MeanIoU:
 
   def result(self):
     """Mean IoU over the classes whose denominator is non-zero (tf.keras.metrics.MeanIoU.result)."""
-    cm = self._ensure().cpu().numpy()
+    cm = self.total_cm.cpu().numpy()
     tp = np.diag(cm).astype(np.float64)
     denom = (cm.sum(0) + cm.sum(1)).astype(np.float64) - tp
     valid = denom != 0
@@ -69,5 +84,6 @@ class MeanIoU:
     if self._cm is not None:
       self._cm.zero_()
       self._dropped.zero_()
+    self._cmw = None
 
   reset_state = reset_states

@@ -3,8 +3,9 @@
 Mirrors pcl_segmentation/nets/SegmentationNetwork.py: the constructor fields (:31-53), the ``call`` contract
 ``model([lidar_input, lidar_mask]) -> (probabilities, predictions)`` (:55-69), ``predict_step`` (:133-136), the
 ``miou_tracker`` and ``get_config`` (:144-151).  The forward itself - the traced layer graph plus ``segmentation_head``
-(softmax -> argmax -> depth-zero mask, :58-69) - runs in libpclseg (pcls_net_forward).  Training members
-(``train_step``, losses, optimizer) are out of scope of this inference path.
+(softmax -> argmax -> depth-zero mask, :58-69) - runs in libpclseg (pcls_net_forward).  ``test_step`` (:118-131) with
+both losses (:71-91, :49) and the weighted MeanIoU is provided forward-only; ``train_step`` and the optimizer are out of
+scope of this inference path.
 """
 import ctypes
 
@@ -15,6 +16,13 @@ from .. import _lib
 from ..device import DeviceTensor, ptr, require_cuda, stream_handle, to_device, wrap
 from ..metrics import MeanIoU
 from .layers import Graph
+
+
+def _dev(x, dtype):
+  """host array / CUDA tensor (incl. the DeviceTensor wrappers the forward returns) -> plain CUDA tensor of `dtype`."""
+  if torch.is_tensor(x) and x.is_cuda:
+    return x.detach().as_subclass(torch.Tensor).to(dtype)
+  return to_device(x, dtype)
 
 
 class PCLSegmentationNetwork:
@@ -32,6 +40,7 @@ class PCLSegmentationNetwork:
     assert self.NUM_FEATURES == 6, "the path implements the reference's 6-channel input (5 lidar channels + mask)"
 
     self.miou_tracker = MeanIoU(num_classes=self.NUM_CLASS, name="MeanIoU")
+    self._loss_sum, self._loss_count = 0.0, 0          # loss_tracker = tf.keras.metrics.Mean (:53)
 
     self.precision = _lib.PCLS_F16
     self.net_options = {}
@@ -212,13 +221,41 @@ class PCLSegmentationNetwork:
     (lidar_input, lidar_mask), _, _ = data
     return self([lidar_input, lidar_mask], training=False)
 
+  # ---- validation-side losses (forward only; nets/SegmentationNetwork.py:71-91, :49).  Not on the inference hot path:
+  # a handful of elementwise torch ops on the device tensors the forward produced. ----
+  def focal_loss(self, probabilities, lidar_mask, label, loss_weight):
+    """sum((1 - p)^gamma * onehot * -log(p) * w * mask) / sum(mask) * CLS_LOSS_COEF with p = probabilities +
+    DENOM_EPSILON (nets/SegmentationNetwork.py:71-91)."""
+    nc = self.NUM_CLASS
+    prob = _dev(probabilities, torch.float32).reshape(-1, nc) + float(self.mc.DENOM_EPSILON)
+    mask = _dev(lidar_mask, torch.float32).reshape(-1, 1)
+    onehot = torch.nn.functional.one_hot(_dev(label, torch.int64).reshape(-1), nc).to(torch.float32)
+    ce = onehot * -torch.log(prob) * _dev(loss_weight, torch.float32).reshape(-1, 1) * mask
+    fl = (1.0 - prob) ** float(self.mc.FOCAL_GAMMA) * ce
+    return fl.sum() / mask.sum() * float(self.mc.CLS_LOSS_COEF)
+
+  def scc_loss(self, label, probabilities, weight):
+    """tf.keras.losses.SparseCategoricalCrossentropy() on probabilities with sample weights (:49, :125): Keras clips
+    the probabilities to [1e-7, 1 - 1e-7], takes -log_softmax(log p)[label] (i.e. renormalises the clipped row),
+    multiplies by the weight and averages over ALL elements (SUM_OVER_BATCH_SIZE)."""
+    nc = self.NUM_CLASS
+    p = _dev(probabilities, torch.float32).reshape(-1, nc).clamp(1e-7, 1.0 - 1e-7)
+    logp = torch.log(p) - torch.log(p.sum(dim=1, keepdim=True))
+    picked = logp.gather(1, _dev(label, torch.int64).reshape(-1, 1)).reshape(-1)
+    return (-picked * _dev(weight, torch.float32).reshape(-1)).sum() / picked.numel()
+
   def test_step(self, data):
-    """Forward + weighted MeanIoU update (nets/SegmentationNetwork.py:118-131); the loss is training-side and not
-    computed here."""
+    """Forward, loss and weighted MeanIoU update (nets/SegmentationNetwork.py:118-131)."""
     (lidar_input, lidar_mask), label, weight = data
     probabilities, predictions = self([lidar_input, lidar_mask], training=False)
-    self.miou_tracker.update_state(label, predictions)
-    return {'miou': self.miou_tracker.result()}
+    if self.mc.USE_FOCAL_LOSS:
+      loss = self.focal_loss(probabilities, lidar_mask, label, weight)
+    else:
+      loss = self.scc_loss(label, probabilities, weight)
+    self._loss_sum += float(loss)
+    self._loss_count += 1
+    self.miou_tracker.update_state(label, predictions, weight)
+    return {'loss': np.float32(self._loss_sum / self._loss_count), 'miou': self.miou_tracker.result()}
 
   @property
   def metrics(self):

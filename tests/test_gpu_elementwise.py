@@ -98,3 +98,54 @@ def test_confusion_out_of_range_pairs_are_dropped_and_counted():
   m = MeanIoU(4)
   m.update_state(np.array([0, 1, 7, -1, 2], np.int32), np.array([0, 9, 1, 1, 2], np.int32))
   assert int(m.total_cm.sum()) == 2 and m.dropped == 3
+
+
+@pytest.mark.gpu
+def test_test_step_losses_and_weighted_miou():
+  """test_step (nets/SegmentationNetwork.py:118-131): focal loss (:71-91), Keras sparse categorical cross-entropy on
+  probabilities with sample weights (:49), running mean of the loss, weighted confusion matrix - against float64 numpy
+  restatements of the same formulas on the probabilities / predictions the GPU forward returned."""
+  from pclsegmentation_b200.utils.args_loader import load_model_config
+  from tests.util import synth_range_images
+  from oracle import nn as O
+  mc, model = load_model_config("squeezesegv2", "squeezesegv2")
+  model.randomize_batch_norm(2)
+  H, W, NC = mc.ZENITH_LEVEL, mc.AZIMUTH_LEVEL, mc.NUM_CLASS
+  rng = np.random.default_rng(5)
+  raw = synth_range_images(rng, 2, H, W, valid_rate=0.7, num_classes=NC)
+  lidar, mask, label = [], [], []
+  for b in range(raw.shape[0]):
+    l, m, y = O.input_stage(raw[b], mc.INPUT_MEAN, mc.INPUT_STD, mc.CLASSES.index("None"))
+    lidar.append(l); mask.append(m); label.append(y)
+  lidar, mask, label = np.stack(lidar), np.stack(mask), np.stack(label).astype(np.int32)
+  weight = np.asarray(mc.CLS_LOSS_WEIGHT, np.float32)[label] if hasattr(mc, "CLS_LOSS_WEIGHT") else \
+      rng.uniform(0.5, 2.0, label.shape).astype(np.float32)
+  probs, preds = model([lidar, mask])
+  p = probs.numpy().astype(np.float64).reshape(-1, NC)
+  y = label.reshape(-1)
+  w = weight.astype(np.float64).reshape(-1)
+  m = mask.astype(np.float64).reshape(-1)
+  # focal loss
+  pe = p + mc.DENOM_EPSILON
+  onehot = np.eye(NC)[y]
+  fl = ((1.0 - pe) ** mc.FOCAL_GAMMA * onehot * -np.log(pe) * w[:, None] * m[:, None]).sum() / m.sum() * mc.CLS_LOSS_COEF
+  got_fl = float(model.focal_loss(probs, mask, label, weight))
+  assert abs(got_fl - fl) <= 2e-5 * max(1.0, abs(fl)), (got_fl, fl)
+  # sparse categorical cross-entropy (Keras: clip, renormalise, weight, mean over all elements)
+  pc = np.clip(p, 1e-7, 1 - 1e-7)
+  scc = (-(np.log(pc[np.arange(len(y)), y]) - np.log(pc.sum(1))) * w).sum() / len(y)
+  got_scc = float(model.scc_loss(label, probs, weight))
+  assert abs(got_scc - scc) <= 2e-5 * max(1.0, abs(scc)), (got_scc, scc)
+  # test_step: running mean of the loss over two steps + weighted MeanIoU
+  model.miou_tracker.reset_states()
+  r1 = model.test_step(((lidar, mask), label, weight))
+  r2 = model.test_step(((lidar, mask), label, weight))
+  expect = fl if mc.USE_FOCAL_LOSS else scc
+  assert abs(float(r1["loss"]) - expect) <= 1e-4 * max(1.0, abs(expect))
+  assert abs(float(r2["loss"]) - expect) <= 1e-4 * max(1.0, abs(expect))
+  cm = np.zeros((NC, NC))
+  np.add.at(cm, (y, preds.numpy().reshape(-1)), w)
+  got_cm = model.miou_tracker.total_cm.cpu().numpy()
+  assert np.allclose(got_cm, 2 * cm, rtol=1e-9, atol=1e-6)
+  tp = np.diag(cm); den = cm.sum(0) + cm.sum(1) - tp
+  assert abs(float(r2["miou"]) - (tp[den > 0] / den[den > 0]).mean()) < 1e-6
