@@ -214,9 +214,12 @@ template <> __device__ __forceinline__ int4 neg_inf8<__nv_bfloat16>() { return m
 template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool3x3_s2_kernel(const int4* __restrict__ in, int4* __restrict__ out, int64_t n_cols, int H, int Win, int Wout,
-                     int CV, int pad_left) {
+                     int CV, int pad_left, int rows_per_seg) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (frame, wo, cv)
   if (i >= n_cols) return;
+  // blockIdx.y = row segment: a column walk keeps only one row of loads (48 B) per thread in flight, so the grid must
+  // offer ~2 x the SMs' thread capacity to cover the DRAM latency; segments pay two halo rows each
+  const int h0 = blockIdx.y * rows_per_seg, h1 = min(H, h0 + rows_per_seg);
   const int cv = (int)(i % CV);
   const int wo = (int)((i / CV) % Wout);
   const int64_t b = i / ((int64_t)CV * Wout);
@@ -235,8 +238,8 @@ maxpool3x3_s2_kernel(const int4* __restrict__ in, int4* __restrict__ out, int64_
     }
     return m;
   };
-  int4 prev = NEG, cur = hrow(0);
-  for (int h = 0; h < H; ++h) {
+  int4 prev = hrow(h0 - 1), cur = hrow(h0);
+  for (int h = h0; h < h1; ++h) {
     const int4 nxt = hrow(h + 1);
     oimg[(int64_t)h * Wout * CV] = max8<T>(max8<T>(prev, cur), nxt);
     prev = cur; cur = nxt;
@@ -248,8 +251,14 @@ int launch_maxpool3x3_s2(const T* in, T* out, int B, int H, int Win, int Wout, i
   const int CV = C / 8;
   const int64_t n_cols = (int64_t)B * Wout * CV;
   if (n_cols == 0) return PCLS_OK;
-  maxpool3x3_s2_kernel<T><<<(unsigned)ceil_div(n_cols, 256), 256, 0, s>>>(
-      reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), n_cols, H, Win, Wout, CV, pad_left);
+  // row segments: enough threads for >= 2 full waves of 2048 threads per SM, at least 8 rows per segment
+  int segs = (int)ceil_div((int64_t)sm_count() * 2048 * 2, n_cols);
+  if (segs > H / 8) segs = H / 8;
+  if (segs < 1) segs = 1;
+  const int rows_per_seg = (int)ceil_div(H, segs);
+  segs = (int)ceil_div(H, rows_per_seg);
+  maxpool3x3_s2_kernel<T><<<dim3((unsigned)ceil_div(n_cols, 256), (unsigned)segs), 256, 0, s>>>(
+      reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), n_cols, H, Win, Wout, CV, pad_left, rows_per_seg);
   return check_launch("maxpool3x3_s2_kernel");
 }
 template int launch_maxpool3x3_s2<__half>(const __half*, __half*, int, int, int, int, int, int, cudaStream_t);
