@@ -238,11 +238,11 @@ maxpool3x3_s2_kernel(const int4* __restrict__ in, int4* __restrict__ out, int64_
     }
     return m;
   };
-  int4 prev = hrow(h0 - 1), cur = hrow(h0);
+  int4 prev = hrow(h0 - 1), cur = hrow(h0), nxt = hrow(h0 + 1);
   for (int h = h0; h < h1; ++h) {
-    const int4 nxt = hrow(h + 1);
+    const int4 nxt2 = (h + 1 < h1) ? hrow(h + 2) : NEG;   // two rows of loads in flight per thread
     oimg[(int64_t)h * Wout * CV] = max8<T>(max8<T>(prev, cur), nxt);
-    prev = cur; cur = nxt;
+    prev = cur; cur = nxt; nxt = nxt2;
   }
 }
 
