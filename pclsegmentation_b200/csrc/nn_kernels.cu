@@ -323,7 +323,7 @@ template <int C> struct CamGeom {
 
 template <typename T, int C>
 __global__ void __launch_bounds__(256, 2)
-cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int H, int W) {
+cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int H, int W, int rows_per_seg) {
   using G = CamGeom<C>;
   constexpr int CV = G::CV, TW = G::TW, PITCH = G::PITCH, ROWB = G::ROWB, NB = G::NB, DIST = G::DIST;
   constexpr int R = C / 16;                // reduced channels (4 or 8)
@@ -391,8 +391,13 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
   }
   for (int i = threadIdx.x; i < TW * 8; i += 256)                          // b1, replicated per pixel (zero beyond R)
     reinterpret_cast<float*>(St + 2 * CVG * STILE)[i] = (i % 8) < R ? p.b1[i % 8] : 0.0f;
+  // blockIdx.z = row segment [h0, h1) of the strip (small batches: more CTAs than SMs; a segment re-reads three rows
+  // above and below).  The walk starts at input row a0 = max(h0 - 3, 0).
+  const int h0 = blockIdx.z * rows_per_seg, h1 = min(H, h0 + rows_per_seg);
+  const int a0 = h0 - 3 < 0 ? 0 : h0 - 3;
+  sptr += (unsigned)a0 * (unsigned)rowv;
   auto stage_row = [&](int r, int slot) {
-    if (r < H) {
+    if (r < H && r <= h1 + 2) {
 #pragma unroll
       for (int k = 0; k < LPT; ++k)
         if (sok[k])
@@ -407,25 +412,25 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
   const unsigned a_off = c * PITCH + cv * 16;                              // ring: pixel c - 3 (+ d * PITCH), this vector
   const unsigned s_off = (c * 8 + 2 * t) * 4;                              // squeeze tile: pixel c, columns 2t, 2t+1
   const bool col_ok = (w0 + c) < W;
-  unsigned optr = (unsigned)((w0 + c) * CV + cv);
+  unsigned optr = (unsigned)((w0 + c) * CV + cv) + (unsigned)h0 * (unsigned)rowv;
 
   int4 win[7];   // horizontal maxima of the last seven input rows (slot = row mod 7)
 #pragma unroll
   for (int k = 0; k < 7; ++k) win[k] = NEG;
 
-  for (int r = 0; r < DIST; ++r) stage_row(r, r);
-  int sc = 0;                                                              // ring slot of row r (r mod NB)
-  for (int r0 = 0; r0 < H + 4; r0 += 7) {
+  for (int r = 0; r < DIST; ++r) stage_row(a0 + r, r);
+  int sc = 0;                                                              // ring slot of row r ((r - a0) mod NB)
+  for (int r0 = a0; r0 < h1 + 4; r0 += 7) {
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
       const int r = r0 + j;
-      if (r >= H + 4) break;
+      if (r >= h1 + 4) break;
       stage_row(r + DIST, sc + DIST >= NB ? sc + DIST - NB : sc + DIST);
       asm volatile("cp.async.wait_group %0;" ::"n"(DIST) : "memory");    // row r has landed (this thread's copies)
       __syncthreads();
 
       // ---------------- phase A: pooled row r - 3, squeeze partial sums -> tiles [r & 1] ----------------
-      if (r < H + 3) {
+      if (r < h1 + 3) {
         int4 hm = NEG;                                                     // rows below the image pad with -inf
         if (r < H) {
           const unsigned char* src = ring + sc * ROWB + a_off;
@@ -437,7 +442,7 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
           for (int d = 4; d < 7; ++d) hm = max8<T>(hm, *reinterpret_cast<const int4*>(src + d * PITCH));
         }
         win[j] = hm;
-        if (r >= 3) {
+        if (r >= h0 + 3) {
           int4 vm = win[0];
 #pragma unroll
           for (int k = 1; k < 7; ++k) vm = max8<T>(vm, win[k]);
@@ -451,7 +456,7 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
       }
 
       // ---------------- phase B: gate and store row r - 4 (tiles [(r - 1) & 1]) ----------------
-      if (r >= 4) {
+      if (r >= h0 + 4) {
         float2 sv = *reinterpret_cast<const float2*>(St + 2 * CVG * STILE + s_off);   // b1
 #pragma unroll
         for (int k = 0; k < CVG; ++k) {
@@ -486,7 +491,13 @@ int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, cud
   PCLS_REQUIRE(p.C == 64 || p.C == 128, "CAM: channels must be 64 or 128, got %d", p.C);
   PCLS_REQUIRE(p.R == p.C / 16, "CAM: reduced channels must be C/16");
   const int TW = 256 / (p.C / 8);
-  dim3 grid((unsigned)ceil_div(W, TW), (unsigned)B);
+  // row segments for small batches: at least two waves of two CTAs per SM, at least 8 rows per segment
+  int segs = (int)ceil_div((int64_t)sm_count() * 4, ceil_div(W, TW) * (int64_t)B);
+  if (segs > H / 8) segs = H / 8;
+  if (segs < 1) segs = 1;
+  const int rows_per_seg = (int)ceil_div(H, segs);
+  segs = (int)ceil_div(H, rows_per_seg);
+  dim3 grid((unsigned)ceil_div(W, TW), (unsigned)B, (unsigned)segs);
   const int smem = p.C == 64 ? CamGeom<64>::SMEM : CamGeom<128>::SMEM;   // ring + P/O tiles, see cam_kernel
   auto kern = p.C == 64 ? cam_kernel<T, 64> : cam_kernel<T, 128>;
   static bool configured[2] = {false, false};
@@ -495,7 +506,7 @@ int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, cud
     PCLS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured[p.C == 128] = true;
   }
-  kern<<<grid, 256, smem, s>>>(reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), p, H, W);
+  kern<<<grid, 256, smem, s>>>(reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), p, H, W, rows_per_seg);
   return check_launch("cam_kernel");
 }
 template int launch_cam<__half>(const __half*, __half*, const CamParams&, int, int, int, cudaStream_t);
