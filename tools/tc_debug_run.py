@@ -1,3 +1,10 @@
+"""Prints the per-role wait-cycle counters of every conv_tc_kernel launch of one forward (producer / issuer / epilogue).
+Needs a library built with the counters compiled in:
+
+    PCLS_NVCC_FLAGS=-DPCLS_TC_DEBUG=1 python -m pclsegmentation_b200.build --force && python tools/tc_debug_run.py
+
+(rebuild without the flag afterwards: the counters cost 2.6 % on SqueezeSegV2).
+"""
 import sys, ctypes, numpy as np, torch
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
