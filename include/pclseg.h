@@ -115,6 +115,11 @@ int pcls_input_stage(const float* sample, int channels, int64_t n_pixels, const 
                      const double* h_std5, int none_index, float* lidar, uint8_t* mask,
                      int32_t* label, pcls_stream stream);
 
+/* float64 -> float32 narrowing on the device (round to nearest even), for the float64 `[H,W,6]` range-image files
+ * the reference's converters write (dataset_convert/semantic_kitti.py:173) and inference.py:47 / the data loader cast
+ * on the host.  in: n doubles (16-byte aligned), out: n floats. */
+int pcls_cast_f64_f32(const double* in, float* out, int64_t n, pcls_stream stream);
+
 /* Replaces tf.keras.metrics.MeanIoU.update_state (eval.py:41,48; tf.math.confusion_matrix +
  * assign_add): cm[label, pred] += 1 for every pixel (rows = label, cols = prediction).
  *   cm [NC*NC] i64 accumulated in place (the caller zeroes it once).  Pairs outside [0,NC) are an

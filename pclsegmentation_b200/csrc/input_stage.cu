@@ -30,7 +30,35 @@ input_stage_kernel(const float* __restrict__ sample, int channels, int64_t n_pix
   }
 }
 
+// float64 -> float32 (round to nearest even, what numpy's astype / TF's cast do): the range-image files of the reference
+// are float64 on disk (dataset_convert/semantic_kitti.py:173); uploading them as they are and narrowing on the device
+// takes the conversion pass off the host.  16 bytes in, 8 bytes out per thread and step.
+__global__ void __launch_bounds__(256)
+cast_f64_f32_kernel(const double2* __restrict__ in, float2* __restrict__ out, int64_t n_pairs, const double* __restrict__ in1,
+                    float* __restrict__ out1, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += stride) {
+    const double2 v = in[i];
+    out[i] = make_float2((float)v.x, (float)v.y);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out1[n - 1] = (float)in1[n - 1];
+}
+
 }  // namespace pcls
+
+extern "C" int pcls_cast_f64_f32(const double* in, float* out, int64_t n, pcls_stream stream) {
+  using namespace pcls;
+  PCLS_REQUIRE(n >= 0, "pcls_cast_f64_f32: negative n");
+  if (n == 0) return PCLS_OK;
+  PCLS_REQUIRE(in != nullptr && out != nullptr, "pcls_cast_f64_f32: NULL buffer");
+  PCLS_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 7) == 0, "pcls_cast_f64_f32: buffers must be 16 / 8 byte aligned");
+  int64_t blocks = ceil_div(n / 2 + 1, 256);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  cast_f64_f32_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double2*>(in),
+                                                                    reinterpret_cast<float2*>(out), n / 2, in, out, n);
+  return check_launch("cast_f64_f32_kernel");
+}
 
 extern "C" int pcls_input_stage(const float* sample, int channels, int64_t n_pixels, const double* h_mean5,
                                 const double* h_std5, int none_index, float* lidar, uint8_t* mask,

@@ -74,6 +74,22 @@ def to_device(x, dtype, pinned_cache=None, key=None):
   return _h2d(t, dev)
 
 
+def samples_to_device(samples, pinned_cache=None, key="samples"):
+  """[B,H,W,C] range images (numpy float64 as stored by the reference's converters, or float32, or a CUDA tensor) ->
+  float32 CUDA tensor.  float64 input is uploaded as it is and narrowed on the device (pcls_cast_f64_f32), which keeps
+  the host out of the conversion pass inference.py:47 / data_loader.py do with numpy."""
+  if torch.is_tensor(samples) and samples.is_cuda and samples.dtype == torch.float32:
+    return samples.contiguous()
+  is64 = (samples.dtype == torch.float64) if torch.is_tensor(samples) else (np.asarray(samples).dtype == np.float64)
+  if not is64:
+    return to_device(samples, torch.float32, pinned_cache, key)
+  from . import _lib
+  d = to_device(samples, torch.float64, pinned_cache, key)
+  out = torch.empty(d.shape, dtype=torch.float32, device=d.device)
+  _lib.check(_lib.load().pcls_cast_f64_f32(ptr(d), ptr(out), d.numel(), stream_handle()), "pcls_cast_f64_f32")
+  return out
+
+
 _d2h_streams = {}
 _d2h_pinned = {}
 

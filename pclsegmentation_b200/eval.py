@@ -41,7 +41,7 @@ def evaluation(arg):
   if rank == 0:
     print("Performing Evaluation")
   for i in range(0, len(files), arg.batch):
-    samples = np.stack([np.load(f).astype(np.float32, copy=False) for f in files[i:i + arg.batch]])
+    samples = np.stack([np.load(f) for f in files[i:i + arg.batch]])   # float64 files are narrowed on the device
     ev.update(samples)
   rep = ev.finish()
 

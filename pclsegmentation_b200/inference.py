@@ -15,6 +15,7 @@ import os
 
 import numpy as np
 
+from .device import samples_to_device
 from .utils.args_loader import load_model_config
 from .utils.util import normalize
 
@@ -33,8 +34,8 @@ def inference(arg):
   files = sorted(glob.iglob(arg.input_path))
   for i in range(0, len(files), arg.batch):
     chunk = files[i:i + arg.batch]
-    samples = np.stack([np.load(f).astype(np.float32, copy=False) for f in chunk])
-    res = model.forward_device(torch.from_numpy(samples).cuda(), None, mean=config.INPUT_MEAN, std=config.INPUT_STD,
+    samples = np.stack([np.load(f) for f in chunk])          # float64 on disk: uploaded as is, narrowed on the device
+    res = model.forward_device(samples_to_device(samples), None, mean=config.INPUT_MEAN, std=config.INPUT_STD,
                                want_probabilities=False)
     predictions = res["predictions"].cpu().numpy()
     for f, sample, pred in zip(chunk, samples, predictions):

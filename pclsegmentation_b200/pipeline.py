@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .device import ptr, stream_handle, to_device
+from .device import ptr, samples_to_device, stream_handle, to_device
 from .laserscan import SphericalProjector
 from .metrics import MeanIoU
 from .sharding import Communicator, shard_range
@@ -61,10 +61,10 @@ class Evaluator:
     self._std = (ctypes.c_double * 5)(*np.asarray(self.mc.INPUT_STD).reshape(-1))
 
   def update(self, samples):
-    """samples: [B,H,W,6] float32 (x,y,z,i,d,label) numpy or CUDA tensor - the .npy frames of the dataset.
+    """samples: [B,H,W,6] float64 / float32 (x,y,z,i,d,label) numpy or CUDA tensor - the .npy frames of the dataset.
     Runs the fused input stage + forward + head, fixes the labels up (label[~mask] = None, data_loader.py:176) and
     accumulates the confusion matrix; nothing returns to the host."""
-    x = to_device(samples, torch.float32)
+    x = samples_to_device(samples)
     B, H, W, C = x.shape
     if C != 6:
       raise ValueError("evaluation samples need 6 channels (x,y,z,intensity,depth,label)")

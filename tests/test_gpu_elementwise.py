@@ -149,3 +149,26 @@ def test_test_step_losses_and_weighted_miou():
   assert np.allclose(got_cm, 2 * cm, rtol=1e-9, atol=1e-6)
   tp = np.diag(cm); den = cm.sum(0) + cm.sum(1) - tp
   assert abs(float(r2["miou"]) - (tp[den > 0] / den[den > 0]).mean()) < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [0, 1, 7, 4096, 32 * 240 * 6 * 3 + 1])
+def test_cast_f64_f32_is_numpy_astype(n):
+  """pcls_cast_f64_f32 == numpy's astype(float32) bit for bit (round to nearest even), incl. values that are not
+  representable in float32, subnormals, infinities and odd lengths."""
+  rng = np.random.default_rng(n)
+  x = rng.normal(0, 50, n)
+  if n >= 7:
+    x[:7] = [0.1, -1e-45, 3.4028235677973366e38, 1e39, -np.inf, 16777217.0, 1.0000000596046448]
+  d = torch.from_numpy(x).cuda()
+  out = torch.empty(n, dtype=torch.float32, device="cuda")
+  lib = _lib.load()
+  with np.errstate(over="ignore"):
+    want = x.astype(np.float32)
+  _lib.check(lib.pcls_cast_f64_f32(d.data_ptr(), out.data_ptr(), n, torch.cuda.current_stream().cuda_stream))
+  got = out.cpu().numpy()
+  assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+  from pclsegmentation_b200.device import samples_to_device
+  if n > 0:
+    t = samples_to_device(x.reshape(1, 1, 1, n))
+    assert t.dtype == torch.float32 and np.array_equal(t.cpu().numpy().reshape(-1).view(np.uint32), want.view(np.uint32))
