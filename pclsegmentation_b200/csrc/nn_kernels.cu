@@ -491,10 +491,15 @@ int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, cud
   PCLS_REQUIRE(p.C == 64 || p.C == 128, "CAM: channels must be 64 or 128, got %d", p.C);
   PCLS_REQUIRE(p.R == p.C / 16, "CAM: reduced channels must be C/16");
   const int TW = 256 / (p.C / 8);
-  // row segments for small batches: at least two waves of two CTAs per SM, at least 8 rows per segment
-  int segs = (int)ceil_div((int64_t)sm_count() * 4, ceil_div(W, TW) * (int64_t)B);
-  if (segs > H / 8) segs = H / 8;
-  if (segs < 1) segs = 1;
+  // row segments (>= 8 rows each): minimise  waves x iterations per CTA  with two CTAs resident per SM; a segment of n
+  // rows runs n + 7 iterations (three rows of halo above / below and the pipeline drain)
+  const int64_t strips = ceil_div(W, TW) * (int64_t)B, slots = (int64_t)sm_count() * 2;
+  int segs = 1;
+  int64_t best = -1;
+  for (int sgs = 1; sgs <= (H >= 8 ? H / 8 : 1); ++sgs) {
+    const int64_t cost = ceil_div(strips * sgs, slots) * (ceil_div(H, sgs) + 7);
+    if (best < 0 || cost < best) { best = cost; segs = sgs; }
+  }
   const int rows_per_seg = (int)ceil_div(H, segs);
   segs = (int)ceil_div(H, rows_per_seg);
   dim3 grid((unsigned)ceil_div(W, TW), (unsigned)B, (unsigned)segs);
