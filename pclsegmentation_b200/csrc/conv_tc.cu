@@ -10,15 +10,24 @@
 //                  by TMA, which IS the SAME padding (no im2col buffer, no halo code).  The stride-2 convolutions read a
 //                  5-D view (C, 2, W/2, H, B) of the same buffer: TF's asymmetric SAME padding for even W (0 left /
 //                  1 right) makes tap kx land on (parity kx&1, pair wo + (kx>>1)), never left of the image.
-//   B operand      folded weights packed [tap][Cout][Cin] (K-major), one TMA load per iteration.
-//   MMA            tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BN x K=16, fp32 accumulators in TMEM,
-//                  double-buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
-//   epilogue       tcgen05.ld -> +bias (BatchNorm folded) -> ReLU / LeakyReLU -> + residual(s) -> 16-bit NHWC store at a
-//                  channel offset (tf.concat) or float32 logits.  The transposed convolution runs as two phases
-//                  (even / odd output columns), each a 2-tap GEMM whose rows are scattered to columns 2j + phase.
+//   A variants     3x3 stride-1 layers >= 128 pixels wide: ONE 130-pixel tile (1-pixel halo) per input row serves the three
+//                  horizontal taps, the UMMA descriptor starts 0 / 1 / 2 rows into it.  Inputs with 16 / 32 channels:
+//                  G = 4 / 2 adjacent pixels form one 128-byte row (pixel-group view) and the MMAs are issued banded.
+//   B operand      folded weights packed [tap][Cout][Cin] (K-major); resident in smem for the whole kernel when the
+//                  layer fits, else one TMA load per iteration.  Split-N: output channels [0, n1) that are zero outside
+//                  the centre tap (merged Fire expand1x1 || expand3x3) are skipped by the eight outer taps.
+//   MMA            tcgen05.mma.cta_group::1.kind::f16, M=128 x N=BN x K=16, fp32 accumulators in TMEM, 2-8 accumulator
+//                  buffers (n_acc x BN <= 512 columns) so the epilogue of tile i overlaps the MMAs of tiles i+1...
+//   epilogue       tcgen05.ld x32 -> +bias (BatchNorm folded) -> ReLU / LeakyReLU -> + residual(s) -> 16-bit NHWC output at
+//                  a channel offset (tf.concat): swizzled smem tile + TMA bulk tensor store when the N tile is a multiple
+//                  of 64 channels (residual blocks are TMA-loaded into the same staging buffers one block ahead), else
+//                  16-byte stores; or float32 logits with the segmentation head (softmax / argmax / mask) fused.
+//                  The transposed convolution runs as ONE 3-tap GEMM with N = 2 Cout (net.cu: build_deconv_row3); the
+//                  two-phase form (even / odd output columns) remains for shapes that form rejects.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
-// (TMEM lane quarter = warp_id % 4).  mbarrier rings: full/empty per smem stage, tmem_full/tmem_empty per accumulator.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (both run warp-uniformly, the
+// instruction is predicated on elect.sync), warps 2-9 = two epilogue groups that alternate tiles (TMEM lane quarter =
+// warp_id % 4).  mbarrier rings: full/empty per smem stage, tmem_full/tmem_empty per accumulator.
 #include "net.cuh"
 
 #include <cuda.h>
