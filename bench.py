@@ -33,6 +33,7 @@ WORKLOADS = {
   "squeezesegv2_kitti_64x2048_b32": ("squeezesegv2", "squeezesegv2kitti", 64, 2048, 32),
   "darknet21_kitti_64x2048_b32": ("darknet21", "darknet53kitti", 64, 2048, 32),
   "darknet53_kitti_64x2048_b16": ("darknet53", "darknet53kitti", 64, 2048, 16),
+  "darknet53_kitti_64x2048_b64": ("darknet53", "darknet53kitti", 64, 2048, 64),
   "squeezesegv2_nuscenes_32x1024_b32": ("squeezesegv2", "squeezesegv2nuscenes", 32, 1024, 32),
 }
 DEFAULT_WORKLOAD = "squeezesegv2_kitti_64x2048_b32"
@@ -195,26 +196,137 @@ def run_reference(args):
     "gpu_launches": 0}))
 
 
-def run_ours(args):
+class Ranks:
+  """torch.distributed plumbing of one bench process (one rank per GPU)."""
+
+  def __init__(self):
+    import torch
+    import torch.distributed as dist
+    self.torch, self.dist = torch, dist
+    self.rank, self.local_rank, self.world = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), \
+        int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+      raise SystemExit("bench.py: no CUDA device - this implementation has no CPU fallback (use --impl reference "
+                       "for the CPU baseline)")
+    torch.cuda.set_device(self.local_rank)
+    self.dev = torch.device("cuda", self.local_rank)
+    if self.world > 1:
+      dist.init_process_group("nccl", device_id=self.dev)
+
+  def barrier(self):
+    if self.world > 1:
+      self.dist.barrier()
+    self.torch.cuda.synchronize()
+
+  def max_over_ranks(self, v):
+    t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+    if self.world > 1:
+      self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+    return float(t.item())
+
+  def close(self):
+    if self.world > 1:
+      self.dist.destroy_process_group()
+
+
+def timed_steps(rk, step, steps, warmup):
+  """`warmup` untimed steps, then exactly `steps` steps bracketed by barrier + synchronize on both sides, timed with CUDA
+  events on the launching stream; returns (max-over-ranks total ms, per-step latencies of this rank, clocks of rank 0)."""
+  torch = rk.torch
+  for i in range(max(warmup, 3)):
+    step(i)
+  rk.barrier()
+  sampler = ClockSampler(rk.local_rank)
+  if rk.rank == 0:
+    sampler.start()
+    time.sleep(0.3)
+  ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+  rk.barrier()
+  ev[0].record()
+  for i in range(steps):
+    step(i)
+    ev[i + 1].record()
+  rk.barrier()
+  total_ms = ev[0].elapsed_time(ev[-1])
+  lat = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+  clocks = sampler.stop() if rk.rank == 0 else None
+  return rk.max_over_ranks(total_ms), lat, clocks
+
+
+def op_roofline(lib, model, mc, sub, pb, outs, peaks, step_ms, B, op_table_path=None, workload=""):
+  """Per-op CUDA-event table at the benchmarked batch -> roofline of the op with the largest share + whole-step totals."""
   import torch
-  import torch.distributed as dist
   from pclsegmentation_b200 import _lib
+  net = model._net
+  n_ops = lib.pcls_net_num_ops(net)
+  ms = (ctypes.c_float * n_ops)()
+  acc = np.zeros(n_ops)
+  mean_p = (ctypes.c_double * 5)(*mc.INPUT_MEAN.reshape(-1))
+  std_p = (ctypes.c_double * 5)(*mc.INPUT_STD.reshape(-1))
+  reps = 5 if pb * mc.ZENITH_LEVEL * mc.AZIMUTH_LEVEL <= 32 * 64 * 2048 and "darknet" not in workload else 2
+  for r in range(reps + 1):
+    _lib.check(lib.pcls_net_profile_ops(net, sub.data_ptr(), 5, None, mean_p, std_p, pb, None,
+                                        outs["probabilities"].data_ptr(), outs["predictions"].data_ptr(), ms,
+                                        torch.cuda.current_stream().cuda_stream), "pcls_net_profile_ops")
+    if r:
+      acc += np.array(list(ms))
+  acc /= reps
+  table = []
+  tot_by = tot_fl = 0
+  for i in range(n_ops):
+    name = ctypes.create_string_buffer(64)
+    fam, fl, by = ctypes.c_int(), ctypes.c_int64(), ctypes.c_int64()
+    lib.pcls_net_op_info(net, i, name, ctypes.byref(fam), ctypes.byref(fl), ctypes.byref(by))
+    tot_by += by.value
+    tot_fl += fl.value
+    t_s = acc[i] / 1e3
+    gbs = by.value * pb / t_s / 1e9 if t_s > 0 else 0.0
+    tfs = fl.value * pb / t_s / 1e12 if t_s > 0 else 0.0
+    ai = fl.value / max(by.value, 1)
+    bound = "tensor" if (fam.value == 1 and ai > peaks["tflops_sustained"] * 1e3 / peaks["hbm_gbs"]) else "hbm"
+    table.append({"op": name.value.decode(), "ms": float(acc[i]), "share": 0.0, "GB/s": gbs, "TFLOP/s": tfs,
+                  "bound": bound, "family": "tcgen05" if fam.value else "cuda-core",
+                  "frac": (tfs / peaks["tflops_sustained"]) if bound == "tensor" else gbs / peaks["hbm_gbs"],
+                  "algorithmic_bytes_per_frame": by.value, "flops_per_frame": fl.value})
+  tot = sum(r["ms"] for r in table)
+  for r in table:
+    r["share"] = r["ms"] / tot if tot else 0.0
+  top = max(table, key=lambda r: r["ms"])
+  if top["bound"] == "tensor":
+    roof = {"bound": "tensor", "achieved": top["TFLOP/s"], "peak": peaks["tflops_sustained"], "unit": "TFLOP/s"}
+  else:
+    roof = {"bound": "hbm", "achieved": top["GB/s"], "peak": peaks["hbm_gbs"], "unit": "GB/s"}
+  traffic = None
+  for tname in ("ncu_traffic_r2.json", "ncu_traffic_r1.json"):
+    tpath = os.path.join(ROOT, "profiles", tname)
+    if os.path.exists(tpath):  # DRAM bytes per launch of this kernel from the committed ncu --set full capture (same batch)
+      t = json.load(open(tpath)).get(top["op"])
+      if t and t.get("batch") == pb:
+        traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
+        break
+  roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, kernel=top["op"], share_of_step=top["share"],
+              peak_source=peaks["source"], batch_profiled=pb,
+              algorithmic_bytes_per_launch=top["algorithmic_bytes_per_frame"] * pb if roof["unit"] == "GB/s" else None,
+              flops_per_launch=top["flops_per_frame"] * pb,
+              ops_above_1pct_below_half=[{"op": r["op"], "share": round(r["share"], 4), "frac": round(r["frac"], 3)}
+                                         for r in table if r["share"] > 0.01 and r["frac"] < 0.5])
+  step_s = step_ms / 1e3
+  whole = {"algorithmic_GB_per_frame": tot_by / 1e9, "GFLOP_per_frame": tot_fl / 1e9,
+           "achieved_GB/s": tot_by * B / step_s / 1e9, "achieved_TFLOP/s": tot_fl * B / step_s / 1e12,
+           "frac_of_hbm_peak": tot_by * B / step_s / 1e9 / peaks["hbm_gbs"],
+           "frac_of_tensor_peak": tot_fl * B / step_s / 1e12 / peaks["tflops_sustained"]}
+  if op_table_path:
+    os.makedirs(os.path.dirname(os.path.abspath(op_table_path)), exist_ok=True)
+    with open(op_table_path, "w") as f:
+      json.dump({"workload": workload, "batch": pb, "ops": table, "whole_step": whole}, f, indent=1)
+  return roof, whole
+
+
+def build_model(workload, args, batch=None):
   from pclsegmentation_b200.utils.args_loader import model_map
-
-  rank, local_rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), \
-      int(os.environ.get("WORLD_SIZE", "1"))
-  if not torch.cuda.is_available():
-    raise SystemExit("bench.py: no CUDA device - this implementation has no CPU fallback (use --impl reference "
-                     "for the CPU baseline)")
-  torch.cuda.set_device(local_rank)
-  dev = torch.device("cuda", local_rank)
-  if world > 1:
-    dist.init_process_group("nccl", device_id=dev)
-
-  model_name, mc, B = make_config(args.workload)
-  if args.batch:
-    B = args.batch
-  H, W, NC = mc.ZENITH_LEVEL, mc.AZIMUTH_LEVEL, mc.NUM_CLASS
+  model_name, mc, B = make_config(workload)
+  if batch:
+    B = batch
   model = model_map[model_name](mc)      # Keras-default init (glorot, seed 0) ...
   model.randomize_batch_norm(1)          # ... + randomised BN statistics so the folding is exercised
   for k, v in (("conv_impl", args.conv_impl), ("use_graph", args.use_graph), ("micro_batch", args.micro_batch)):
@@ -223,12 +335,191 @@ def run_ours(args):
   for kv in args.opt:                      # A/B switches of the library (pcls_net_set_option), e.g. --opt tc_vstream=1
     k, v = kv.split("=")
     model.set_option(k, int(v))
+  return model_name, mc, model, B
+
+
+def resident_inputs(rk, B, H, W, nbuf):
+  """`nbuf` distinct raw batches resident in HBM (rotated, so consecutive steps never see the same input)."""
+  raw_host = [synth_raw(1234 + 97 * rk.rank + i, B, H, W) for i in range(nbuf)]
+  return raw_host, [rk.torch.from_numpy(r).to(rk.dev) for r in raw_host]
+
+
+def run_extra_workload(rk, args, workload, steps, peaks):
+  """One more BASELINE configuration measured inside the same bench process (device-resident inputs, same timing
+  rules); returns the entry of the line's `extra_workloads` array."""
+  torch = rk.torch
+  from pclsegmentation_b200 import _lib
   lib = _lib.load()
+  if workload in PROJECTION_WORKLOADS:
+    return projection_entry(rk, args, workload, steps, peaks)
+  model_name, mc, model, B = build_model(workload, args)
+  H, W, NC = mc.ZENITH_LEVEL, mc.AZIMUTH_LEVEL, mc.NUM_CLASS
+  nbuf = 2 if B * H * W * 20 > 300e6 else 4
+  raw_host, raw_dev = resident_inputs(rk, B, H, W, nbuf)
+  outs = {"predictions": torch.empty((B, H, W), dtype=torch.int32, device=rk.dev),
+          "probabilities": torch.empty((B, H, W, NC), dtype=torch.float32, device=rk.dev)}
+  step = lambda i: model.forward_device(raw_dev[i % nbuf], None, mean=mc.INPUT_MEAN, std=mc.INPUT_STD,
+                                        want_probabilities=True, out=outs)
+  total_ms, lat, clocks = timed_steps(rk, step, steps, 3)
+  entry = {"workload": workload, "metric": "range-image frames/sec", "value": rk.world * B * steps / (total_ms / 1e3),
+           "unit": "frames/s", "n_gpus": rk.world, "steps": steps, "warmup": 3, "ms_per_step": total_ms / steps,
+           "per_gpu_batch": B, "H": H, "W": W, "dtype": "f16 storage / f32 accumulate", "clocks": clocks,
+           "p50_latency_ms": statistics.median(lat)}
+  if rk.rank == 0:
+    roof, whole = op_roofline(lib, model, mc, raw_dev[0], B, outs, peaks, total_ms / steps, B, workload=workload,
+                              op_table_path=(os.path.join(os.path.dirname(os.path.abspath(args.op_table)),
+                                                          "optable_%s.json" % workload) if args.op_table else None))
+    entry.update(roofline=roof, whole_step=whole)
+  model._release()
+  del raw_dev, outs
+  torch.cuda.empty_cache()
+  return entry
+
+
+EVAL_CLASS_HIST = [0.35, 0.08, 0.20, 0.02, 0.20, 0.01, 0.01, 0.10, 0.02, 0.01]   # synthetic: Road ... Bus (None = invalid px)
+
+
+def synth_eval_chunk(torch, dev, chunk_id, n, H, W):
+  """BASELINE config 5 synthetic val frames [n,H,W,6] f32 (x,y,z,intensity,depth,label), generated ON the device from a
+  seed that depends only on the global chunk index, so every rank (and rank 0's single-GPU recomputation) sees
+  identical frames: valid ~ Bernoulli(0.60), depth ~ U(2,80), direction from the pixel centre (fov 10 / -30),
+  labels ~ Categorical(EVAL_CLASS_HIST); invalid pixels all-zero."""
+  g = torch.Generator(device=dev)
+  g.manual_seed(90000 + chunk_id)
+  valid = torch.rand((n, H, W), generator=g, device=dev) < 0.60
+  depth = 2.0 + 78.0 * torch.rand((n, H, W), generator=g, device=dev)
+  inten = 0.99 * torch.rand((n, H, W), generator=g, device=dev)
+  hist = torch.tensor(EVAL_CLASS_HIST, device=dev)
+  label = torch.multinomial(hist, n * H * W, replacement=True, generator=g).reshape(n, H, W).to(torch.float32)
+  pitch = torch.deg2rad(10.0 - 40.0 * (torch.arange(H, device=dev) + 0.5) / H).reshape(1, H, 1)
+  yaw = (np.pi - 2 * np.pi * (torch.arange(W, device=dev) + 0.5) / W).reshape(1, 1, W)
+  x = depth * torch.cos(pitch) * torch.cos(yaw)
+  y = depth * torch.cos(pitch) * torch.sin(yaw)
+  z = depth * torch.sin(pitch) * torch.ones_like(yaw)
+  img = torch.stack([x, y, z, inten, depth, label], -1) * valid[..., None]
+  return img.to(torch.float32).contiguous()
+
+
+def run_eval_leg(rk, args, frames_per_rank=1024, chunk=32):
+  """BASELINE config 5 (pcl_segmentation/eval.py:41-58 sharded): SqueezeSegV2, nuScenes config (32x1024, NC 11), a
+  synthetic val split of `frames_per_rank` x world frames sharded contiguously over the ranks; every rank runs
+  forward -> head -> confusion update per batch on its shard, then ONE ncclAllReduce(int64) of the [NC,NC] matrix
+  (pcls_confusion_allreduce).  Rank 0 then recomputes the matrix alone over ALL frames and with np.bincount on the
+  host, and reports whether the three are identical."""
+  torch = rk.torch
+  from pclsegmentation_b200 import _lib
+  from pclsegmentation_b200.pipeline import Evaluator
+  from pclsegmentation_b200.sharding import Communicator, shard_range
+  from pclsegmentation_b200.utils.args_loader import config_map, model_map
+  lib = _lib.load()
+  mc = config_map["squeezesegv2nuscenes"]()
+  H, W, NC = mc.ZENITH_LEVEL, mc.AZIMUTH_LEVEL, mc.NUM_CLASS
+  model = model_map["squeezesegv2"](mc)
+  model.randomize_batch_norm(1)
+  comm = Communicator() if rk.world > 1 else None
+  n_total = frames_per_rank * rk.world
+  lo, hi = shard_range(n_total // chunk, rk.rank, rk.world)          # shards of whole chunks
+  data = [synth_eval_chunk(torch, rk.dev, c, chunk, H, W) for c in range(lo, hi)]   # resident in HBM
+  ev = Evaluator(model, comm)
+  ev.update(data[0])                                                    # warm-up (graph capture, NCCL communicator)
+  if comm is not None:
+    ev.miou_tracker.allreduce(comm)
+  ev.miou_tracker.reset_states()
+  rk.barrier()
+  e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+  e0.record()
+  for d in data:
+    ev.update(d)
+  e1.record()
+  if comm is not None:
+    ev.miou_tracker.allreduce(comm)
+  e2.record()
+  rk.barrier()
+  total_ms = rk.max_over_ranks(e0.elapsed_time(e2))
+  cm = ev.miou_tracker.total_cm.clone()
+  # the collective alone (all ranks arrive together): mean of 20 all-reduces of a scratch matrix
+  ar_us = None
+  if comm is not None:
+    scratch = torch.ones((NC, NC), dtype=torch.int64, device=rk.dev)
+    rk.barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(20):
+      comm.allreduce_confusion(scratch)
+    a1.record()
+    torch.cuda.synchronize()
+    ar_us = rk.max_over_ranks(a0.elapsed_time(a1) / 20 * 1e3)
+    assert int(scratch[0, 0].item()) == rk.world ** 20
+  same_everywhere = True
+  if rk.world > 1:
+    cm0 = cm.clone()
+    rk.dist.broadcast(cm0, src=0)
+    same = torch.tensor([1 if torch.equal(cm, cm0) else 0], device=rk.dev)
+    rk.dist.all_reduce(same, op=rk.dist.ReduceOp.MIN)
+    same_everywhere = bool(same.item())
+  out = None
+  if rk.rank == 0:
+    solo = Evaluator(model, None)
+    cm_np = np.zeros((NC, NC), np.int64)
+    for c in range(n_total // chunk):
+      d = data[c - lo] if lo <= c < hi else synth_eval_chunk(torch, rk.dev, c, chunk, H, W)
+      pred, label = solo.update(d, return_label=True)
+      idx = label.cpu().numpy().astype(np.int64).ravel() * NC + pred.cpu().numpy().astype(np.int64).ravel()
+      cm_np += np.bincount(idx, minlength=NC * NC).reshape(NC, NC)
+    cm_solo = solo.miou_tracker.total_cm
+    from pclsegmentation_b200.utils.util import confusion_matrix_to_iou_recall_precision
+    iou, _, _ = confusion_matrix_to_iou_recall_precision(cm)
+    out = {"workload": "squeezesegv2_nuscenes_32x1024 eval: forward + head + confusion update per batch of %d, one "
+                       "ncclAllReduce(int64 [%d,%d])" % (chunk, NC, NC),
+           "frames": n_total, "frames_per_rank": frames_per_rank, "frames_per_s": n_total / (total_ms / 1e3),
+           "ms_total": total_ms, "nranks": rk.world, "allreduce_us": ar_us,
+           "collective": "ncclAllReduce(int64, sum) via pcls_confusion_allreduce" if comm is not None else None,
+           "cm_pixels": int(cm.sum().item()), "cm_expected_pixels": n_total * H * W,
+           "cm_equal_single_gpu": bool(torch.equal(cm, cm_solo)), "cm_equal_numpy": bool(np.array_equal(cm.cpu().numpy(), cm_np)),
+           "cm_identical_on_all_ranks": same_everywhere, "miou": float(ev.miou_tracker.result()),
+           "iou_per_class": [float(v) for v in np.asarray(iou)]}
+  if comm is not None:
+    comm.close()
+  model._release()
+  del data
+  torch.cuda.empty_cache()
+  return out
+
+
+def h2d_ceiling(rk, nbytes, reps=10):
+  """What the host can feed: every rank copies `nbytes` from pinned memory to its GPU `reps` times, all ranks at once
+  (plain cudaMemcpyAsync on one stream) -> GB/s per rank (slowest rank) and aggregate.  The e2e number cannot exceed
+  aggregate / bytes-per-frame whatever the kernels do."""
+  torch = rk.torch
+  src = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+  dst = torch.empty(nbytes, dtype=torch.uint8, device=rk.dev)
+  dst.copy_(src, non_blocking=True)
+  rk.barrier()
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
+  for _ in range(reps):
+    dst.copy_(src, non_blocking=True)
+  b.record()
+  rk.barrier()
+  ms = rk.max_over_ranks(a.elapsed_time(b))
+  per_rank = nbytes * reps / (ms / 1e3) / 1e9
+  return {"GBps_per_rank": per_rank, "GBps_aggregate": per_rank * rk.world, "bytes_per_copy": nbytes, "reps": reps,
+          "how": "pinned -> device cudaMemcpyAsync, all ranks concurrently, slowest rank"}
+
+
+def run_ours(args):
+  rk = Ranks()
+  torch, dev, rank, world = rk.torch, rk.dev, rk.rank, rk.world
+  from pclsegmentation_b200 import _lib
+  lib = _lib.load()
+  peaks = measured_peaks()
+
+  model_name, mc, model, B = build_model(args.workload, args, args.batch)
+  H, W, NC = mc.ZENITH_LEVEL, mc.AZIMUTH_LEVEL, mc.NUM_CLASS
 
   # ---- inputs: NBUF distinct raw batches resident in HBM (rotated, so consecutive steps never see the same input) ----
   NBUF = 4
-  raw_host = [synth_raw(1234 + 97 * rank + i, B, H, W) for i in range(NBUF)]
-  raw_dev = [torch.from_numpy(r).to(dev) for r in raw_host]
+  raw_host, raw_dev = resident_inputs(rk, B, H, W, NBUF)
   outs = [{"predictions": torch.empty((B, H, W), dtype=torch.int32, device=dev),
            "probabilities": torch.empty((B, H, W, NC), dtype=torch.float32, device=dev)} for _ in range(2)]
 
@@ -236,34 +527,8 @@ def run_ours(args):
     return model.forward_device(raw_dev[i % NBUF], None, mean=mc.INPUT_MEAN, std=mc.INPUT_STD,
                                 want_probabilities=True, out=outs[i % 2])
 
-  def barrier():
-    if world > 1:
-      dist.barrier()
-    torch.cuda.synchronize()
-
-  for i in range(max(args.warmup, 3)):
-    step(i)
-  barrier()
-
   # ---- timed region: K steps, CUDA events on the launching stream, max over ranks ----
-  sampler = ClockSampler(local_rank)
-  if rank == 0:
-    sampler.start()
-    time.sleep(0.3)
-  ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-  barrier()
-  ev[0].record()
-  for i in range(args.steps):
-    step(i)
-    ev[i + 1].record()
-  barrier()
-  total_ms = ev[0].elapsed_time(ev[-1])
-  lat = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-  clocks = sampler.stop() if rank == 0 else None
-  t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-  if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  total_ms = float(t.item())
+  total_ms, lat, clocks = timed_steps(rk, step, args.steps, args.warmup)
   value = world * B * args.steps / (total_ms / 1e3)
 
   # ---- e2e: the reference-facing call with HOST buffers (pinned), H2D + forward + D2H of the predictions ----
@@ -277,7 +542,7 @@ def run_ours(args):
     lid = torch.empty((B, H, W, 6), dtype=torch.float32, device=dev)
     msk = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
     _lib.check(lib.pcls_input_stage(r.data_ptr(), 5, B * H * W, mean_c, std_c, none, lid.data_ptr(), msk.data_ptr(),
-                                    None, torch.cuda.current_stream().cuda_stream), "pcls_input_stage")
+                                    None, None, 0, None, torch.cuda.current_stream().cuda_stream), "pcls_input_stage")
     host_inputs.append((lid.cpu().pin_memory(), msk.cpu().bool().pin_memory()))
     del lid, msk
   e2e_steps = max(3, min(args.steps, 20))
@@ -298,21 +563,39 @@ def run_ours(args):
     pending.numpy()
 
   e2e_run(2)
-  barrier()
+  rk.barrier()
   t0 = time.perf_counter()
   e2e_run(e2e_steps)
-  barrier()
-  e2e_s = time.perf_counter() - t0
-  t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-  if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  e2e = {"value": world * B * e2e_steps / float(t.item()), "unit": "frames/s",
-         "h2d_bytes_per_step": B * H * W * (6 * 4 + 1), "d2h_bytes_per_step": B * H * W * 4,
-         "call": "model([lidar, mask]) -> predictions.numpy(), pinned host inputs, double-buffered, %d steps" % e2e_steps}
+  rk.barrier()
+  e2e_s = rk.max_over_ranks(time.perf_counter() - t0)
+  h2d_bytes, d2h_bytes = B * H * W * (6 * 4 + 1), B * H * W * 4
+  ceiling = h2d_ceiling(rk, h2d_bytes)
+  e2e_value = world * B * e2e_steps / e2e_s
+  e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+         "call": "model([lidar, mask]) -> predictions.numpy(), pinned host inputs, double-buffered, %d steps" % e2e_steps,
+         "h2d_GBps_aggregate_achieved": e2e_value * (h2d_bytes / B) / 1e9,
+         "host_h2d_ceiling": ceiling,
+         "frac_of_host_ceiling": e2e_value * (h2d_bytes / B) / 1e9 / ceiling["GBps_aggregate"]}
+  del host_inputs
+
+  # ---- the other BASELINE configurations, same process, same timing rules (all ranks take part) ----
+  extras = []
+  if not args.no_extras and args.workload == DEFAULT_WORKLOAD:
+    main_bufs = (raw_dev, outs)
+    for w, st in EXTRA_WORKLOADS:
+      try:
+        extras.append(run_extra_workload(rk, args, w, st, peaks))
+      except Exception as e:  # an extra workload must never take the headline line down
+        extras.append({"workload": w, "error": "%s: %s" % (type(e).__name__, e)})
+  eval_leg = None
+  if not args.no_eval and args.workload == DEFAULT_WORKLOAD:
+    try:
+      eval_leg = run_eval_leg(rk, args, frames_per_rank=args.eval_frames)
+    except Exception as e:
+      eval_leg = {"error": "%s: %s" % (type(e).__name__, e)}
 
   if rank != 0:
-    if world > 1:
-      dist.destroy_process_group()
+    rk.close()
     return
 
   # ---- rank 0 only: batch-1 latency, per-op roofline table, CPU baseline ----
@@ -328,65 +611,9 @@ def run_ours(args):
       lat1.append(a.elapsed_time(b))
 
   net = model._net
-  n_ops = lib.pcls_net_num_ops(net)
   pb = B if not args.micro_batch else min(B, args.micro_batch)   # profile at the benchmarked batch
-  ms = (ctypes.c_float * n_ops)()
-  acc = np.zeros(n_ops)
-  mean_p = (ctypes.c_double * 5)(*mc.INPUT_MEAN.reshape(-1))
-  std_p = (ctypes.c_double * 5)(*mc.INPUT_STD.reshape(-1))
-  reps = 5
-  sub = raw_dev[1][:pb].contiguous()
-  for r in range(reps + 1):
-    _lib.check(lib.pcls_net_profile_ops(net, sub.data_ptr(), 5, None, mean_p, std_p, pb, None,
-                                        outs[0]["probabilities"].data_ptr(), outs[0]["predictions"].data_ptr(), ms,
-                                        torch.cuda.current_stream().cuda_stream), "pcls_net_profile_ops")
-    if r:
-      acc += np.array(list(ms))
-  acc /= reps
-  peaks = measured_peaks()
-  table = []
-  for i in range(n_ops):
-    name = ctypes.create_string_buffer(64)
-    fam, fl, by = ctypes.c_int(), ctypes.c_int64(), ctypes.c_int64()
-    lib.pcls_net_op_info(net, i, name, ctypes.byref(fam), ctypes.byref(fl), ctypes.byref(by))
-    t_s = acc[i] / 1e3
-    gbs = by.value * pb / t_s / 1e9 if t_s > 0 else 0.0
-    tfs = fl.value * pb / t_s / 1e12 if t_s > 0 else 0.0
-    ai = fl.value / max(by.value, 1)
-    bound = "tensor" if (fam.value == 1 and ai > peaks["tflops_sustained"] * 1e3 / peaks["hbm_gbs"]) else "hbm"
-    table.append({"op": name.value.decode(), "ms": float(acc[i]), "share": 0.0, "GB/s": gbs, "TFLOP/s": tfs,
-                  "bound": bound, "family": "tcgen05" if fam.value else "cuda-core"})
-  tot = sum(r["ms"] for r in table)
-  for r in table:
-    r["share"] = r["ms"] / tot if tot else 0.0
-  top = max(table, key=lambda r: r["ms"])
-  if top["bound"] == "tensor":
-    roof = {"bound": "tensor", "achieved": top["TFLOP/s"], "peak": peaks["tflops_sustained"], "unit": "TFLOP/s"}
-  else:
-    roof = {"bound": "hbm", "achieved": top["GB/s"], "peak": peaks["hbm_gbs"], "unit": "GB/s"}
-  traffic = None
-  tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
-  if os.path.exists(tpath):  # DRAM bytes per launch of this kernel from the committed ncu --set full capture (same batch)
-    t = json.load(open(tpath)).get(top["op"])
-    if t and t.get("batch") == pb:
-      traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
-  roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, kernel=top["op"], share_of_step=top["share"],
-              peak_source=peaks["source"], batch_profiled=pb,
-              algorithmic_bytes_per_launch=roof["achieved"] * 1e9 * top["ms"] / 1e3 if roof["unit"] == "GB/s" else None)
-  # whole-step view: algorithmic bytes and flops of all ops over the measured step time
-  tot_by = tot_fl = 0
-  for i in range(n_ops):
-    fl, by = ctypes.c_int64(), ctypes.c_int64()
-    lib.pcls_net_op_info(net, i, None, None, ctypes.byref(fl), ctypes.byref(by))
-    tot_by += by.value
-    tot_fl += fl.value
-  step_s = total_ms / 1e3 / args.steps
-  whole = {"algorithmic_GB_per_frame": tot_by / 1e9, "GFLOP_per_frame": tot_fl / 1e9,
-           "achieved_GB/s": tot_by * B / step_s / 1e9, "achieved_TFLOP/s": tot_fl * B / step_s / 1e12}
-  if args.op_table:
-    os.makedirs(os.path.dirname(os.path.abspath(args.op_table)), exist_ok=True)
-    with open(args.op_table, "w") as f:
-      json.dump({"workload": args.workload, "batch": pb, "ops": table, "whole_step": whole}, f, indent=1)
+  roof, whole = op_roofline(lib, model, mc, raw_dev[1][:pb].contiguous(), pb, outs[0], peaks, total_ms / args.steps, B,
+                            op_table_path=args.op_table, workload=args.workload)
 
   cpu = time_cpu_baseline(model_name, mc, model, raw_host[0]) if not args.no_cpu_baseline else None
   launches = lib.pcls_net_launches_per_forward(net)
@@ -398,7 +625,8 @@ def run_ours(args):
     "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
     "dtype": "f16 storage / f32 accumulate", "data": "synthetic",
     "config": {"workload": args.workload, "per_gpu_batch": B, "global_batch": B * world, "H": H, "W": W,
-               "input": "raw [B,H,W,5] f32 resident in HBM, input stage fused", "outputs": "predictions i32 + probabilities f32",
+               "input": "raw [B,H,W,5] f32 resident in HBM; input stage (mask / normalise) inside pcls_net_forward",
+               "outputs": "predictions i32 + probabilities f32",
                "weights": "Keras-default init seed 0 + randomised BN", "l2_policy":
                "inputs rotate over %d resident batches (%.0f MB) and each step streams > 1 GB of activations, far above "
                "the 126 MB L2" % (NBUF, NBUF * B * H * W * 20 / 1e6),
@@ -408,9 +636,64 @@ def run_ours(args):
     "clocks": clocks, "e2e": e2e, "gpu_launches": launches * passes * args.steps,
     "roofline": roof, "whole_step": whole, "cpu_baseline": cpu,
   }
+  if extras:
+    line["extra_workloads"] = extras
+  if eval_leg is not None:
+    line["eval"] = eval_leg
   print(json.dumps(line))
-  if world > 1:
-    dist.destroy_process_group()
+  rk.close()
+
+
+EXTRA_WORKLOADS = [  # (workload, timed steps): BASELINE configs 3, 4 and 5's network, measured inside the default run
+  ("darknet21_kitti_64x2048_b32", 10),
+  ("darknet53_kitti_64x2048_b64", 5),
+  ("darknet53_projection_64x2048_b64", 5),
+  ("projection_kitti_64x2048_b64", 20),
+  ("squeezesegv2_nuscenes_32x1024_b32", 20),
+]
+
+
+def projection_entry(rk, args, workload, steps, peaks):
+  """BASELINE config 4 inside the default run: 64 raw scans (~120 k points each) per rank -> range images (+ Darknet53
+  forward + head for the fused workload)."""
+  torch = rk.torch
+  from pclsegmentation_b200.laserscan import SphericalProjector
+  from pclsegmentation_b200.pipeline import ScanSegmenter
+  from tests.util import synth_scan
+  dev = rk.dev
+  B, H, W = 64, 64, 2048
+  rng = np.random.default_rng(4321 + rk.rank)
+  sizes = rng.integers(115000, 125001, B)
+  bufs = []
+  for k in range(3):  # rotate over three resident scan sets (3 x 123 MB > L2)
+    bufs.append(torch.from_numpy(np.concatenate([synth_scan(rng, int(n)) for n in sizes])).to(dev))
+  offsets = torch.as_tensor(np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)).to(dev)
+  total = int(sizes.sum())
+  fused = workload.startswith("darknet53")
+  model = None
+  if fused:
+    _, mc, model, _ = build_model("darknet53_kitti_64x2048_b64", args)
+    seg = ScanSegmenter(model, 3.0, -25.0)
+    step = lambda i: seg.segment_device(bufs[i % 3], offsets)
+  else:
+    proj = SphericalProjector(H, W, 3.0, -25.0)
+    step = lambda i: proj.project(bufs[i % 3], offsets, empty_fill=0.0)
+  total_ms, lat, clocks = timed_steps(rk, step, steps, 3)
+  ms = total_ms / steps
+  entry = {"workload": workload, "metric": "scans/sec", "value": rk.world * B / (ms / 1e3), "unit": "scans/s",
+           "n_gpus": rk.world, "steps": steps, "warmup": 3, "ms_per_step": ms, "scans_per_gpu": B, "points_per_gpu": total,
+           "H": H, "W": W, "dtype": "f32/i32 (projection)" + (" + f16 net" if fused else ""), "clocks": clocks}
+  if not fused:
+    alg = 16 * total + B * H * W * (24 + 4)   # SURVEY.md §8(d): 16 N read + H W (6*4 + 4) written
+    entry["roofline"] = {"bound": "hbm", "achieved": alg / (ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": alg / (ms / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                         "kernel": "project_scatter + project_resolve", "peak_source": peaks["source"],
+                         "algorithmic_bytes_per_launch": alg}
+  if model is not None:
+    model._release()
+  del bufs
+  torch.cuda.empty_cache()
+  return entry
 
 
 def run_projection(args):
@@ -495,6 +778,9 @@ def main():
   ap.add_argument("--opt", action="append", default=[], help="library A/B switch name=value (repeatable)")
   ap.add_argument("--op-table", default=None, help="write the per-op roofline table (JSON) here")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-extras", action="store_true", help="skip the extra_workloads array (BASELINE configs 3-5)")
+  ap.add_argument("--no-eval", action="store_true", help="skip the config-5 eval leg (sharded eval + NCCL all-reduce)")
+  ap.add_argument("--eval-frames", type=int, default=1024, help="eval leg: synthetic val frames per rank")
   ap.add_argument("--ref-frames", type=int, default=2, help="--impl reference: frames per step (bounded sample)")
   args = ap.parse_args()
   if args.workload in PROJECTION_WORKLOADS:

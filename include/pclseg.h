@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PCLS_ABI_VERSION 1
+#define PCLS_ABI_VERSION 2
 
 typedef enum pcls_status {
   PCLS_OK = 0,
@@ -105,15 +105,18 @@ int pcls_head(const float* logits, const uint8_t* mask, int64_t n_pixels, int nu
               int none_index, float* probs, int32_t* preds, pcls_stream stream);
 
 /* Replaces the input stage inference.py:47-72 == DataLoader.parse_sample (data_loader.py:153-187):
- * mask = depth > 0; (x - INPUT_MEAN) / INPUT_STD in float64; zero where ~mask; append mask; and the
- * label fix-up label[~mask] = none_index.
+ * mask = depth > 0; (x - INPUT_MEAN) / INPUT_STD in float64; zero where ~mask; append mask; the label fix-up
+ * label[~mask] = none_index; and the class-weight map weight[label == l] = CLS_LOSS_WEIGHT[l] (:181-185).
  *   sample  [n_pixels, channels] f32, channels = 5 (x,y,z,i,d) or 6 (+label)
  *   h_mean5 / h_std5  host doubles (mc.INPUT_MEAN / mc.INPUT_STD)
  *   lidar   [n_pixels,6] f32 or NULL; mask [n_pixels] u8 or NULL; label [n_pixels] i32 or NULL
- *           (label requires channels == 6). */
+ *   h_cls_loss_weight  host doubles [num_classes] (mc.CLS_LOSS_WEIGHT) or NULL; weight [n_pixels] f32 or NULL: 0 where
+ *           the label is not one of 0 .. num_classes-1 (the reference starts from np.zeros), num_classes <= 32
+ *           (label and weight require channels == 6). */
 int pcls_input_stage(const float* sample, int channels, int64_t n_pixels, const double* h_mean5,
                      const double* h_std5, int none_index, float* lidar, uint8_t* mask,
-                     int32_t* label, pcls_stream stream);
+                     int32_t* label, const double* h_cls_loss_weight, int num_classes, float* weight,
+                     pcls_stream stream);
 
 /* float64 -> float32 narrowing on the device (round to nearest even), for the float64 `[H,W,6]` range-image files
  * the reference's converters write (dataset_convert/semantic_kitti.py:173) and inference.py:47 / the data loader cast
@@ -245,6 +248,8 @@ int64_t pcls_net_workspace_bytes(const pcls_net* net);
  *   "use_graph"  1 = replay the forward as a CUDA graph (default), 0 = plain launches
  *   "micro_batch" frames per pass through the graph (0 = whole batch)
  *   "fuse_head"  1 = softmax / argmax / mask in the epilogue of the final convolution (default), 0 = separate kernel
+ *   "keep_tensors" (before finalize) 1 = no workspace reuse: every intermediate tensor of the last forward stays readable
+ *                with pcls_net_read_tensor (per-layer parity tests); default 0 = liveness-planned arena
  * planning switches of the tcgen05 path, process-wide, to be set BEFORE pcls_net_finalize (all default 1):
  *   "tc_halo" (one 130-pixel tile serves three horizontal taps), "tc_resident" (weights stay in smem), "tc_group"
  *   (pixel-group view for 16 / 32-channel inputs), "tc_tma_store" (TMA-store epilogue), "tc_res_tma" (residual blocks

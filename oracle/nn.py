@@ -269,3 +269,12 @@ def forward(arch: str, params: dict, lidar_bhw6, mask_bhw, none_index: int,
     logits = logits.permute(0, 2, 3, 1).contiguous()
     prob, pred = segmentation_head(logits, torch.as_tensor(np.asarray(mask_bhw)), none_index)
     return logits.numpy(), prob.numpy(), pred.numpy()
+
+
+def class_weight_map(label_hw, cls_loss_weight):
+    """data_loader.py:181-185: weight = zeros(label.shape); weight[label == l] = CLS_LOSS_WEIGHT[l] for l in
+    range(NUM_CLASS); returned as float32 like parse_sample (:187)."""
+    weight = np.zeros(np.asarray(label_hw).shape)
+    for l in range(len(cls_loss_weight)):
+        weight[np.asarray(label_hw) == l] = cls_loss_weight[int(l)]
+    return weight.astype("float32")

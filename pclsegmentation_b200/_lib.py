@@ -12,6 +12,7 @@ PCLS_F16, PCLS_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 KIND_CONV, KIND_DECONV_1x4_S2 = 0, 1
 NCCL_UNIQUE_ID_BYTES = 128
+ABI_VERSION = 2   # include/pclseg.h PCLS_ABI_VERSION
 
 _fp = POINTER(c_float)
 
@@ -41,7 +42,7 @@ SIGNATURES = {
   "pcls_head": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
   "pcls_cast_f64_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
   "pcls_input_stage": (c_int, [c_void_p, c_int, c_int64, POINTER(c_double), POINTER(c_double), c_int, c_void_p,
-                               c_void_p, c_void_p, c_void_p]),
+                               c_void_p, c_void_p, POINTER(c_double), c_int, c_void_p, c_void_p]),
   "pcls_confusion_update": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
   "pcls_comm_unique_id": (c_int, [c_char_p]),
   "pcls_comm_init": (c_int, [POINTER(c_void_p), c_int, c_char_p, c_int]),
@@ -86,8 +87,8 @@ def load():
     fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
     fn.restype = res
     fn.argtypes = args
-  if lib.pcls_abi_version() != 1:
-    raise PclsError("libpclseg.so ABI version %d, expected 1" % lib.pcls_abi_version())
+  if lib.pcls_abi_version() != ABI_VERSION:
+    raise PclsError("libpclseg.so ABI version %d, expected %d" % (lib.pcls_abi_version(), ABI_VERSION))
   _lib = lib
   return lib
 

@@ -7,10 +7,16 @@
 namespace pcls {
 
 struct Norm5 { double mean[5]; double inv_unused; double std[5]; };
+constexpr int IS_MAX_NC = 32;
+struct ClsWeight { float w[IS_MAX_NC]; int nc; };
 
 __global__ void __launch_bounds__(256)
 input_stage_kernel(const float* __restrict__ sample, int channels, int64_t n_pixels, Norm5 nrm, int none_index,
-                   float* __restrict__ lidar, uint8_t* __restrict__ mask, int32_t* __restrict__ label) {
+                   float* __restrict__ lidar, uint8_t* __restrict__ mask, int32_t* __restrict__ label, ClsWeight cw,
+                   float* __restrict__ weight) {
+  __shared__ float cw_s[IS_MAX_NC];
+  if (threadIdx.x < IS_MAX_NC) cw_s[threadIdx.x] = cw.w[threadIdx.x];
+  __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pixels; p += stride) {
     const float* s = sample + p * channels;
@@ -26,7 +32,14 @@ input_stage_kernel(const float* __restrict__ sample, int channels, int64_t n_pix
       o[5] = m ? 1.0f : 0.0f;
     }
     if (mask) mask[p] = m ? 1 : 0;
-    if (label) label[p] = m ? (int32_t)__ldg(s + 5) : none_index;  // label[~mask] = None (inference.py:65-68)
+    if (label || weight) {
+      const float lf = m ? __ldg(s + 5) : (float)none_index;       // label[~mask] = None (inference.py:65-68)
+      if (label) label[p] = (int32_t)lf;
+      if (weight) {   // weight = zeros; weight[label == l] = CLS_LOSS_WEIGHT[l] for l < NUM_CLASS (data_loader.py:181-185)
+        const int li = (int)lf;
+        weight[p] = (lf == (float)li && li >= 0 && li < cw.nc) ? cw_s[li] : 0.0f;
+      }
+    }
   }
 }
 
@@ -62,10 +75,14 @@ extern "C" int pcls_cast_f64_f32(const double* in, float* out, int64_t n, pcls_s
 
 extern "C" int pcls_input_stage(const float* sample, int channels, int64_t n_pixels, const double* h_mean5,
                                 const double* h_std5, int none_index, float* lidar, uint8_t* mask,
-                                int32_t* label, pcls_stream stream) {
+                                int32_t* label, const double* h_cls_loss_weight, int num_classes, float* weight,
+                                pcls_stream stream) {
   using namespace pcls;
   PCLS_REQUIRE(channels == 5 || channels == 6, "pcls_input_stage: channels must be 5 or 6, got %d", channels);
-  PCLS_REQUIRE(label == nullptr || channels == 6, "pcls_input_stage: label output needs a 6-channel sample");
+  PCLS_REQUIRE((label == nullptr && weight == nullptr) || channels == 6,
+               "pcls_input_stage: label / weight outputs need a 6-channel sample");
+  PCLS_REQUIRE(weight == nullptr || (h_cls_loss_weight != nullptr && num_classes >= 1 && num_classes <= IS_MAX_NC),
+               "pcls_input_stage: the weight output needs h_cls_loss_weight[num_classes], 1 <= num_classes <= %d", IS_MAX_NC);
   PCLS_REQUIRE(h_mean5 != nullptr && h_std5 != nullptr, "pcls_input_stage: mean/std must not be NULL");
   PCLS_REQUIRE(n_pixels >= 0, "pcls_input_stage: negative n_pixels");
   if (n_pixels == 0) return PCLS_OK;
@@ -75,7 +92,10 @@ extern "C" int pcls_input_stage(const float* sample, int channels, int64_t n_pix
   int64_t blocks = ceil_div(n_pixels, 256);
   int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
+  ClsWeight cw;
+  cw.nc = weight ? num_classes : 0;
+  for (int c = 0; c < IS_MAX_NC; ++c) cw.w[c] = (weight && c < num_classes) ? (float)h_cls_loss_weight[c] : 0.0f;
   input_stage_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(sample, channels, n_pixels, nrm, none_index,
-                                                                   lidar, mask, label);
+                                                                   lidar, mask, label, cw, weight);
   return check_launch("input_stage_kernel");
 }

@@ -314,6 +314,8 @@ int Net::finalize(int logits_tensor_, int num_classes_, int none_index_) {
     }
   }
   tensors[logits_tensor].last = n_ops;
+  if (keep_tensors)
+    for (auto& t : tensors) t.last = n_ops;
 
   // greedy first-fit arena planning (per-frame offsets; scaled by the frames per pass)
   struct Block { size_t off, size; };
@@ -739,6 +741,10 @@ extern "C" int pcls_net_set_option(pcls_net* net, const char* name, int value) {
     PCLS_REQUIRE(!n->finalized, "micro_batch must be set before pcls_net_finalize");
     PCLS_REQUIRE(value >= 0, "micro_batch must be >= 0");
     n->micro_batch = value; return PCLS_OK;
+  }
+  if (!strcmp(name, "keep_tensors")) {
+    PCLS_REQUIRE(!n->finalized, "keep_tensors must be set before pcls_net_finalize");
+    n->keep_tensors = value != 0; return PCLS_OK;
   }
   if (!strcmp(name, "tc_halo")) { tc_halo_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_tma_store")) { tc_tma_store_mode = value; return PCLS_OK; }

@@ -67,6 +67,7 @@ struct Net {
   bool fuse_head = true;   // run softmax/argmax/mask in the epilogue of the final convolution (tcgen05 path)
   struct HeadArgs { int head = 0, none_index = 0; const uint8_t* mask = nullptr; float* probs = nullptr; int32_t* preds = nullptr; float* logits = nullptr; } head_args;
   int micro_batch = 0;
+  bool keep_tensors = false;  // test aid: no arena reuse, every intermediate stays readable after the forward
   // device state
   int frames_per_pass = 0;
   size_t frame_bytes = 0, mask_offset = 0;

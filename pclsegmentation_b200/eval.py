@@ -14,6 +14,7 @@ import os
 
 import numpy as np
 
+from .inference import load_model_weights
 from .pipeline import Evaluator, shard_files
 from .utils.args_loader import load_model_config
 
@@ -31,10 +32,7 @@ def evaluation(arg):
 
   config, model = load_model_config(arg.model, arg.config)
   config.DATA_AUGMENTATION = False
-  if arg.path_to_model and os.path.exists(arg.path_to_model):
-    model.load_weights(arg.path_to_model)
-  elif rank == 0:
-    print("No weight file given/found: using the Keras-default initialisation")
+  load_model_weights(model, arg, verbose=rank == 0)
 
   files = shard_files(glob.glob(os.path.join(arg.data_path, arg.image_set, "*.npy")), comm)
   ev = Evaluator(model, comm)
@@ -70,6 +68,7 @@ def main(argv=None):
                       help='Which configuration `squeezesegv2`, `squeezesegv2kitti`, `squeezesegv2nuscenes`, '
                            '`darknet53`, `darknet21`, `darknet53kitti`')
   parser.add_argument('-b', '--batch', type=int, default=8, help='frames per forward call (the reference uses 1)')
+  parser.add_argument('--random_init', action='store_true', help='run without --path_to_model on Keras-default weights')
   return evaluation(parser.parse_args(argv))
 
 

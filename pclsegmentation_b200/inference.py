@@ -5,7 +5,7 @@ matched by --input_path it writes ``pred_<name>.npy`` (int32 [H,W] class ids) pl
 
 Differences, all documented in DESIGN.md: --path_to_model takes the reference's SavedModel directory / checkpoint prefix
 (its TensorBundle is read without TensorFlow, utils/tensor_bundle.py) or an ``.npz`` container keyed by Keras attribute
-paths (absent -> Keras-default initialisation, as a freshly constructed reference model); --config selects the ``mc`` factory
+paths (a missing path is an error; --random_init runs an untrained, Keras-default-initialised network on purpose); --config selects the ``mc`` factory
 (the reference hard-codes SqueezeSegV2Config, inference.py:37 - that is the default here); the normalise / mask stage
 (inference.py:50-62) runs fused on the GPU; --batch frames go through the network per call.
 """
@@ -20,13 +20,27 @@ from .utils.args_loader import load_model_config
 from .utils.util import normalize
 
 
+def load_model_weights(model, arg, verbose=True):
+  """--path_to_model given: ALWAYS load it (a SavedModel directory, a checkpoint PREFIX - which never exists as a file,
+  only `<prefix>.index` / `.data-*` do - or an .npz); a wrong path raises FileNotFoundError like the reference's
+  `tf.keras.models.load_model` (inference.py:39).  Random (Keras-default) weights only on the explicit --random_init."""
+  if arg.path_to_model:
+    if not str(arg.path_to_model).endswith(".npz") or os.path.exists(arg.path_to_model):
+      model.load_weights(arg.path_to_model)    # tensor_bundle.resolve_prefix raises FileNotFoundError for a bad path
+    else:
+      raise FileNotFoundError("--path_to_model %r does not exist" % arg.path_to_model)
+  elif getattr(arg, "random_init", False):
+    if verbose:
+      print("--random_init: using the Keras-default initialisation (untrained network)")
+  else:
+    raise SystemExit("--path_to_model is required (SavedModel dir / checkpoint prefix / .npz); pass --random_init to run "
+                     "an untrained network on purpose")
+
+
 def inference(arg):
   import torch
   config, model = load_model_config(arg.model or "squeezesegv2", arg.config)
-  if arg.path_to_model and os.path.exists(arg.path_to_model):
-    model.load_weights(arg.path_to_model)
-  else:
-    print("No weight file given/found: using the Keras-default initialisation")
+  load_model_weights(model, arg)
 
   if not os.path.exists(arg.output_dir):
     os.makedirs(arg.output_dir)
@@ -68,6 +82,7 @@ def main(argv=None):
   parser.add_argument('-n', '--config', type=str, default='squeezesegv2', help='Which `mc` configuration to use')
   parser.add_argument('-b', '--batch', type=int, default=8, help='frames per forward call')
   parser.add_argument('--no_plots', action='store_true', help='only write pred_*.npy')
+  parser.add_argument('--random_init', action='store_true', help='run without --path_to_model on Keras-default weights')
   inference(parser.parse_args(argv))
 
 

@@ -148,12 +148,13 @@ class Darknet(PCLSegmentationNetwork):
     skips, os = {}, 1  # skip connections keyed by the output stride at which they were taken
 
     x, skips, os = self.run_enc_block(lidar_input, self.conv1, skips, os)
-    x = self.leaky_relu1(self.bn1(x))
+    x = self._tap("conv1", self.leaky_relu1(self.bn1(x)))
     for i in (1, 2, 3, 4, 5):  # encoder, dropout (identity at inference) after every layer
       x, skips, os = self.run_enc_block(x, getattr(self, "enc%d" % i), skips, os)
-      x = self.dropout(x, training)
+      x = self._tap("enc%d" % i, self.dropout(x, training))
     for i in (5, 4, 3, 2, 1):  # decoder
       x, skips, os = self.run_dec_block(x, getattr(self, "dec%d" % i), skips, os)
+      self._tap("dec%d" % i, x)
 
     logits = self.head(self.dropout(x, training))
     return self.segmentation_head(logits, lidar_mask)

@@ -46,6 +46,7 @@ class PCLSegmentationNetwork:
     self.net_options = {}
     self._graph = Graph(self.ZENITH_LEVEL, self.AZIMUTH_LEVEL)
     self._logits_sym = None
+    self._taps = {}          # name -> symbolic tensor, recorded by call() (per-layer parity tests, see read_tap)
     self._net = None
     self._net_batch = 0
     self._pinned = {}
@@ -56,6 +57,23 @@ class PCLSegmentationNetwork:
 
   def _trace(self):
     self._logits_sym = self.call([self._graph.input, None])
+
+  def _tap(self, name, x):
+    """Names an intermediate tensor of call() (same names as the `taps` of oracle/nn.py)."""
+    self._taps[name] = x
+    return x
+
+  def read_tap(self, name, batch):
+    """float32 CUDA copy [batch,H,width,channels] of a tapped intermediate of the LAST forward.  Intermediates share a
+    liveness-planned arena, so this is only meaningful with set_option("keep_tensors", 1)."""
+    if not self.net_options.get("keep_tensors"):
+      raise _lib.PclsError("read_tap needs set_option('keep_tensors', 1) before the forward")
+    sym = self._taps[name]
+    out = torch.empty((batch, self.ZENITH_LEVEL, sym.width, sym.channels), dtype=torch.float32,
+                      device=torch.device("cuda", torch.cuda.current_device()))
+    _lib.check(_lib.load().pcls_net_read_tensor(self._net, sym.tid, batch, ptr(out), stream_handle()),
+               "pcls_net_read_tensor")
+    return out
 
   def segmentation_head(self, logits, lidar_mask):
     """Symbolic marker: the head (softmax, argmax, mask fill with CLASSES.index("None")) is executed by

@@ -102,35 +102,35 @@ class SqueezeSegV2(PCLSegmentationNetwork):
     lidar_input, lidar_mask = inputs[0], inputs[1]
 
     # Encoder
-    x = L.relu(self.bn1(self.conv1(lidar_input)))
-    cam1_output = self.cam1(x)
-    conv1_skip = self.bn1_skip(self.conv1_skip(lidar_input))
+    x = self._tap("conv1", L.relu(self.bn1(self.conv1(lidar_input))))
+    cam1_output = self._tap("cam1", self.cam1(x))
+    conv1_skip = self._tap("conv1_skip", self.bn1_skip(self.conv1_skip(lidar_input)))
 
     x = L.max_pool2d(cam1_output, ksize=3, strides=[1, 2], padding='SAME')
-    x = self.fire2(x)
+    x = self._tap("fire2", self.fire2(x))
     x = self.cam2(x)
     x = self.fire3(x)
-    cam3_output = self.cam3(x)
+    cam3_output = self._tap("cam3", self.cam3(x))
 
     x = L.max_pool2d(cam3_output, ksize=3, strides=[1, 2], padding='SAME')
     x = self.fire4(x)
-    fire5_output = self.fire5(x)
+    fire5_output = self._tap("fire5", self.fire5(x))
 
     x = L.max_pool2d(fire5_output, ksize=3, strides=[1, 2], padding='SAME')
     x = self.fire6(x)
     x = self.fire7(x)
     x = self.fire8(x)
-    fire9_output = self.fire9(x)
+    fire9_output = self._tap("fire9", self.fire9(x))
 
     # Decoder (each tf.add skip is folded into the FireDeconv's expand epilogues)
     x = self.fire10(fire9_output)
-    x = L.add(x, fire5_output)
+    x = self._tap("fire10", L.add(x, fire5_output))
     x = self.fire11(x)
     x = L.add(x, cam3_output)
     x = self.fire12(x)
     x = L.add(x, cam1_output)
     x = self.fire13(x)
-    x = L.add(x, conv1_skip)
+    x = self._tap("fire13", L.add(x, conv1_skip))
 
     x = self.dropout(x, training)
     logits = self.conv14(x)

@@ -60,7 +60,7 @@ class Evaluator:
     self._mean = (ctypes.c_double * 5)(*np.asarray(self.mc.INPUT_MEAN).reshape(-1))
     self._std = (ctypes.c_double * 5)(*np.asarray(self.mc.INPUT_STD).reshape(-1))
 
-  def update(self, samples):
+  def update(self, samples, return_label=False):
     """samples: [B,H,W,6] float64 / float32 (x,y,z,i,d,label) numpy or CUDA tensor - the .npy frames of the dataset.
     Runs the fused input stage + forward + head, fixes the labels up (label[~mask] = None, data_loader.py:176) and
     accumulates the confusion matrix; nothing returns to the host."""
@@ -71,9 +71,9 @@ class Evaluator:
     res = self.model.forward_device(x, None, mean=self.mc.INPUT_MEAN, std=self.mc.INPUT_STD, want_probabilities=False)
     label = torch.empty((B, H, W), dtype=torch.int32, device=x.device)
     _lib.check(_lib.load().pcls_input_stage(ptr(x), 6, B * H * W, self._mean, self._std, self._none, None, None,
-                                            ptr(label), stream_handle()), "pcls_input_stage")
+                                            ptr(label), None, 0, None, stream_handle()), "pcls_input_stage")
     self.miou_tracker.update_state(label, res["predictions"])
-    return res["predictions"]
+    return (res["predictions"], label) if return_label else res["predictions"]
 
   def finish(self):
     """All-reduce (if sharded) and compute the report of eval.py:50-58."""

@@ -71,7 +71,39 @@ def run_case(name, seed, n, H, W, fov_up, fov_down, dup=0, out_of_fov=0):
   print(name, "n", n, "valid px", int(mask.sum()), "final dtype", final.dtype)
 
 
+def run_ring_case(name, seed, n, H, W):
+  """The nuScenes variant: `laserscan_nuscenes.LaserScan` imported UNMODIFIED (its top-level `from nuscenes...` imports,
+  :3-4, are satisfied by empty stand-in modules: the devkit classes are only used by open_scan, not by set_points /
+  do_range_projection_ring :191-223 / do_range_projection :226-286)."""
+  import types
+  for mod, attrs in (("nuscenes", {}), ("nuscenes.utils", {}),
+                     ("nuscenes.utils.data_classes", {"PointCloud": type("PointCloud", (), {})}),
+                     ("nuscenes.utils.data_io", {"load_bin_file": lambda path: None})):
+    m = types.ModuleType(mod)
+    m.__dict__.update(attrs)
+    sys.modules.setdefault(mod, m)
+  import laserscan_nuscenes as refn
+  rng = np.random.default_rng(seed)
+  pts, rem, _ = synth_scan(rng, n, 12.0, -30.0, H)
+  ring = rng.integers(0, H, n).astype(np.int32)       # several points per (ring, column): the last one written wins
+  src, dst = rng.integers(0, n, 200), rng.integers(0, n, 200)
+  pts[dst] = pts[src]
+  scan = refn.LaserScan(project=True, H=H, W=W, fov_up=12.0, fov_down=-30.0, use_ring_projection=True)
+  scan.set_points(pts, rem, ring)
+  out = dict(points=pts, remissions=rem, ring=ring, H=H, W=W, proj_range=scan.proj_range.copy(),
+             proj_xyz=scan.proj_xyz.copy(), proj_remission=scan.proj_remission.copy(), proj_idx=scan.proj_idx.copy(),
+             proj_x=scan.proj_x.copy(), proj_mask=scan.proj_mask.copy())
+  # the same class with use_ring_projection=False runs its copy of do_range_projection (:226-286)
+  scan2 = refn.LaserScan(project=True, H=H, W=W, fov_up=12.0, fov_down=-30.0, use_ring_projection=False)
+  scan2.set_points(pts, rem)
+  out.update(fov_proj_range=scan2.proj_range.copy(), fov_proj_idx=scan2.proj_idx.copy(), fov_proj_x=scan2.proj_x.copy(),
+             fov_proj_y=scan2.proj_y.copy(), fov_unproj_range=scan2.unproj_range.copy())
+  np.savez_compressed(os.path.join(HERE, "projection_%s.npz" % name), **out)
+  print(name, "n", n, "occupied px", int((scan.proj_idx >= 0).sum()))
+
+
 if __name__ == "__main__":
+  run_ring_case("nusc_ring_32x1024", 14, 30000, 32, 1024)
   run_case("kitti_64x512", 11, 20000, 64, 512, 3.0, -25.0, dup=300, out_of_fov=50)
   run_case("kitti_64x2048", 12, 40000, 64, 2048, 3.0, -25.0, dup=100)
   run_case("nusc_32x1024", 13, 12000, 32, 1024, 12.0, -30.0, dup=100, out_of_fov=20)

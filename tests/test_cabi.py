@@ -25,7 +25,7 @@ def test_every_declared_symbol_is_exported_and_bound():
   for n in names:
     assert hasattr(lib, n), "libpclseg.so does not export %s" % n
   assert sorted(_lib.SIGNATURES) == names, "ctypes SIGNATURES and include/pclseg.h disagree"
-  assert lib.pcls_abi_version() == 1
+  assert lib.pcls_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_struct_layout_matches_header():
@@ -41,7 +41,7 @@ def test_argument_validation_without_gpu():
   assert b"num_classes" in lib.pcls_last_error()
   assert lib.pcls_confusion_update(None, None, 0, 99, None, None, None) == -1
   assert lib.pcls_project_scatter(None, None, None, 1, 0, 0, 8, 3.0, -25.0, None, None, None, None, None) == -1
-  assert lib.pcls_input_stage(None, 4, 0, None, None, 0, None, None, None, None) == -1
+  assert lib.pcls_input_stage(None, 4, 0, None, None, 0, None, None, None, None, 0, None, None) == -1
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

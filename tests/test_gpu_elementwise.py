@@ -60,14 +60,29 @@ def test_input_stage_matches_oracle():
   label = torch.empty(n, dtype=torch.int32, device="cuda")
   mean = (ctypes.c_double * 5)(*mc.INPUT_MEAN.reshape(-1))
   std = (ctypes.c_double * 5)(*mc.INPUT_STD.reshape(-1))
+  weight = torch.empty(n, dtype=torch.float32, device="cuda")
+  cls_w = np.linspace(0.25, 3.0, mc.NUM_CLASS)          # distinct per class (the shipped configs use ones / a 0 for None)
+  cw = (ctypes.c_double * mc.NUM_CLASS)(*cls_w)
+  raw[0, :4, :8, 5] = 25.0                              # labels outside [0, NUM_CLASS): weight stays 0 (np.zeros)
+  raw[0, :4, :8, 4] = 5.0
+  d = torch.from_numpy(raw).cuda()
   _lib.check(lib.pcls_input_stage(d.data_ptr(), 6, n, mean, std, 0, lidar.data_ptr(), mask.data_ptr(),
-                                  label.data_ptr(), _s()))
+                                  label.data_ptr(), cw, mc.NUM_CLASS, weight.data_ptr(), _s()))
   for b in range(2):
     l_ref, m_ref, lab_ref = O.input_stage(raw[b], mc.INPUT_MEAN, mc.INPUT_STD, 0)
     sl = slice(b * 64 * 512, (b + 1) * 64 * 512)
     assert np.array_equal(lidar[sl].cpu().numpy().reshape(64, 512, 6), l_ref)     # bit-exact (float64 normalise)
     assert np.array_equal(mask[sl].cpu().numpy().reshape(64, 512).astype(bool), m_ref)
     assert np.array_equal(label[sl].cpu().numpy().reshape(64, 512), lab_ref)
+    w_ref = O.class_weight_map(lab_ref, cls_w)                                     # data_loader.py:181-185
+    assert np.array_equal(weight[sl].cpu().numpy().reshape(64, 512), w_ref)
+  assert (weight.cpu().numpy().reshape(2, 64, 512)[0, :4, :8] == 0).all()
+  # the DataLoader.parse_sample facade returns the same four arrays
+  from pclsegmentation_b200.data_loader import parse_samples
+  mc.CLS_LOSS_WEIGHT = cls_w
+  lid, msk, lab, wgt = parse_samples(raw, mc)
+  assert np.array_equal(lid.cpu().numpy(), lidar.cpu().numpy().reshape(2, 64, 512, 6)) and msk.dtype == torch.bool
+  assert np.array_equal(lab.cpu().numpy().ravel(), label.cpu().numpy()) and np.array_equal(wgt.cpu().numpy().ravel(), weight.cpu().numpy())
 
 
 @pytest.mark.parametrize("n,nc", [(32 * 64 * 2048, 20), (3 * 32 * 240 + 3, 11), (1, 2), (0, 11)])

@@ -35,10 +35,14 @@ class TinyNet:
     # tensor under test is the last thing written into the arena
     self.logits = L.Conv2D("zz_logits", 2, 1)(self.g.input)
 
-  def run(self, out_sym, B, x6, conv_impl):
+  def run(self, out_sym, B, x6, conv_impl, keep=None):
+    """Runs the graph; returns `out_sym` as float32 NHWC.  keep = list of further symbolic tensors to read back
+    (self.kept, same order): the net is then built with keep_tensors = 1 (no arena reuse)."""
     lib = _lib.load()
     g = self.g
     opts = {"conv_impl": conv_impl, "use_graph": 0}
+    if keep:
+      opts["keep_tensors"] = 1
     for kv in os.environ.get("PCLS_TEST_OPTS", "").split(","):  # e.g. tc_base_offset=0 (A/B experiments)
       if "=" in kv:
         opts[kv.split("=")[0]] = int(kv.split("=")[1])
@@ -50,6 +54,16 @@ class TinyNet:
                                       torch.cuda.current_stream().cuda_stream), "forward")
       out = torch.empty((B, g.H, out_sym.width, out_sym.channels), dtype=torch.float32, device="cuda")
       _lib.check(lib.pcls_net_read_tensor(net, out_sym.tid, B, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+      self.kept = []
+      for sym in keep or []:
+        if sym.is_input:    # the network input as the device stores it: 6 channels (+ 2 zero pad) in 16-bit
+          k = torch.empty((B, g.H, g.W, 8), dtype=torch.float32, device="cuda")
+          _lib.check(lib.pcls_net_read_tensor(net, 0, B, k.data_ptr(), torch.cuda.current_stream().cuda_stream))
+          self.kept.append(k.cpu().numpy()[..., :6])
+          continue
+        k = torch.empty((B, g.H, sym.width, sym.channels), dtype=torch.float32, device="cuda")
+        _lib.check(lib.pcls_net_read_tensor(net, sym.tid, B, k.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        self.kept.append(k.cpu().numpy())
       torch.cuda.synchronize()
       return out.cpu().numpy()
     finally:
@@ -86,11 +100,54 @@ def _tp(g):
   return {k: torch.from_numpy(v) for k, v in g.variables.items()}
 
 
+# ---- per-layer error model -------------------------------------------------------------------------------------
+# Every conv op is checked at ITS OWN output against a float64 evaluation on the device's own 16-bit input tensor, so
+# errors do not compound and the bound is the arithmetic's, not a fraction of the largest value:
+#   folded weights are rounded to fp16            -> |d| <= 2^-11 * S,  S = sum |w'| |x| (+ |b'|)
+#   fp32 accumulation of K = taps * Cin products  -> a fraction of 2^-11 * S for K <= ~10^3 (allowed: 0.5 * 2^-11 * S)
+#   the stored output is rounded to fp16 once     -> |d| <= 2^-11 * |y|
+# A wrong / misplaced tap weight changes the output by ~S / taps, two orders of magnitude above this bound.
+U16 = 2.0 ** -11
+
+
+def _fold64(p, conv, bn, transpose=False):
+  """Folded float64 kernel (Keras layout) and bias of conv(+BN), like Net::add_conv."""
+  k = p[conv + "/kernel"].double()
+  cout = k.shape[2] if transpose else k.shape[3]
+  b = p[conv + "/bias"].double() if (conv + "/bias") in p else torch.zeros(cout, dtype=torch.float64)
+  if bn:
+    sc = p[bn + "/gamma"].double() / torch.sqrt(p[bn + "/moving_variance"].double() + O.BN_EPS)
+    k = k * (sc.view(1, 1, -1, 1) if transpose else sc.view(1, 1, 1, -1))
+    b = (b - p[bn + "/moving_mean"].double()) * sc + p[bn + "/beta"].double()
+  return k, b
+
+
+def _check_layer(x_dev, y_dev, p, conv, bn=None, strides=(1, 1), act=None, transpose=False, residuals=(), what=""):
+  """x_dev / y_dev / residuals: NHWC float32 arrays read back from the device (exact 16-bit values)."""
+  k, b = _fold64(p, conv, bn, transpose)
+  x = _nchw(x_dev).double()
+  if transpose:
+    pre = O.conv2d_transpose_1x4_s2(x, k, b)
+    S = O.conv2d_transpose_1x4_s2(x.abs(), k.abs(), b.abs())
+  else:
+    pre = O.conv2d_same(x, k, b, strides)
+    S = O.conv2d_same(x.abs(), k.abs(), b.abs(), strides)
+  y = pre if act is None else (torch.relu(pre) if act == "relu" else O.leaky(pre))
+  for r in residuals:
+    y = y + _nchw(r).double()
+  bound = U16 * (1.5 * S + y.abs()) + 1e-6
+  d = (_nchw(y_dev).double() - y).abs()
+  worst = float((d / bound).max())
+  assert tuple(y.shape) == tuple(_nchw(y_dev).shape), what
+  assert worst <= 1.0, "%s: error %.3g x the fp16 error model (max abs err %.3e)" % (what, worst, float(d.max()))
+  return worst
+
+
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("H,W,c1,c2", [(5, 48, 32, 48), (3, 27, 16, 64), (8, 256, 64, 128), (2, 130, 128, 32)])
 def test_conv_flavours_in_isolation(impl, H, W, c1, c2):
   """3x3 s1 from the 6-channel input, 1x1, 3x3 s[1,2] (asymmetric SAME for even W / symmetric for odd), transposed
-  [1,4] s2, concat-by-offset and a residual add - each checked against the oracle at its own output."""
+  [1,4] s2, concat-by-offset (merged Fire expand) - each checked at its own output against the error model."""
   rng = np.random.default_rng(H * W + c1)
   B = 2
   t = TinyNet(H, W)
@@ -99,34 +156,33 @@ def test_conv_flavours_in_isolation(impl, H, W, c1, c2):
   b = L.LeakyReLU(0.1)(L.BatchNormalization("b1")(L.Conv2D("c1", c2, 1, use_bias=False)(a)))  # 1x1
   c = L.relu(L.Conv2D("c2", c1, 3, strides=[1, 2])(b))                                        # 3x3 s2, bias only
   d = L.relu(L.Conv2DTranspose("c3", c1)(c))                                                  # deconv back to >= W
-  Wd = d.width
   e1 = L.relu(L.BatchNormalization("b4")(L.Conv2D("c4", c2, 1)(d)))
   e3 = L.relu(L.BatchNormalization("b5")(L.Conv2D("c5", c2, 3)(d)))
   cat = L.concat([e1, e3])
   _rand_vars(g, rng)
   x = _input(rng, B, H, W)
   p = _tp(g)
-  xa = F_relu(O.batch_norm(O._conv(_nchw(x), p, "c0"), p, "b0"))
-  xb = O.leaky(O.batch_norm(O._conv(xa, p, "c1"), p, "b1"))
-  xc = F_relu(O._conv(xb, p, "c2", (1, 2)))
-  xd = F_relu(O.conv2d_transpose_1x4_s2(xc, p["c3/kernel"], p["c3/bias"]))
-  xe = torch.cat([F_relu(O.batch_norm(O._conv(xd, p, "c4"), p, "b4")), F_relu(O.batch_norm(O._conv(xd, p, "c5"), p, "b5"))], 1)
-  assert Wd == xd.shape[3]
-  got = t.run(cat, B, x, impl)
-  ref = _nhwc(xe)
-  err = np.abs(got - ref).max()
-  assert got.shape == ref.shape and err < 3e-2 * max(1.0, np.abs(ref).max()), err
+  got = t.run(cat, B, x, impl, keep=[g.input, a, b, c, d])
+  xin, ya, yb, yc, yd = t.kept
+  assert np.array_equal(xin, x)                                      # the input was representable in fp16
+  _check_layer(xin, ya, p, "c0", "b0", act="relu", what="3x3 s1 from the input")
+  _check_layer(ya, yb, p, "c1", "b1", act="leaky", what="1x1")
+  _check_layer(yb, yc, p, "c2", None, strides=(1, 2), act="relu", what="3x3 s[1,2]")
+  _check_layer(yc, yd, p, "c3", None, act="relu", transpose=True, what="transposed [1,4] s[1,2]")
+  _check_layer(yd, got[..., :c2], p, "c4", "b4", act="relu", what="expand1x1 (concat offset 0)")
+  _check_layer(yd, got[..., c2:], p, "c5", "b5", act="relu", what="expand3x3 (concat offset c2)")
 
 
 def F_relu(x):
   return torch.relu(x)
 
 
-@pytest.mark.parametrize("W,cs,ce", [(512, 16, 64), (1024, 16, 32), (512, 32, 64), (256, 32, 128), (512, 16, 16)])
+@pytest.mark.parametrize("W,cs,ce", [(512, 16, 64), (1024, 16, 32), (512, 32, 64), (256, 32, 128), (512, 16, 16),
+                                     (128, 48, 192), (256, 64, 128)])
 def test_wide_narrow_channel_layers(W, cs, ce):
-  """The shapes of the benchmark's narrow-channel Fire layers (Cin = 16 / 32 at W >= 256): pixel-group view (G = 4 / 2),
-  banded MMA issue, halo tiles, resident weights, TMA-store epilogue with the 5-D group map, residual prefetch and the
-  single-pass transposed conv - each against the oracle."""
+  """The shapes of the benchmark's Fire layers (Cin = 16 / 32 at W >= 256: pixel-group view G = 4 / 2, banded MMA issue;
+  Cin = 48 / 64 at W = 128 / 256: fire6-10), halo tiles, resident weights, split-N, TMA-store epilogue with the 5-D group
+  map, residual prefetch and the single-pass transposed conv - each op against the error model at its own output."""
   rng = np.random.default_rng(W + cs + ce)
   B, H = 2, 3
   t = TinyNet(H, W)
@@ -142,18 +198,16 @@ def test_wide_narrow_channel_layers(W, cs, ce):
   _rand_vars(g, rng)
   x = _input(rng, B, H, W)
   p = _tp(g)
-  xa = F_relu(O.batch_norm(O._conv(_nchw(x), p, "c0"), p, "b0"))
-  xs = F_relu(O.batch_norm(O._conv(xa, p, "cs"), p, "bs"))
-  xq = F_relu(O.batch_norm(O._conv(xa, p, "c1"), p, "b1"))
-  xcat = torch.cat([F_relu(O.batch_norm(O._conv(xq, p, "c2"), p, "b2")), F_relu(O.batch_norm(O._conv(xq, p, "c3"), p, "b3"))], 1) + xs
-  xq2 = F_relu(O.batch_norm(O._conv(xcat, p, "c4"), p, "b4"))
-  xup = F_relu(O.conv2d_transpose_1x4_s2(xq2, p["c5/kernel"], p["c5/bias"]))
   for impl in IMPLS:
-    got = TinyNet.run(t, up, B, x, impl)
-    ref = _nhwc(xup)
-    assert got.shape == ref.shape
-    err = np.abs(got - ref).max()
-    assert err < 3e-2 * max(1.0, np.abs(ref).max()), (impl, err)
+    got = TinyNet.run(t, up, B, x, impl, keep=[g.input, a, skip, sq, cat, sq2])
+    xin, ya, ys, yq, ycat, yq2 = t.kept
+    _check_layer(xin, ya, p, "c0", "b0", act="relu", what="impl %d: 3x3 from the input" % impl)
+    _check_layer(ya, ys, p, "cs", "bs", act="relu", what="impl %d: 1x1 64 -> 2ce" % impl)
+    _check_layer(ya, yq, p, "c1", "b1", act="relu", what="impl %d: squeeze" % impl)
+    _check_layer(yq, ycat[..., :ce], p, "c2", "b2", act="relu", residuals=[ys[..., :ce]], what="impl %d: expand1x1 + skip" % impl)
+    _check_layer(yq, ycat[..., ce:], p, "c3", "b3", act="relu", residuals=[ys[..., ce:]], what="impl %d: expand3x3 + skip" % impl)
+    _check_layer(ycat, yq2, p, "c4", "b4", act="relu", what="impl %d: squeeze 2" % impl)
+    _check_layer(yq2, got, p, "c5", None, act="relu", transpose=True, what="impl %d: transposed conv" % impl)
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -170,11 +224,11 @@ def test_residual_and_skip_adds(impl):
   _rand_vars(g, rng)
   x = _input(rng, B, H, W)
   p = _tp(g)
-  xa = O.leaky(O.batch_norm(O._conv(_nchw(x), p, "c0"), p, "b0"))
-  xs = O.leaky(O.batch_norm(O._conv(xa, p, "c1"), p, "b1"))
-  xy = O.leaky(O.batch_norm(O._conv(xs, p, "c2"), p, "b2")) + xs + xa
-  got = t.run(y, B, x, impl)
-  assert np.abs(got - _nhwc(xy)).max() < 3e-2
+  got = t.run(y, B, x, impl, keep=[g.input, a, s])
+  xin, ya, ys = t.kept
+  _check_layer(xin, ya, p, "c0", "b0", act="leaky", what="conv1")
+  _check_layer(ya, ys, p, "c1", "b1", act="leaky", what="block 1x1")
+  _check_layer(ys, got, p, "c2", "b2", act="leaky", residuals=[ys, ya], what="block 3x3 + residual + skip")
 
 
 @pytest.mark.parametrize("C,W", [(64, 70), (128, 33)])

@@ -108,6 +108,30 @@ def test_ring_variant_and_facade_classes(golden_dir):
   assert np.array_equal(sem.proj_mask, (o["proj_idx"] > 0).astype(np.float32))
 
 
+def test_ring_variant_against_reference_fixture(golden_dir):
+  """a2 pinned: the fixture is the output of the reference's own laserscan_nuscenes.LaserScan (ring projection,
+  :191-223).  Equality on every pixel no libm-ambiguous point (column from atan2) can touch, incl. colliding points
+  (the highest index written wins) - and equality with the CR oracle everywhere."""
+  from pclsegmentation_b200.laserscan import LaserScan
+  g = _golden(golden_dir, "nusc_ring_32x1024")
+  H, W = int(g["H"]), int(g["W"])
+  scan = LaserScan(project=True, H=H, W=W, fov_up=None, fov_down=None, use_ring_projection=True)
+  scan.set_points(g["points"].copy(), g["remissions"].copy(), g["ring"].copy())
+  o = P.range_projection_ring(g["points"], g["remissions"], g["ring"], H, W, "cr")
+  for k in ("proj_range", "proj_xyz", "proj_remission", "proj_idx", "proj_x"):
+    assert np.array_equal(getattr(scan, k), o[k]), k
+  amb = P.ambiguous_points(g["points"], H, W, 12.0, -30.0, columns_only=True)
+  assert np.array_equal(scan.proj_x[~amb], g["proj_x"][~amb])
+  rows = (H - 1) - g["ring"]
+  touched = np.zeros((H, W), bool)
+  touched[rows[amb], scan.proj_x[amb]] = True
+  touched[rows[amb], g["proj_x"][amb]] = True
+  ok = ~touched
+  assert ok.mean() > 0.99
+  for k in ("proj_idx", "proj_range", "proj_xyz", "proj_remission", "proj_mask"):
+    assert np.array_equal(getattr(scan, k)[ok], g[k][ok]), k
+
+
 def test_full_size_properties():
   """BASELINE config 4 size (64 scans x ~120 k points -> 64x2048): size-independent properties checked on the GPU:
   the winner of every pixel is the minimum (depth, index) over the points that map to it."""

@@ -1,4 +1,6 @@
 """Host side of the drop-in: config contract, registries, model builders' traces, error behaviour (no GPU)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -32,6 +34,29 @@ def test_config_contract_values():
   mc = SqueezeSegV2Config()
   mc.FOO = 3
   assert mc["FOO"] == 3  # attribute-dict behaviour of EasyDict
+
+
+def test_configs_equal_reference_field_by_field(golden_dir):
+  """a11: every field of the six `mc` factories equals the reference's (tests/golden/reference_configs.json, dumped by
+  tests/golden/make_config_golden.py from the unmodified pcl_segmentation/configs/*.py): same field set, same values,
+  and for arrays the same dtype and shape (INPUT_MEAN / INPUT_STD are float64 [1,1,5])."""
+  import json
+  import os
+  ref = json.load(open(os.path.join(golden_dir, "reference_configs.json")))
+  assert set(ref) == set(config_map)
+  for key, fields in ref.items():
+    mc = config_map[key]()
+    assert set(mc.keys()) == set(fields), (key, set(mc.keys()) ^ set(fields))
+    for name, want in fields.items():
+      got = mc[name]
+      if isinstance(want, dict) and set(want) == {"dtype", "shape", "data"}:
+        assert isinstance(got, np.ndarray), (key, name)
+        assert str(got.dtype) == want["dtype"] and list(got.shape) == want["shape"], (key, name, got.dtype, got.shape)
+        assert np.array_equal(got, np.array(want["data"], dtype=got.dtype)), (key, name)
+      elif isinstance(want, dict):
+        assert {str(k): v for k, v in got.items()} == want, (key, name)
+      else:
+        assert type(got) is type(want) and got == want, (key, name, got, want)
 
 
 def test_registries():
@@ -174,3 +199,26 @@ def test_iou_helper_matches_oracle():
   a = confusion_matrix_to_iou_recall_precision(cm)
   b = C.iou_recall_precision(cm)
   assert all(np.allclose(x, y) for x, y in zip(a, b))
+
+
+def test_cli_weight_loading_never_falls_back_silently(tmp_path):
+  """--path_to_model must always be loaded when given (a checkpoint PREFIX never exists as a file), a wrong
+  path is an error (the reference's tf.keras.models.load_model raises, inference.py:39), and running on random weights
+  needs the explicit --random_init."""
+  import argparse
+  from pclsegmentation_b200.inference import load_model_weights
+  mc, model = load_model_config("squeezesegv2", "squeezesegv2")
+  model.randomize_batch_norm(3)
+  want = model.get_weights_dict()
+  prefix = str(tmp_path / "ckpt")
+  model.save_weights_bundle(prefix)
+  assert not os.path.exists(prefix) and os.path.exists(prefix + ".index")
+  _, fresh = load_model_config("squeezesegv2", "squeezesegv2")
+  load_model_weights(fresh, argparse.Namespace(path_to_model=prefix, random_init=False))
+  assert all(np.array_equal(fresh.variables[k], want[k]) for k in want)
+  for bad in (str(tmp_path / "nope"), str(tmp_path / "nope.npz")):
+    with pytest.raises(FileNotFoundError):
+      load_model_weights(fresh, argparse.Namespace(path_to_model=bad, random_init=False))
+  with pytest.raises(SystemExit):
+    load_model_weights(fresh, argparse.Namespace(path_to_model=None, random_init=False))
+  load_model_weights(fresh, argparse.Namespace(path_to_model=None, random_init=True), verbose=False)

@@ -90,3 +90,34 @@ def test_empty_scan_and_ring_variant():
   # ring 0 -> last row; in-order scatter: the HIGHER index (1) wins even though it is farther
   assert o["proj_idx"][3, o["proj_x"][0]] == 1 and o["proj_range"][3, o["proj_x"][0]] == 20
   assert o["proj_idx"][0, o["proj_x"][2]] == 2
+
+
+def test_ring_oracle_matches_reference_fixture(golden_dir):
+  """`do_range_projection_ring` (laserscan_nuscenes.py:191-223) as run by the reference class itself
+  (tests/golden/make_projection_golden.py: run_ring_case): the column depends on atan2 (libm-ambiguous points excluded
+  like above), the row on the ring index; the highest point index written to a pixel wins."""
+  g = load(golden_dir, "nusc_ring_32x1024")
+  H, W = int(g["H"]), int(g["W"])
+  assert np.unique(np.stack([(H - 1) - g["ring"], g["proj_x"]]), axis=1).shape[1] < g["ring"].shape[0]  # collisions exist
+  for trig in ("libm", "cr"):
+    o = P.range_projection_ring(g["points"], g["remissions"], g["ring"], H, W, trig)
+    amb = P.ambiguous_points(g["points"], H, W, 12.0, -30.0, columns_only=True)
+    assert amb.mean() < 2e-3
+    assert np.array_equal(o["proj_x"][~amb], g["proj_x"][~amb])
+    touched = np.zeros((H, W), bool)
+    rows = (H - 1) - g["ring"]
+    for src in (o, g):
+      touched[rows[amb], src["proj_x"][amb]] = True
+    ok = ~touched
+    for k in ("proj_idx", "proj_range", "proj_xyz", "proj_remission"):
+      assert np.array_equal(o[k][ok], g[k][ok]), (trig, k)
+    assert ok.mean() > 0.99
+  # the nuScenes file's own copy of do_range_projection (:226-286) equals the KITTI one the oracle restates
+  o = P.range_projection(g["points"], g["remissions"], H, W, 12.0, -30.0, "libm")
+  assert np.array_equal(o["unproj_range"], g["fov_unproj_range"])
+  amb = P.ambiguous_points(g["points"], H, W, 12.0, -30.0)
+  assert np.array_equal(o["proj_x"][~amb], g["fov_proj_x"][~amb]) and np.array_equal(o["proj_y"][~amb], g["fov_proj_y"][~amb])
+  touched = np.zeros((H, W), bool)
+  for src_x, src_y in ((o["proj_x"], o["proj_y"]), (g["fov_proj_x"], g["fov_proj_y"])):
+    touched[src_y[amb], src_x[amb]] = True
+  assert np.array_equal(o["proj_range"][~touched], g["fov_proj_range"][~touched])
