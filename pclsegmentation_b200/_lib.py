@@ -6,7 +6,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int
     c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpclseg.so")
+LIB_PATH = os.path.join(_HERE, "libpclseg%s.so" % os.environ.get("PCLS_LIB_SUFFIX", ""))  # suffix: development builds
 
 PCLS_F16, PCLS_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2

@@ -13,8 +13,10 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libpclseg.so")
-OBJ_DIR = os.path.join(HERE, "build")
+# PCLS_LIB_SUFFIX=_dbg builds a second library next to the product one (development builds with extra flags)
+_SUFFIX = os.environ.get("PCLS_LIB_SUFFIX", "")
+LIB = os.path.join(HERE, "libpclseg%s.so" % _SUFFIX)
+OBJ_DIR = os.path.join(HERE, "build%s" % _SUFFIX)
 SOURCES = ["error.cu", "projection.cu", "head.cu", "input_stage.cu", "confusion.cu", "nn_kernels.cu", "conv_tc.cu",
            "net.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
