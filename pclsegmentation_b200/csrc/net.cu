@@ -432,7 +432,7 @@ int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool ra
       if (conv_impl == 0 && L.tc_ok) {
         // the final conv can run the segmentation head in its epilogue (every 32-pixel warp row must be contiguous
         // in memory: full-width tiles of 128 pixels)
-        const bool fuse = fuse_head && L.out == logits_tensor && (W % 128 == 0);
+        const bool fuse = fuse_head && L.out == logits_tensor && (W % 128 == 0 || L.hp != nullptr);
         head_args.head = fuse ? 1 : 0;
         head_args.none_index = none_index; head_args.mask = mask_buf;
         head_args.probs = probs; head_args.preds = preds; head_args.logits = logits;
@@ -746,6 +746,7 @@ extern "C" int pcls_net_set_option(pcls_net* net, const char* name, int value) {
     PCLS_REQUIRE(!n->finalized, "keep_tensors must be set before pcls_net_finalize");
     n->keep_tensors = value != 0; return PCLS_OK;
   }
+  if (!strcmp(name, "tc_head")) { tc_head_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_halo")) { tc_halo_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_tma_store")) { tc_tma_store_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_group")) { tc_group_mode = value; return PCLS_OK; }

@@ -13,7 +13,9 @@ struct TensorInfo {
   size_t offset = 0;          // per-frame byte offset inside the arena (scaled by frames_per_pass)
 };
 
-struct TcPlan;  // tcgen05 launch plan of one conv layer (conv_tc.cu)
+struct TcPlan;    // tcgen05 launch plan of one conv layer (conv_tc.cu)
+struct HeadPlan;  // launch plan of the logits layer + fused segmentation head (conv_head.cu)
+extern int tc_head_mode;
 extern int tc_halo_mode, tc_resident_mode, tc_base_offset_mode, tc_tma_store_mode, tc_group_mode, tc_res_tma_mode, tc_split_mode, tc_vstream_mode;
 extern const int tc_debug_compiled;
 extern unsigned long long* tc_debug_buf;  // A/B measurement switches (process-wide)
@@ -25,6 +27,7 @@ struct ConvLayer {
   std::vector<float> bias_f32;  // folded [cout_pad]
   bool tc_ok = false;
   TcPlan* tc = nullptr;
+  HeadPlan* hp = nullptr;
   // Pixel-pair view for the convolutions that read the 8-channel network input (tensor-core path only):
   // [B,H,W,8] is viewed as [B,H,W/2,16]; `ptc` / `w_tc` / `bias_tc` describe the equivalent convolution on pairs.
   bool pair_view = false;
@@ -109,6 +112,10 @@ struct Net {
   int tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry);
   int tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s);
   void tc_release();
+  // logits layer + fused head (conv_head.cu)
+  int head_plan_layer(ConvLayer& L);
+  int head_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s);
+  void head_release(ConvLayer& L);
 };
 
 }  // namespace pcls
