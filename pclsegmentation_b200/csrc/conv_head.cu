@@ -287,8 +287,8 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
         for (int c = 0; c < CS; c += 4) mx = fmaxf(fmaxf(mx, fmaxf(lg[c], lg[c + 1])), fmaxf(lg[c + 2], lg[c + 3]));
         float sum = 0.0f;
-#pragma unroll
         const float mxl = -mx * 1.4426950408889634f;
+#pragma unroll
         for (int c = 0; c < CS; ++c) { lg[c] = ex2_ftz(fmaf(lg[c], 1.4426950408889634f, mxl)); sum += lg[c]; }
         const float inv = __fdividef(1.0f, sum);
         int best = 0;

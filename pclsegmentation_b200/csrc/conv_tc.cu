@@ -84,6 +84,12 @@ struct TcParams {
   // kernel only at the centre tap.  The other eight taps then load and multiply only the weight rows [n1, BN).
   int n1, b_small_bytes, bres_tx;
   uint32_t idesc_small, idesc_lo;
+  // N-split across CTAs (nsplit = 1): the layer's N is cut into n_nt tiles of BN channels and the grid is a multiple of n_nt,
+  // so a CTA only ever sees ONE N tile (tile % n_nt == blockIdx.x % n_nt) and keeps that tile's weights resident - for
+  // layers whose whole weight set does not fit in smem (the A tiles are read n_nt times, from L2).  With perm = 1 the
+  // weight / bias rows were permuted so that every N tile holds a slice of both halves of a merged Fire expand
+  // (centre-tap-only channels first, split-N applies per tile); cblk_off[i] = output channel of 64-column block i.
+  int nsplit, perm, cblk_off[8];
   // vertical streaming (3x3 stride-1 layers with the halo tile and resident weights): a CTA walks R consecutive output
   // rows of one 128-pixel column strip; every input row travels to smem ONCE per strip and serves the three output rows
   // around it (R + 2 row loads per R tiles instead of 3 R).  R is chosen per launch (R = 1: plain tiles).
@@ -106,9 +112,11 @@ struct TcParams {
 };
 
 // 8 accumulator columns -> +bias, activation, +residuals -> one 16-byte vector of 16-bit outputs.
-// Branch-free activation: act(v) = max(v, v * slope) with slope 1 (none), 0 (ReLU), 0.1 (LeakyReLU).
-template <typename T>
-__device__ __forceinline__ int4 epilogue_vec8(const uint32_t* acc, const float* bias8, float slope, bool has_r0,
+// Activation: ONE instruction per element for ReLU / none - max(v, lo) with lo = 0 / -inf - and two for LeakyReLU(0.1)
+// (max(v, 0.1 v)); LEAKY is a kernel template parameter (the epilogue's instruction count is what bounds the
+// memory-side layers: ncu, 291 instructions per 32-column chunk before this).
+template <typename T, bool LEAKY>
+__device__ __forceinline__ int4 epilogue_vec8(const uint32_t* acc, const float* bias8, float lo, bool has_r0,
                                               const int4& r0, bool has_r1, const int4& r1) {
   const float4 b0 = *reinterpret_cast<const float4*>(bias8);
   const float4 b1 = *reinterpret_cast<const float4*>(bias8 + 4);
@@ -116,7 +124,7 @@ __device__ __forceinline__ int4 epilogue_vec8(const uint32_t* acc, const float* 
                 __uint_as_float(acc[3]) + b0.w, __uint_as_float(acc[4]) + b1.x, __uint_as_float(acc[5]) + b1.y,
                 __uint_as_float(acc[6]) + b1.z, __uint_as_float(acc[7]) + b1.w};
 #pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], v[j] * slope);
+  for (int j = 0; j < 8; ++j) v[j] = LEAKY ? fmaxf(v[j], v[j] * 0.1f) : fmaxf(v[j], lo);
   if (has_r0) {
     float f[8];
     unpack8<T>(r0, f);
@@ -133,7 +141,7 @@ __device__ __forceinline__ int4 epilogue_vec8(const uint32_t* acc, const float* 
 }
 
 
-template <typename T, int KC, int SUB, int G, bool RES>
+template <typename T, int KC, int SUB, int G, bool RES, bool LEAKY>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
@@ -204,6 +212,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // [phase][group][K chunk][sub] so that the issuer only increments an address
         mbar_arrive_expect_tx_elect(BRES_BAR, (uint32_t)p.bres_tx);
         uint32_t dst = bres_base;
+        const int n0r = p.nsplit ? (int)(blockIdx.x % (unsigned)n_nt) * BN : 0;   // this CTA's N tile (N-split across CTAs)
         for (int ph = 0; ph < n_phase; ++ph)
           for (int g = 0; g < n_groups; ++g)
             for (int kc = 0; kc < kchunks; ++kc)
@@ -211,10 +220,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               for (int u = 0; u < SUB; ++u) {
                 const int tap = p.grp_w[ph][g][u];
                 if (p.n1 > 0 && tap != 4) {   // rows [n1, BN) only
-                  tma_load_3d_elect(dst, &map_b2, BRES_BAR, kc * KC, p.n1, tap);
+                  tma_load_3d_elect(dst, &map_b2, BRES_BAR, kc * KC, n0r + p.n1, tap);
                   dst += (uint32_t)p.b_small_bytes;
                 } else {
-                  tma_load_3d_elect(dst, &map_b, BRES_BAR, kc * KC, 0, tap);
+                  tma_load_3d_elect(dst, &map_b, BRES_BAR, kc * KC, n0r, tap);
                   dst += b_tile_bytes;
                 }
               }
@@ -418,7 +427,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int cout = p.cout, out_channels = p.out_channels, out_coff = p.out_coff;
     const int blk_shift = p.cout_blk_shift;              // pixel-group view: column n -> pixel n >> blk_shift
     const int blk_mask = G > 1 ? (1 << blk_shift) - 1 : -1;
-    const float slope = p.act == PCLS_ACT_RELU ? 0.0f : (p.act == PCLS_ACT_LEAKY ? 0.1f : 1.0f);
+    const float slope = p.act == PCLS_ACT_RELU ? 0.0f : (p.act == PCLS_ACT_LEAKY ? 0.1f : 1.0f);   // (float32 logits path)
+    const float act_lo = p.act == PCLS_ACT_RELU ? 0.0f : -INFINITY;
     const uint16_t* res0 = reinterpret_cast<const uint16_t*>(p.res0);
     const uint16_t* res1 = reinterpret_cast<const uint16_t*>(p.res1);
     const int res0_channels = p.res0_channels, res1_channels = p.res1_channels;
@@ -432,6 +442,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // never run more groups than there are accumulators
     const uint32_t ng = n_acc < (uint32_t)TC_NG ? n_acc : (uint32_t)TC_NG;
     uint32_t tl = 0, blk = 0;
+    const uint32_t nrb = (uint32_t)p.n_cbuf;   // staging buffers per group (res_tma: 3, or 2 when smem is short)
     // res_tma: TMA load of the residual block (tile, channel block cb) into staging buffer `bi` of this group
     auto issue_res = [&](int rtile, int rcb, uint32_t bi) {
       int r2 = rtile;
@@ -440,10 +451,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int wt2 = r2 % n_wt; r2 /= n_wt;
       const int ht2 = r2 % n_ht;
       const int b2 = r2 / n_ht;
-      const uint32_t dst = cstage_base + (uint32_t)(grp * 3 + (int)bi) * c_stage_bytes;
+      const uint32_t dst = cstage_base + (uint32_t)(grp * p.n_cbuf + (int)bi) * c_stage_bytes;
       const uint32_t bar = RFULL_BAR(grp * 3 + (int)bi);
       const int pp2 = G > 1 ? (nt2 * BN + rcb) >> blk_shift : 0;
-      const int c02 = out_coff + ((nt2 * BN + rcb) & blk_mask);
+      const int c02 = out_coff + (p.perm ? p.cblk_off[(nt2 * BN + rcb) >> 6] : ((nt2 * BN + rcb) & blk_mask));
       mbar_arrive_expect_tx(bar, 128u * 64u * 2u);
       if (c_is_5d) tma_load_5d(dst, &map_r, bar, c02, G > 1 ? pp2 : ph2, wt2 * BW, ht2 * BH, b2);
       else tma_load_4d(dst, &map_r, bar, c02, wt2 * BW, ht2 * BH, b2);
@@ -551,7 +562,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             r0v = res_tma ? ld_shared_v4(res_row + (uint32_t)(((((cc & 63) >> 3) + g) ^ (m & 7)) << 4))
                 : res_smem ? ld_shared_v4(rslot + (uint32_t)(((cc & 63) >> 3) + g) * 2048u) : r0[g];
           }
-          sink(g, epilogue_vec8<T>(v + g * 8, bias_s + n0 + cc + g * 8, slope, RES && has_r0, r0v, RES && has_r1, r1[g]));
+          sink(g, epilogue_vec8<T, LEAKY>(v + g * 8, bias_s + n0 + cc + g * 8, act_lo, RES && has_r0, r0v, RES && has_r1, r1[g]));
         }
         if (reg_res && cc + 32 < BN) load_r1(cc + 32);
       };
@@ -664,12 +675,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               int ntile = tile, ncb = cb + 64;
               if (ncb >= BN) { ncb = 0; ntile = tile_at(tl + ng); }
               if (ntile >= 0) {
-                bulk_wait_read1();
-                issue_res(ntile, ncb, (blk + 1u) % 3u);
+                // three buffers: store k-1 may still be reading its buffer; two buffers: it must have finished (same buffer)
+                if (nrb == 3u) bulk_wait_read1(); else bulk_wait_read0();
+                issue_res(ntile, ncb, (blk + 1u) % nrb);
               }
             }
-            buf = cstage_base + (uint32_t)(grp * 3 + (int)(blk % 3u)) * c_stage_bytes;
-            { DBG_T0; mbar_wait(RFULL_BAR(grp * 3 + (int)(blk % 3u)), (blk / 3u) & 1u); DBG_ADD(4); }
+            buf = cstage_base + (uint32_t)(grp * (int)nrb + (int)(blk % nrb)) * c_stage_bytes;
+            { DBG_T0; mbar_wait(RFULL_BAR(grp * 3 + (int)(blk % nrb)), (blk / nrb) & 1u); DBG_ADD(4); }
           } else {
             // two staging buffers per group: block k is written while the TMA store of block k-1 drains the other one
             buf = cstage_base + (uint32_t)(grp * 2 + (int)(blk & 1u)) * c_stage_bytes;
@@ -685,7 +697,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           { DBG_T0; group_barrier(bar_id); DBG_ADD(5); }
           if (issuer) {
             const int pp = G > 1 ? (n0 + cb) >> blk_shift : 0;
-            const int c0 = out_coff + ((n0 + cb) & blk_mask);
+            const int c0 = out_coff + (p.perm ? p.cblk_off[(n0 + cb) >> 6] : ((n0 + cb) & blk_mask));
             if (c_is_5d) tma_store_5d(&map_c, buf, c0, G > 1 ? pp : ph, wt * BW, ht * BH, b);
             else tma_store_4d(&map_c, buf, c0, wt * BW, ht * BH, b);
             bulk_commit();
@@ -733,25 +745,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const int);
-template <typename T, bool RES>
+template <typename T, bool RES, bool LEAKY>
 static TcKernelFn tc_kernel_for_t(int KC, int SUB, int G) {
-  if (G == 4) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 4, RES> : conv_tc_kernel<T, 64, 1, 4, RES>;
+  if (G == 4) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 4, RES, LEAKY> : conv_tc_kernel<T, 64, 1, 4, RES, LEAKY>;
   if (G == 2) {
-    if (KC == 64) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 2, RES> : conv_tc_kernel<T, 64, 1, 2, RES>;
-    return SUB == 3 ? conv_tc_kernel<T, 32, 3, 2, RES> : conv_tc_kernel<T, 32, 1, 2, RES>;
+    if (KC == 64) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 2, RES, LEAKY> : conv_tc_kernel<T, 64, 1, 2, RES, LEAKY>;
+    return SUB == 3 ? conv_tc_kernel<T, 32, 3, 2, RES, LEAKY> : conv_tc_kernel<T, 32, 1, 2, RES, LEAKY>;
   }
-  if (SUB == 3) return KC == 64 ? conv_tc_kernel<T, 64, 3, 1, RES> : KC == 32 ? conv_tc_kernel<T, 32, 3, 1, RES> : conv_tc_kernel<T, 16, 3, 1, RES>;
-  return KC == 64 ? conv_tc_kernel<T, 64, 1, 1, RES> : KC == 32 ? conv_tc_kernel<T, 32, 1, 1, RES> : conv_tc_kernel<T, 16, 1, 1, RES>;
+  if (SUB == 3) return KC == 64 ? conv_tc_kernel<T, 64, 3, 1, RES, LEAKY> : KC == 32 ? conv_tc_kernel<T, 32, 3, 1, RES, LEAKY> : conv_tc_kernel<T, 16, 3, 1, RES, LEAKY>;
+  return KC == 64 ? conv_tc_kernel<T, 64, 1, 1, RES, LEAKY> : KC == 32 ? conv_tc_kernel<T, 32, 1, 1, RES, LEAKY> : conv_tc_kernel<T, 16, 1, 1, RES, LEAKY>;
 }
-static TcKernelFn tc_kernel_for(int KC, int SUB, int G, int is_bf16, int res) {
-  if (res) return is_bf16 ? tc_kernel_for_t<__nv_bfloat16, true>(KC, SUB, G) : tc_kernel_for_t<__half, true>(KC, SUB, G);
-  return is_bf16 ? tc_kernel_for_t<__nv_bfloat16, false>(KC, SUB, G) : tc_kernel_for_t<__half, false>(KC, SUB, G);
+template <typename T>
+static TcKernelFn tc_kernel_for_tt(int KC, int SUB, int G, int res, int leaky) {
+  if (res) return leaky ? tc_kernel_for_t<T, true, true>(KC, SUB, G) : tc_kernel_for_t<T, true, false>(KC, SUB, G);
+  return leaky ? tc_kernel_for_t<T, false, true>(KC, SUB, G) : tc_kernel_for_t<T, false, false>(KC, SUB, G);
+}
+static TcKernelFn tc_kernel_for(int KC, int SUB, int G, int is_bf16, int res, int leaky) {
+  return is_bf16 ? tc_kernel_for_tt<__nv_bfloat16>(KC, SUB, G, res, leaky) : tc_kernel_for_tt<__half>(KC, SUB, G, res, leaky);
 }
 
 struct TcPlan {
   CUtensorMap map_a, map_b, map_c, map_r, map_b2;
   TcParams prm;
   size_t smem_bytes;
+  void* w_dev;       // plan-owned copies with permuted rows (N-split across CTAs of a merged Fire expand), else NULL
+  float* bias_dev;
+  ~TcPlan() { if (w_dev) cudaFree(w_dev); if (bias_dev) cudaFree(bias_dev); }
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -789,7 +808,7 @@ int make_map(CUtensorMap* map, bool bf16, void* base, int rank, const uint64_t* 
 }
 
 // A/B switches for measurement (pcls_net_set_option before finalize): halo reuse, resident weights, base offset
-int tc_tma_store_mode = 1, tc_group_mode = 1, tc_res_tma_mode = 1, tc_split_mode = 1, tc_vstream_mode = 0;
+int tc_tma_store_mode = 1, tc_group_mode = 1, tc_res_tma_mode = 1, tc_split_mode = 1, tc_vstream_mode = 0, tc_nsplit_mode = 1;
 const int tc_debug_compiled = PCLS_TC_DEBUG;
 unsigned long long* tc_debug_buf = nullptr;  // [148][24] counters of the most recent launch when enabled
 int tc_halo_mode = 1, tc_resident_mode = 1, tc_base_offset_mode = 0;  // measured: UMMA swizzles on absolute smem address bits, a row-shifted start needs NO base offset
@@ -852,6 +871,38 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
       z = z / 16 * 16;
       if (z >= 16 && q.BN - z >= 16) q.n1 = z;
     }
+    // N-split across CTAs: a 3x3 layer whose weights do not fit in smem next to the pipeline (fire10's merged expand: 160 KB;
+    // fire6 / fire7's 64(48) -> 192 expand3x3: 216 KB) streams them from L2 for every tile - 10 x the bytes of the A tile,
+    // L2 -> smem bound (wait-cycle counters: issuer 50 % on FULL).  Cutting N in two and giving every CTA one half keeps the
+    // half resident; the A tiles are then loaded twice, from L2.  Merged expands ([expand1x1 | expand3x3], n1 centre-only
+    // channels) are cut so that each half holds half of BOTH parts (rows permuted): equal work per CTA, split-N per half.
+    q.nsplit = 0; q.perm = 0;
+    for (int i = 0; i < 8; ++i) q.cblk_off[i] = i * 64;
+    std::vector<int> row_perm;   // new weight row -> old weight row, when permuted
+    if (tc_nsplit_mode && tc_resident_mode && tc_halo_mode && G == 1 && cp.mode == MODE_3x3_S1 && q.n_nt == 1 && !L.pair_view &&
+        q.KC == 64 && !cp.out_f32 && cp.cout == cp.cout_pad && cp.Wout >= 128 && L.res1 < 0) {
+      const int btile1 = q.BN * q.KC * 2, bsmall1 = (q.BN - q.n1) * q.KC * 2;
+      const int all_w1 = q.n1 > 0 ? q.kchunks * (btile1 + 8 * bsmall1) : 9 * q.kchunks * btile1;
+      const int half = q.BN / 2;
+      if (all_w1 > 112 * 1024) {
+        if (q.n1 > 0 && q.n1 % 128 == 0 && (q.BN - q.n1) % 128 == 0 && tc_tma_store_mode && (L.res0 < 0 || tc_res_tma_mode)) {
+          const int h1 = q.n1 / 2, h3 = (q.BN - q.n1) / 2;
+          if (q.kchunks * ((h1 + h3) * q.KC * 2 + 8 * h3 * q.KC * 2) <= 112 * 1024) {
+            row_perm.resize(q.BN);
+            int blk = 0;
+            for (int nt = 0; nt < 2; ++nt) {
+              for (int j = 0; j < h1; ++j) row_perm[nt * (h1 + h3) + j] = nt * h1 + j;
+              for (int j = 0; j < h3; ++j) row_perm[nt * (h1 + h3) + h1 + j] = q.n1 + nt * h3 + j;
+              for (int j = 0; j < h1; j += 64) q.cblk_off[blk++] = nt * h1 + j;
+              for (int j = 0; j < h3; j += 64) q.cblk_off[blk++] = q.n1 + nt * h3 + j;
+            }
+            q.BN = h1 + h3; q.n_nt = 2; q.n1 = h1; q.nsplit = 1; q.perm = 1;
+          }
+        } else if (q.n1 == 0 && half % 32 == 0 && 9 * q.kchunks * half * q.KC * 2 <= 112 * 1024) {
+          q.BN = half; q.n_nt = 2; q.nsplit = 1;
+        }
+      }
+    }
     q.b_small_bytes = (q.BN - q.n1) * q.KC * 2;
     // pixel grid tiled by BW x BH = 128
     const bool deconv = cp.mode == MODE_DECONV;  // (two-phase form; MODE_ROW3 is the single-pass form)
@@ -877,9 +928,10 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
     if (halo) {
       const int btile_ = G > 1 ? cp.cout_pad * cin_blk * 2 : q.BN * q.KC * 2;
       const int all_w_ = q.n1 > 0 ? q.kchunks * (btile_ + (cp.ntaps - 1) * q.b_small_bytes) : cp.ntaps * q.kchunks * btile_;
-      const bool resident_ = tc_resident_mode && q.n_nt == 1 && all_w_ <= 112 * 1024;
+      const bool resident_ = tc_resident_mode && (q.n_nt == 1 || q.nsplit) && all_w_ <= 112 * 1024;
       const int st_ = (130 * q.KC * 2 + 1023) / 1024 * 1024 + (resident_ ? 0 : 3 * btile_);
-      const int staging_ = 2 * TC_NG * 16384 + ((L.res0 >= 0 && (q.BN <= 128 || resident_)) ? TC_NG * 16384 : 0);
+      // (N-split layers hold half of a big weight set: they take two staging buffers per group instead of three)
+      const int staging_ = 2 * TC_NG * 16384 + ((L.res0 >= 0 && (q.BN <= 128 || resident_) && !q.nsplit) ? TC_NG * 16384 : 0);
       if ((max_smem - 2048 - staging_ - cp.cout_pad * 4 - (resident_ ? all_w_ + 1024 : 0)) / st_ < 3) halo = false;
     }
     if (G > 1 && cp.mode != MODE_1x1 && !halo) {  // the banded issue of a 3-tap row needs the halo tile: plan again ungrouped
@@ -941,12 +993,13 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
     const int all_w = q.n1 > 0 ? q.kchunks * (q.b_tile_bytes + 8 * q.b_small_bytes)
                                : q.n_phase * q.n_groups * q.kchunks * q.sub * q.b_tile_bytes;
     q.bres_tx = all_w;
-    q.b_resident = (tc_resident_mode && q.n_nt == 1 && all_w <= 112 * 1024) ? 1 : 0;
+    q.b_resident = (tc_resident_mode && (q.n_nt == 1 || q.nsplit) && all_w <= 112 * 1024) ? 1 : 0;
+    if (q.nsplit && !q.b_resident) { set_error("tc plan: N-split layer lost its resident weights"); delete plan; return PCLS_ERR_STATE; }
     q.bres_bytes = q.b_resident ? (all_w + 1023) / 1024 * 1024 : 0;
     // residual0 of the memory-bound layers (resident weights) with the TMA-store epilogue: TMA-loaded into a third
     // staging buffer and added in place (no per-thread address arithmetic, a whole block of latency hiding)
     q.res_tma = (tc_res_tma_mode && L.res0 >= 0 && q.tma_store && q.cbw == 64 && q.b_resident && (cp.res0_channels * 2) % 16 == 0) ? 1 : 0;
-    q.n_cbuf = q.res_tma ? 3 : 2;
+    q.n_cbuf = (q.res_tma && !q.nsplit) ? 3 : 2;
     q.res_smem = (!q.res_tma && L.res0 >= 0 && q.BN <= 128) ? 1 : 0;
     const int cstage_total = (q.tma_store ? q.n_cbuf * TC_NG * q.c_stage_bytes : 0) + (q.res_smem ? TC_NG * 16384 : 0);
     if (G > 1 && !q.b_resident) { delete plan; *retry = true; return PCLS_OK; }
@@ -1000,11 +1053,33 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
       rc = make_map(&plan->map_a, bf16, a_base, 4, dims, str, box, swz);
     }
     if (rc) { delete plan; return rc; }
+    const void* w_src = cp.w;
+    if (q.perm) {   // permuted copies of the packed weights [tap][row][cin_pad] and of the bias
+      std::vector<uint16_t> hw((size_t)cp.ntaps * cp.cout_pad * cp.cin_pad);
+      std::vector<float> hb(cp.cout_pad);
+      for (int t = 0; t < cp.ntaps; ++t)
+        for (int n = 0; n < cp.cout_pad; ++n)
+          for (int ci = 0; ci < cp.cin_pad; ++ci) {
+            const float w = L.w_f32[((size_t)t * cp.cout_pad + row_perm[n]) * cp.cin_pad + ci];
+            uint16_t bits;
+            if (bf16) { __nv_bfloat16 hv = __float2bfloat16_rn(w); memcpy(&bits, &hv, 2); }
+            else { __half hv = __float2half_rn(w); memcpy(&bits, &hv, 2); }
+            hw[((size_t)t * cp.cout_pad + n) * cp.cin_pad + ci] = bits;
+          }
+      for (int n = 0; n < cp.cout_pad; ++n) hb[n] = L.bias_f32[row_perm[n]];
+      if (cudaMalloc(&plan->w_dev, hw.size() * 2) != cudaSuccess || cudaMalloc((void**)&plan->bias_dev, hb.size() * 4) != cudaSuccess ||
+          cudaMemcpy(plan->w_dev, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+          cudaMemcpy(plan->bias_dev, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("tc plan: upload of the permuted weights failed"); delete plan; return PCLS_ERR_CUDA;
+      }
+      w_src = plan->w_dev;
+      q.bias = plan->bias_dev;
+    }
     {
       const uint64_t dims[3] = {(uint64_t)cp.cin_pad, (uint64_t)cp.cout_pad, (uint64_t)cp.ntaps};
       const uint64_t str[2] = {(uint64_t)cp.cin_pad * 2, (uint64_t)cp.cin_pad * cp.cout_pad * 2};
       const uint32_t box[3] = {(uint32_t)(G > 1 ? cin_blk : q.KC), (uint32_t)(G > 1 ? cp.cout_pad : q.BN), 1};
-      rc = make_map(&plan->map_b, bf16, const_cast<void*>(cp.w), 3, dims, str, box, swz_b);
+      rc = make_map(&plan->map_b, bf16, const_cast<void*>(w_src), 3, dims, str, box, swz_b);
     }
     if (rc) { delete plan; return rc; }
     plan->map_b2 = plan->map_b;
@@ -1012,7 +1087,7 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
       const uint64_t dims[3] = {(uint64_t)cp.cin_pad, (uint64_t)cp.cout_pad, (uint64_t)cp.ntaps};
       const uint64_t str[2] = {(uint64_t)cp.cin_pad * 2, (uint64_t)cp.cin_pad * cp.cout_pad * 2};
       const uint32_t box[3] = {(uint32_t)q.KC, (uint32_t)(q.BN - q.n1), 1};
-      rc = make_map(&plan->map_b2, bf16, const_cast<void*>(cp.w), 3, dims, str, box, swz_b);
+      rc = make_map(&plan->map_b2, bf16, const_cast<void*>(w_src), 3, dims, str, box, swz_b);
       if (rc) { delete plan; return rc; }
     }
     if (q.tma_store) {  // C: the output tensor (or its re-viewed form) inside the arena
@@ -1060,7 +1135,10 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
 
 int Net::tc_prepare() {
   const int max_smem = 227 * 1024;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};   // the opt-in to > 48 KB dynamic smem is per device (and context)
+  int dev = 0;
+  PCLS_CHECK_CUDA(cudaGetDevice(&dev));
+  bool& attr_set = attr_set_dev[dev & 63];
   for (auto& L : convs) {
     bool retry = false;
     int rc = head_plan_layer(L);   // the logits layer has its own kernel (conv_head.cu); falls through when it does not qualify
@@ -1077,7 +1155,8 @@ int Net::tc_prepare() {
           if ((g == 4 && kc != 64) || (g == 2 && kc == 16)) continue;
           for (int bf = 0; bf < 2; ++bf)
             for (int rs = 0; rs < 2; ++rs)
-              PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(kc, sub, g, bf, rs), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+              for (int lk = 0; lk < 2; ++lk)
+                PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(kc, sub, g, bf, rs, lk), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         }
     attr_set = true;
   }
@@ -1104,8 +1183,9 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
     prm.R = R; prm.n_hseg = prm.Hgrid / R;
     work = num_tiles / R;
   }
-  const int grid = work < sm_count() ? work : sm_count();
-  tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0)<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, plan->map_r, plan->map_b2, prm, num_tiles);
+  int grid = work < sm_count() ? work : sm_count();
+  if (prm.nsplit) grid -= grid % prm.n_nt;   // every CTA sees one N tile only (tile % n_nt == blockIdx.x % n_nt)
+  tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0, prm.act == PCLS_ACT_LEAKY ? 1 : 0)<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, plan->map_r, plan->map_b2, prm, num_tiles);
   return check_launch("conv_tc_kernel");
 }
 

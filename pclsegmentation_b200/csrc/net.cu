@@ -13,6 +13,8 @@
 
 namespace pcls {
 
+int pad48_mode = 1;   // A/B switch (pcls_net_set_option "pad48", before the ops are added)
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 template <typename T>
@@ -50,13 +52,14 @@ int Net::add_tensor(int width, int channels, bool logits) {
   TensorInfo t;
   t.width = width;
   t.channels = channels;
+  t.stride = channels;
   t.logits = logits;
   tensors.push_back(t);
   return (int)tensors.size() - 1;
 }
 
 size_t Net::tensor_frame_bytes(const TensorInfo& t) const {
-  return (size_t)H * t.width * t.channels * (t.logits ? 4 : 2);
+  return (size_t)H * t.width * t.stride * (t.logits ? 4 : 2);
 }
 
 int Net::add_conv(const pcls_conv_desc& d) {
@@ -76,6 +79,14 @@ int Net::add_conv(const pcls_conv_desc& d) {
   PCLS_REQUIRE(d.in_tensor >= 0 && d.in_tensor < (int)tensors.size() && d.out_tensor > 0 &&
                    d.out_tensor < (int)tensors.size() && d.in_tensor != d.out_tensor,
                "pcls_net_conv: bad tensor ids in=%d out=%d", d.in_tensor, d.out_tensor);
+  // Channel padding 48 -> 64 (fire6 / fire7 squeeze outputs): with 48 channels the tcgen05 path has to walk K in
+  // 16-channel chunks (32-byte TMA / UMMA rows: nine 4 KB loads per tile, measured 0.21 of the HBM roofline for the 3x3
+  // expand); stored with a 64-channel pixel stride the tensor takes the 128-byte-row path like every other layer.  The
+  // producing conv writes all 64 channels (zero weights and bias beyond 48: act(0) = 0), consumers contract 64 input
+  // channels against zero-padded kernels.  Only for tensors that ONE convolution writes completely.
+  if (pad48_mode && !tensors[d.out_tensor].logits && tensors[d.out_tensor].channels == 48 && tensors[d.out_tensor].stride == 48 &&
+      d.out_channel_offset == 0 && d.cout == 48 && d.residual0 < 0 && d.residual1 < 0 && d.kind == PCLS_CONV)
+    tensors[d.out_tensor].stride = 64;
   const TensorInfo& ti = tensors[d.in_tensor];
   const TensorInfo& to = tensors[d.out_tensor];
   PCLS_REQUIRE(!ti.logits, "pcls_net_conv: cannot read a logits tensor");
@@ -104,10 +115,12 @@ int Net::add_conv(const pcls_conv_desc& d) {
 
   ConvParams& p = L.p;
   p.H = H; p.Win = ti.width; p.Wout = wout;
-  p.cin = d.cin; p.cin_pad = (d.cin + 15) / 16 * 16;
-  p.in_channels = ti.channels;
-  p.cout = d.cout; p.cout_pad = (d.cout + 15) / 16 * 16;
-  p.out_channels = to.channels; p.out_coff = d.out_channel_offset;
+  const bool in_padded = ti.stride > ti.channels, out_padded = to.stride > to.channels;
+  p.cin = d.cin; p.cin_pad = in_padded ? ti.stride : (d.cin + 15) / 16 * 16;
+  p.in_channels = ti.stride;
+  p.cout = out_padded ? to.stride : d.cout; p.cout_pad = (p.cout + 15) / 16 * 16;
+  p.out_channels = to.stride; p.out_coff = d.out_channel_offset;
+  L.cin_logical = d.cin; L.cout_logical = d.cout;
   p.act = d.act;
   p.ntaps = (p.mode == MODE_1x1) ? 1 : (p.mode == MODE_DECONV ? 4 : 9);
   p.pad_left = 0;
@@ -116,8 +129,8 @@ int Net::add_conv(const pcls_conv_desc& d) {
     p.pad_left = total / 2;
   }
   p.out_f32 = d.out_is_logits ? 1 : 0;
-  p.res0_channels = d.residual0 >= 0 ? tensors[d.residual0].channels : 0;
-  p.res1_channels = d.residual1 >= 0 ? tensors[d.residual1].channels : 0;
+  p.res0_channels = d.residual0 >= 0 ? tensors[d.residual0].stride : 0;
+  p.res1_channels = d.residual1 >= 0 ? tensors[d.residual1].stride : 0;
   L.in = d.in_tensor; L.out = d.out_tensor; L.res0 = d.residual0; L.res1 = d.residual1;
 
   // fold BN, pack [tap][cout_pad][cin_pad]
@@ -232,6 +245,7 @@ int Net::add_pool(int in, int out) {
   const TensorInfo &ti = tensors[in], &to = tensors[out];
   PCLS_REQUIRE(!ti.logits && !to.logits && ti.channels == to.channels && to.width == (ti.width + 1) / 2,
                "pcls_net_maxpool3x3_s2: shape mismatch");
+  tensors[out].stride = tensors[in].stride;   // a padded input (zero pads) pools into a padded output
   PoolLayer L;
   L.in = in; L.out = out;
   L.pad_left = std::max((to.width - 1) * 2 + 3 - ti.width, 0) / 2;
@@ -432,7 +446,7 @@ int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool ra
       if (conv_impl == 0 && L.tc_ok) {
         // the final conv can run the segmentation head in its epilogue (every 32-pixel warp row must be contiguous
         // in memory: full-width tiles of 128 pixels)
-        const bool fuse = fuse_head && L.out == logits_tensor && (W % 128 == 0 || L.hp != nullptr);
+        const bool fuse = L.out == logits_tensor && head_is_fused();
         head_args.head = fuse ? 1 : 0;
         head_args.none_index = none_index; head_args.mask = mask_buf;
         head_args.probs = probs; head_args.preds = preds; head_args.logits = logits;
@@ -449,7 +463,7 @@ int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool ra
     } else if (op.type == OP_POOL) {
       const PoolLayer& L = pools[op.index];
       rc = launch_maxpool3x3_s2<T>((const T*)tensor_ptr(L.in, nb), (T*)tensor_ptr(L.out, nb), nb, H, tensors[L.in].width,
-                                   tensors[L.out].width, tensors[L.in].channels, L.pad_left, s);
+                                   tensors[L.out].width, tensors[L.in].stride, L.pad_left, s);
     } else {
       const CamLayer& L = cams[op.index];
       rc = launch_cam<T>((const T*)tensor_ptr(L.in, nb), (T*)tensor_ptr(L.out, nb), L.p, nb, H, tensors[L.in].width, s);
@@ -523,10 +537,14 @@ int Net::forward(const float* lidar, int channels, const uint8_t* mask, const do
   for (auto& g : graphs) {
     if (!memcmp(&g.key, &key, sizeof(key))) {
       g.stamp = ++graph_clock;
+      graph_misses = 0;
       PCLS_CHECK_CUDA(cudaGraphLaunch(g.exec, s));
       return PCLS_OK;
     }
   }
+  // A caller that hands in fresh buffers on every call (outputs kept alive, so the allocator cannot recycle them) would pay
+  // a stream capture + cudaGraphInstantiate of ~60 nodes per forward: after a few misses in a row run the plain launches.
+  if (++graph_misses > 4) return run_all(lidar, channels, mask, raw, mean5, std5, B, logits, probs, preds, s, nullptr);
   if (!cap_stream) PCLS_CHECK_CUDA(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
   PCLS_CHECK_CUDA(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeRelaxed));
   rc = run_all(lidar, channels, mask, raw, mean5, std5, B, logits, probs, preds, cap_stream, nullptr);
@@ -576,6 +594,13 @@ int Net::profile_ops(const float* lidar, int channels, const uint8_t* mask, cons
   return rc;
 }
 
+bool Net::head_is_fused() const {
+  if (!fuse_head || conv_impl != 0) return false;
+  for (const auto& L : convs)
+    if (L.out == logits_tensor) return L.tc_ok && (W % 128 == 0 || L.hp != nullptr);
+  return false;
+}
+
 int Net::op_info(int i, char* name, int* family, int64_t* flops, int64_t* bytes) const {
   const int n = (int)ops.size() + 2;
   PCLS_REQUIRE(i >= 0 && i < n, "pcls_net_op_info: op index %d out of range", i);
@@ -587,21 +612,26 @@ int Net::op_info(int i, char* name, int* family, int64_t* flops, int64_t* bytes)
     snprintf(buf, sizeof(buf), "input_stage");
     by = HW * (5 * 4 + 16 + 1);
   } else if (i == n - 1) {
-    snprintf(buf, sizeof(buf), "head_softmax_argmax");
-    by = HW * ((int64_t)num_classes * 4 * 2 + 4 + 1);
+    // fused into the epilogue of the logits convolution: that op carries the probability / prediction / mask bytes
+    snprintf(buf, sizeof(buf), head_is_fused() ? "head_softmax_argmax(fused)" : "head_softmax_argmax");
+    by = head_is_fused() ? 0 : HW * ((int64_t)num_classes * 4 * 2 + 4 + 1);
   } else {
     const OpRef& op = ops[i - 1];
     if (op.type == OP_CONV) {
       const ConvLayer& L = convs[op.index];
       const ConvParams& p = L.p;
       const char* mode = p.mode == MODE_1x1 ? "conv1x1" : p.mode == MODE_3x3_S1 ? "conv3x3" : p.mode == MODE_3x3_S2 ? "conv3x3s2" : "deconv1x4s2";
-      snprintf(buf, sizeof(buf), "%s_%dx%d_w%d", mode, p.cin, p.cout, p.Wout);
+      const int64_t cin = L.cin_logical, cout = L.cout_logical;   // algorithmic work: the layer's own channels, not the padding
+      snprintf(buf, sizeof(buf), "%s_%dx%d_w%d", mode, (int)cin, (int)cout, p.Wout);
       const int64_t taps = p.mode == MODE_DECONV ? 2 : p.ntaps;  // 2 of the 4 taps hit each output column
-      fl = 2 * (int64_t)H * p.Wout * p.cin * p.cout * taps;
-      by = (int64_t)H * p.Win * p.cin * 2 + (int64_t)H * p.Wout * p.cout * (p.out_f32 ? 4 : 2) +
-           (int64_t)p.ntaps * p.cin * p.cout * 2;
-      if (L.res0 >= 0) by += (int64_t)H * p.Wout * p.cout * 2;
-      if (L.res1 >= 0) by += (int64_t)H * p.Wout * p.cout * 2;
+      fl = 2 * (int64_t)H * p.Wout * cin * cout * taps;
+      by = (int64_t)H * p.Win * cin * 2 + (int64_t)H * p.Wout * cout * (p.out_f32 ? 4 : 2) +
+           (int64_t)p.ntaps * cin * cout * 2;
+      // logits layer with the head in its epilogue: it writes probabilities (the same NC x 4 bytes) instead of logits,
+      // plus the 4-byte prediction, and reads the mask byte
+      if (L.out == logits_tensor && head_is_fused()) by += (int64_t)H * p.Wout * (4 + 1);
+      if (L.res0 >= 0) by += (int64_t)H * p.Wout * cout * 2;
+      if (L.res1 >= 0) by += (int64_t)H * p.Wout * cout * 2;
       fam = (conv_impl == 0 && L.tc_ok) ? 1 : 0;
     } else if (op.type == OP_POOL) {
       const PoolLayer& L = pools[op.index];
@@ -627,8 +657,8 @@ int Net::read_tensor(int t, int B, float* out, cudaStream_t s) {
   const TensorInfo& ti = tensors[t];
   const int64_t n = (int64_t)B * H * ti.width * ti.channels;
   if (ti.logits) { PCLS_CHECK_CUDA(cudaMemcpyAsync(out, tensor_ptr(t, B), n * 4, cudaMemcpyDeviceToDevice, s)); return PCLS_OK; }
-  return precision == PCLS_F16 ? launch_tensor_to_f32<__half>((const __half*)tensor_ptr(t, B), out, n, s)
-                               : launch_tensor_to_f32<__nv_bfloat16>((const __nv_bfloat16*)tensor_ptr(t, B), out, n, s);
+  return precision == PCLS_F16 ? launch_tensor_to_f32<__half>((const __half*)tensor_ptr(t, B), out, n, ti.channels, ti.stride, s)
+                               : launch_tensor_to_f32<__nv_bfloat16>((const __nv_bfloat16*)tensor_ptr(t, B), out, n, ti.channels, ti.stride, s);
 }
 
 Net::~Net() {
@@ -747,6 +777,11 @@ extern "C" int pcls_net_set_option(pcls_net* net, const char* name, int value) {
     n->keep_tensors = value != 0; return PCLS_OK;
   }
   if (!strcmp(name, "tc_head")) { tc_head_mode = value; return PCLS_OK; }
+  if (!strcmp(name, "tc_nsplit")) { tc_nsplit_mode = value; return PCLS_OK; }
+  if (!strcmp(name, "pad48")) {
+    PCLS_REQUIRE(n->convs.empty(), "pad48 must be set before the first pcls_net_conv");
+    pad48_mode = value; return PCLS_OK;
+  }
   if (!strcmp(name, "tc_halo")) { tc_halo_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_tma_store")) { tc_tma_store_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_group")) { tc_group_mode = value; return PCLS_OK; }

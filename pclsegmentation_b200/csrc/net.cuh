@@ -8,6 +8,7 @@ namespace pcls {
 
 struct TensorInfo {
   int width = 0, channels = 0;
+  int stride = 0;             // channels per pixel in memory (>= channels: 48-channel tensors are padded to 64, see add_conv)
   bool logits = false;
   int first = -1, last = -1;  // op indices of first write / last use
   size_t offset = 0;          // per-frame byte offset inside the arena (scaled by frames_per_pass)
@@ -16,12 +17,14 @@ struct TensorInfo {
 struct TcPlan;    // tcgen05 launch plan of one conv layer (conv_tc.cu)
 struct HeadPlan;  // launch plan of the logits layer + fused segmentation head (conv_head.cu)
 extern int tc_head_mode;
-extern int tc_halo_mode, tc_resident_mode, tc_base_offset_mode, tc_tma_store_mode, tc_group_mode, tc_res_tma_mode, tc_split_mode, tc_vstream_mode;
+extern int tc_halo_mode, tc_resident_mode, tc_base_offset_mode, tc_tma_store_mode, tc_group_mode, tc_res_tma_mode, tc_split_mode, tc_vstream_mode, tc_nsplit_mode;
+extern int pad48_mode;  // 48-channel tensors written by one conv are stored with a 64-channel pixel stride (zero pads)
 extern const int tc_debug_compiled;
 extern unsigned long long* tc_debug_buf;  // A/B measurement switches (process-wide)
 
 struct ConvLayer {
   ConvParams p;
+  int cin_logical = 0, cout_logical = 0;   // the layer's own channel counts (p.cin_pad / p.cout may include tensor padding)
   int in = -1, out = -1, res0 = -1, res1 = -1;
   std::vector<float> w_f32;     // folded, packed [tap][cout_pad][cin_pad]
   std::vector<float> bias_f32;  // folded [cout_pad]
@@ -81,6 +84,7 @@ struct Net {
   int last_B = 0;
   std::vector<CachedGraph> graphs;
   uint64_t graph_clock = 0;
+  int graph_misses = 0;       // consecutive forwards whose argument set was not in the graph cache
   cudaStream_t cap_stream = nullptr;
 
   ~Net();
@@ -102,6 +106,7 @@ struct Net {
   void drop_graphs();
   int profile_ops(const float* lidar, int channels, const uint8_t* mask, const double* mean5, const double* std5, int B,
                   float* logits, float* probs, int32_t* preds, float* h_ms, cudaStream_t s);
+  bool head_is_fused() const;
   int op_info(int i, char* name, int* family, int64_t* flops, int64_t* bytes) const;
   int forward(const float* lidar, int channels, const uint8_t* mask, const double* mean5, const double* std5, int B,
               float* logits, float* probs, int32_t* preds, cudaStream_t s);

@@ -321,8 +321,11 @@ template <int C> struct CamGeom {
   static constexpr int SMEM = NB * ROWB + (2 * (CV / 4) + 1) * TW * 8 * 4;
 };
 
+#ifndef PCLS_CAM_CTAS
+#define PCLS_CAM_CTAS 2   // resident CTAs per SM the register allocation targets (3 needs <= 85 registers: spills, measured slower)
+#endif
 template <typename T, int C>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, PCLS_CAM_CTAS)
 cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int H, int W, int rows_per_seg) {
   using G = CamGeom<C>;
   constexpr int CV = G::CV, TW = G::TW, PITCH = G::PITCH, ROWB = G::ROWB, NB = G::NB, DIST = G::DIST;
@@ -493,7 +496,7 @@ int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, cud
   const int TW = 256 / (p.C / 8);
   // row segments (>= 8 rows each): minimise  waves x iterations per CTA  with two CTAs resident per SM; a segment of n
   // rows runs n + 7 iterations (three rows of halo above / below and the pipeline drain)
-  const int64_t strips = ceil_div(W, TW) * (int64_t)B, slots = (int64_t)sm_count() * 2;
+  const int64_t strips = ceil_div(W, TW) * (int64_t)B, slots = (int64_t)sm_count() * PCLS_CAM_CTAS;
   int segs = 1;
   int64_t best = -1;
   for (int sgs = 1; sgs <= (H >= 8 ? H / 8 : 1); ++sgs) {
@@ -518,20 +521,22 @@ template int launch_cam<__half>(const __half*, __half*, const CamParams&, int, i
 template int launch_cam<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, const CamParams&, int, int, int, cudaStream_t);
 
 // --------------------------------------------------------------------------------------------------
+// n dense output elements [pixels][channels]; the input holds `stride` >= channels values per pixel (padded tensors)
 template <typename T>
-__global__ void tensor_to_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int64_t n) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = to_f32<T>(in[i]);
+__global__ void tensor_to_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int64_t n, int channels, int stride) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
+    out[i] = to_f32<T>(in[channels == stride ? i : (i / channels) * stride + i % channels]);
 }
 template <typename T>
-int launch_tensor_to_f32(const T* in, float* out, int64_t n, cudaStream_t s) {
+int launch_tensor_to_f32(const T* in, float* out, int64_t n, int channels, int stride, cudaStream_t s) {
   if (n == 0) return PCLS_OK;
   int64_t blocks = ceil_div(n, 256);
   if (blocks > 65535) blocks = 65535;
-  tensor_to_f32_kernel<T><<<(int)blocks, 256, 0, s>>>(in, out, n);
+  tensor_to_f32_kernel<T><<<(int)blocks, 256, 0, s>>>(in, out, n, channels, stride);
   return check_launch("tensor_to_f32_kernel");
 }
-template int launch_tensor_to_f32<__half>(const __half*, float*, int64_t, cudaStream_t);
-template int launch_tensor_to_f32<__nv_bfloat16>(const __nv_bfloat16*, float*, int64_t, cudaStream_t);
+template int launch_tensor_to_f32<__half>(const __half*, float*, int64_t, int, int, cudaStream_t);
+template int launch_tensor_to_f32<__nv_bfloat16>(const __nv_bfloat16*, float*, int64_t, int, int, cudaStream_t);
 
 }  // namespace pcls

@@ -65,8 +65,11 @@ class MeanIoU:
     return int(self._dropped.item()) if self._dropped is not None else 0
 
   def allreduce(self, comm):
-    """Sum the matrix over all ranks of ``comm`` (sharding.Communicator), in place, on the current stream."""
+    """Sum the matrix over all ranks of ``comm`` (sharding.Communicator), in place, on the current stream: the int64
+    counts with ONE ncclAllReduce through the C ABI; the float64 matrix of weighted updates (test_step) and the dropped
+    counter, when present on any rank, with ``torch.distributed`` (off the hot path)."""
     comm.allreduce_confusion(self._ensure())
+    comm.allreduce_aux(self)
 
   def result(self):
     """Mean IoU over the classes whose denominator is non-zero (tf.keras.metrics.MeanIoU.result)."""

@@ -68,6 +68,20 @@ class Communicator:
       dist.all_reduce(cm, op=dist.ReduceOp.SUM)
     return cm
 
+  def allreduce_aux(self, metric):
+    """The parts of a MeanIoU that are not the int64 matrix: ``_cmw`` (float64, weighted updates) and ``_dropped``.
+    Ranks agree first on whether anyone holds a weighted matrix (a rank that never saw a weighted update has none)."""
+    if self.world_size == 1:
+      return
+    dev = metric._cm.device
+    has_w = torch.tensor([1 if metric._cmw is not None else 0], dtype=torch.int64, device=dev)
+    dist.all_reduce(has_w, op=dist.ReduceOp.MAX)
+    if int(has_w.item()):
+      if metric._cmw is None:
+        metric._cmw = torch.zeros(tuple(metric._cm.shape), dtype=torch.float64, device=dev)
+      dist.all_reduce(metric._cmw, op=dist.ReduceOp.SUM)
+    dist.all_reduce(metric._dropped, op=dist.ReduceOp.SUM)
+
   def close(self):
     if self._comm is not None:
       _lib.load().pcls_comm_destroy(self._comm)
