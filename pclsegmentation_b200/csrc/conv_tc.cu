@@ -44,8 +44,15 @@ constexpr int TC_MAX_TAPS = 9;
 #ifndef PCLS_TC_VSTREAM
 #define PCLS_TC_VSTREAM 0
 #endif
-constexpr int TC_NG = 2;                        // epilogue warp-groups (4 warps each); tiles are dealt round-robin
-constexpr int TC_THREADS = 64 + 128 * TC_NG;    // warp 0 TMA producer, warp 1 MMA issuer, then the epilogue groups
+// Epilogue warp-groups (4 warps each; tiles are dealt round-robin).  Kernels with residual adds need ~166 registers per
+// thread: two groups (320 threads).  Kernels without (bias pre-loaded, ReLU in the conversion) need ~125 and could run
+// three (448 threads, -DPCLS_TC_NG_NORES=3) - measured slower on SqueezeSegV2 (3.83 vs 3.71 ms): the third group's
+// staging buffers cost the layers with resident weights their pipeline stages.
+#ifndef PCLS_TC_NG_NORES
+#define PCLS_TC_NG_NORES 2
+#endif
+constexpr int tc_ng(bool res) { return res ? 2 : PCLS_TC_NG_NORES; }
+constexpr int tc_threads(bool res) { return 64 + 128 * tc_ng(res); }   // warp 0 TMA producer, warp 1 MMA issuer, then the groups
 
 struct TcParams {
   // tile geometry
@@ -111,18 +118,54 @@ struct TcParams {
   unsigned long long* dbg;    // optional [gridDim.x][16] cycle counters (pcls_net_set_option "tc_debug")
 };
 
-// 8 accumulator columns -> +bias, activation, +residuals -> one 16-byte vector of 16-bit outputs.
-// Activation: ONE instruction per element for ReLU / none - max(v, lo) with lo = 0 / -inf - and two for LeakyReLU(0.1)
-// (max(v, 0.1 v)); LEAKY is a kernel template parameter (the epilogue's instruction count is what bounds the
-// memory-side layers: ncu, 291 instructions per 32-column chunk before this).
-template <typename T, bool LEAKY>
-__device__ __forceinline__ int4 epilogue_vec8(const uint32_t* acc, const float* bias8, float lo, bool has_r0,
-                                              const int4& r0, bool has_r1, const int4& r1) {
-  const float4 b0 = *reinterpret_cast<const float4*>(bias8);
-  const float4 b1 = *reinterpret_cast<const float4*>(bias8 + 4);
-  float v[8] = {__uint_as_float(acc[0]) + b0.x, __uint_as_float(acc[1]) + b0.y, __uint_as_float(acc[2]) + b0.z,
-                __uint_as_float(acc[3]) + b0.w, __uint_as_float(acc[4]) + b1.x, __uint_as_float(acc[5]) + b1.y,
-                __uint_as_float(acc[6]) + b1.z, __uint_as_float(acc[7]) + b1.w};
+// 16-bit pack of two floats with the ReLU fused into the conversion (cvt.rn.relu: exact - rounding is monotonic)
+template <typename T> __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2_relu<__half>(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+template <> __device__ __forceinline__ uint32_t pack2_relu<__nv_bfloat16>(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+// 8 accumulator columns (the bias is already in them: the epilogue pre-loads every TMEM accumulator with the bias row
+// before its MMAs run, see preload_bias) -> activation, +residuals -> one 16-byte vector of 16-bit outputs.
+// Without residuals ReLU rides in the float -> 16-bit conversion: 4 instructions per 8 outputs.  With residuals
+// (added AFTER the activation, in float32): one max per element for ReLU / none (max(v, lo), lo = 0 / -inf), two for
+// LeakyReLU(0.1).  LEAKY is a kernel template parameter: the epilogue's instruction count bounds the memory-side layers.
+template <typename T, bool LEAKY, bool BIAS>
+__device__ __forceinline__ int4 epilogue_vec8(const uint32_t* acc, const float* bias8, float lo, bool has_r0, const int4& r0,
+                                              bool has_r1, const int4& r1) {
+  if constexpr (!BIAS && !LEAKY) {
+    if (!has_r0 && !has_r1) {
+      int4 o;
+      if (lo == 0.0f) {
+        o.x = (int)pack2_relu<T>(__uint_as_float(acc[0]), __uint_as_float(acc[1]));
+        o.y = (int)pack2_relu<T>(__uint_as_float(acc[2]), __uint_as_float(acc[3]));
+        o.z = (int)pack2_relu<T>(__uint_as_float(acc[4]), __uint_as_float(acc[5]));
+        o.w = (int)pack2_relu<T>(__uint_as_float(acc[6]), __uint_as_float(acc[7]));
+      } else {
+        const float f[8] = {__uint_as_float(acc[0]), __uint_as_float(acc[1]), __uint_as_float(acc[2]), __uint_as_float(acc[3]),
+                            __uint_as_float(acc[4]), __uint_as_float(acc[5]), __uint_as_float(acc[6]), __uint_as_float(acc[7])};
+        o = pack8<T>(f);
+      }
+      return o;
+    }
+  }
+  float v[8];
+  if constexpr (BIAS) {   // (kernels with residuals: the bias is added here, not pre-loaded)
+    const float4 b0 = *reinterpret_cast<const float4*>(bias8);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias8 + 4);
+    v[0] = __uint_as_float(acc[0]) + b0.x; v[1] = __uint_as_float(acc[1]) + b0.y; v[2] = __uint_as_float(acc[2]) + b0.z;
+    v[3] = __uint_as_float(acc[3]) + b0.w; v[4] = __uint_as_float(acc[4]) + b1.x; v[5] = __uint_as_float(acc[5]) + b1.y;
+    v[6] = __uint_as_float(acc[6]) + b1.z; v[7] = __uint_as_float(acc[7]) + b1.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[j]);
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = LEAKY ? fmaxf(v[j], v[j] * 0.1f) : fmaxf(v[j], lo);
   if (has_r0) {
@@ -140,12 +183,13 @@ __device__ __forceinline__ int4 epilogue_vec8(const uint32_t* acc, const float* 
   return pack8<T>(v);
 }
 
-
 template <typename T, int KC, int SUB, int G, bool RES, bool LEAKY>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(tc_threads(RES), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
                const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ TcParams p, const int num_tiles) {
+  constexpr bool PRELOAD = !RES;   // bias pre-loaded into the TMEM accumulators (see preload_bias)
+  constexpr int TC_NG = tc_ng(RES);
   extern __shared__ uint8_t smem_raw[];
   // carve: [stages x (A tile | B tiles)] 1024-aligned, resident weights, barriers, TMEM base slot, bias
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -317,11 +361,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       };
       for (int seq = 0; seq < my_tiles; ++seq) {
         const int tile = blockIdx.x + seq * gridDim.x;   // (only the transposed-conv phase below reads it; not vstream)
-        { DBG_T0; mbar_wait(TEMPTY_BAR(acc), acc_phase ^ 1u); DBG_ADD(1); }  // epilogue has drained this accumulator
+        { DBG_T0; mbar_wait(TEMPTY_BAR(acc), PRELOAD ? acc_phase : (acc_phase ^ 1u)); DBG_ADD(1); }  // the epilogue has drained this accumulator and pre-loaded the bias row
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)BN;
         uint32_t b_res = bres_base + (n_phase > 1 ? (uint32_t)((tile / n_nt) % n_phase) * bres_phase_bytes : 0u);
-        uint32_t accumulate = 0u, acc_lo = 0u;
+        uint32_t accumulate = PRELOAD ? 1u : 0u, acc_lo = accumulate;   // PRELOAD: the accumulator starts from the bias row
         int kc_i = 0, g_i = 0;   // K chunk and A-load group of iteration k
         for (int k = 0; k < k_iters; ++k) {
           uint32_t a_addr;
@@ -397,7 +441,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < CIN / 16; ++j)
                   umma_f16_elect(d_tmem + (uint32_t)pp * cout_blk, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j),
-                           idesc_blk, (k | u | j) != 0 ? 1u : 0u);
+                           idesc_blk, (PRELOAD || (k | u | j) != 0) ? 1u : 0u);
               }
             }
           }
@@ -475,6 +519,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     };
     if (RES && p.res_tma != 0 && has_r0 && issuer && (uint32_t)grp < ng && tile_at((uint32_t)grp) >= 0)
       issue_res(tile_at((uint32_t)grp), 0, 0u);
+    // Bias through the accumulator (kernels without residuals): before an accumulator's MMAs start, its rows are pre-loaded with the bias row of
+    // the tile that will use it (tcgen05.st, 4x the TMEM read rate; every MMA then accumulates).  This takes the bias
+    // add - one FADD per output element plus the shared-memory reads of the bias - out of the epilogue's inner loop.
+    // Done by the group that owns the accumulator: once up front, then right after draining it, for the tile n_acc later.
+    // (Measured: the residual kernels - epilogue-bound, 166 registers - lose 9 % with it, interleaved with the chunk reads
+    // or not; they keep the bias add in the epilogue.)
+    auto preload_bias = [&](uint32_t a, int tile_next) {
+      if (tile_next >= 0) {
+        const float* bsrc = bias_s + (tile_next % n_nt) * BN;
+        const uint32_t t_dst = tmem_base + ((uint32_t)(q * 32) << 16) + a * (uint32_t)BN;
+#pragma unroll 1
+        for (int c = 0; c + 32 <= BN; c += 32) {
+          uint32_t bv[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(bsrc + c + j);
+            bv[j] = __float_as_uint(t4.x); bv[j + 1] = __float_as_uint(t4.y); bv[j + 2] = __float_as_uint(t4.z); bv[j + 3] = __float_as_uint(t4.w);
+          }
+          tmem_st32(t_dst + (uint32_t)c, bv);
+        }
+        if (BN & 16) {
+          uint32_t bv[16];
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(bsrc + (BN & ~31) + j);
+            bv[j] = __float_as_uint(t4.x); bv[j + 1] = __float_as_uint(t4.y); bv[j + 2] = __float_as_uint(t4.z); bv[j + 3] = __float_as_uint(t4.w);
+          }
+          tmem_st16(t_dst + (uint32_t)(BN & ~31), bv);
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(TEMPTY_BAR(a));
+    };
+    if (PRELOAD && (uint32_t)grp < ng)
+      for (uint32_t a = (uint32_t)grp; a < n_acc; a += ng) preload_bias(a, tile_at(a));
     for (; (uint32_t)grp < ng; ++tl) {
       const int tile = tile_at(tl);
       if (tile < 0) break;
@@ -562,7 +643,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             r0v = res_tma ? ld_shared_v4(res_row + (uint32_t)(((((cc & 63) >> 3) + g) ^ (m & 7)) << 4))
                 : res_smem ? ld_shared_v4(rslot + (uint32_t)(((cc & 63) >> 3) + g) * 2048u) : r0[g];
           }
-          sink(g, epilogue_vec8<T, LEAKY>(v + g * 8, bias_s + n0 + cc + g * 8, act_lo, RES && has_r0, r0v, RES && has_r1, r1[g]));
+          sink(g, epilogue_vec8<T, LEAKY, !PRELOAD>(v + g * 8, bias_s + n0 + cc + g * 8, act_lo, RES && has_r0, r0v, RES && has_r1, r1[g]));
         }
         if (reg_res && cc + 32 < BN) load_r1(cc + 32);
       };
@@ -589,7 +670,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (c4 < cout) {
 #pragma unroll
               for (int j = c4; j < c4 + 4; ++j) {
-                const float x = __uint_as_float(v[j]) + bias_s[n0 + j];
+                const float x = __uint_as_float(v[j]) + (PRELOAD ? 0.0f : bias_s[n0 + j]);   // (PRELOAD: the bias is in the accumulator)
                 lg[j] = (j < cout) ? fmaxf(x, x * slope) : -INFINITY;
               }
             }
@@ -712,9 +793,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (off >= 0) *reinterpret_cast<int4*>(outp + off) = o;
           });
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(TEMPTY_BAR(acc));
+      if constexpr (PRELOAD) {
+        preload_bias(acc, tile_at(tl + n_acc));   // (+ hands the accumulator back to the MMA issuer)
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(TEMPTY_BAR(acc));
+      }
       if (dbg) { dbg_acc[6] += clk() - _te; dbg_acc[7] += 1; }
     }
     if (p.tma_store && q == 2 && lane == 0) bulk_wait_all();  // smem must outlive the last stores
@@ -831,6 +916,7 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
     TcPlan* plan = new TcPlan();
     memset(plan, 0, sizeof(TcPlan));
     TcParams& q = plan->prm;
+    const int TC_NG = tc_ng(L.res0 >= 0 || L.res1 >= 0);   // epilogue groups of the kernel this layer will run
     const bool bf16 = precision == PCLS_BF16;
     // K chunk / swizzle: the widest of 64/32/16 channels that divides cin_pad
     q.KC = (cp.cin_pad % 64 == 0) ? 64 : (cp.cin_pad % 32 == 0) ? 32 : 16;
@@ -1185,7 +1271,7 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
   }
   int grid = work < sm_count() ? work : sm_count();
   if (prm.nsplit) grid -= grid % prm.n_nt;   // every CTA sees one N tile only (tile % n_nt == blockIdx.x % n_nt)
-  tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0, prm.act == PCLS_ACT_LEAKY ? 1 : 0)<<<grid, TC_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, plan->map_r, plan->map_b2, prm, num_tiles);
+  tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0, prm.act == PCLS_ACT_LEAKY ? 1 : 0)<<<grid, tc_threads(prm.res0 || prm.res1), plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, plan->map_r, plan->map_b2, prm, num_tiles);
   return check_launch("conv_tc_kernel");
 }
 
