@@ -291,6 +291,7 @@ void Net::op_tensors(const OpRef& op, std::vector<int>& reads, std::vector<int>&
   if (op.type == OP_CONV) {
     const ConvLayer& L = convs[op.index];
     reads.push_back(L.in);
+    if (L.pool_src >= 0) reads.push_back(L.pool_src);   // (fused max-pool: the un-pooled tensor is what the kernel reads)
     if (L.res0 >= 0) reads.push_back(L.res0);
     if (L.res1 >= 0) reads.push_back(L.res1);
     writes.push_back(L.out);
@@ -311,8 +312,29 @@ int Net::finalize(int logits_tensor_, int num_classes_, int none_index_) {
   PCLS_REQUIRE(none_index_ >= 0 && none_index_ < num_classes_, "pcls_net_finalize: none_index out of range");
   logits_tensor = logits_tensor_; num_classes = num_classes_; none_index = none_index_;
 
-  // liveness: first write .. last read (op order); the logits tensor lives to the end (head reads it)
+  // max-pool + 1x1 conv fusion (pool_conv.cu): a pool whose output has ONE reader, the 1x1 convolution right behind it
   const int n_ops = (int)ops.size();
+  if (fuse_pool)
+    for (int i = 0; i + 1 < n_ops; ++i) {
+      if (ops[i].type != OP_POOL || ops[i + 1].type != OP_CONV) continue;
+      PoolLayer& P = pools[ops[i].index];
+      ConvLayer& L = convs[ops[i + 1].index];
+      const ConvParams& cp = L.p;
+      if (L.in != P.out || cp.mode != MODE_1x1 || L.res0 >= 0 || L.res1 >= 0 || cp.out_f32 || cp.out_coff != 0) continue;
+      if (tensors[P.in].stride != tensors[P.in].channels || cp.cin_pad != tensors[P.in].channels) continue;
+      if (!pool_conv1x1_supported(tensors[P.in].channels, (L.cout_logical + 15) / 16 * 16) || cp.cout != cp.cout_pad) continue;
+      bool other_reader = false;
+      std::vector<int> rd, wr;
+      for (int k = 0; k < n_ops; ++k) {
+        if (k == i + 1) continue;
+        op_tensors(ops[k], rd, wr);
+        for (int r : rd) other_reader = other_reader || r == P.out;
+      }
+      if (other_reader) continue;
+      P.fused_conv = ops[i + 1].index;
+      L.pool_src = P.in; L.pool_pad_left = P.pad_left;
+    }
+  // liveness: first write .. last read (op order); the logits tensor lives to the end (head reads it)
   std::vector<int> reads, writes;
   for (auto& t : tensors) { t.first = -1; t.last = -1; }
   tensors[0].first = -1; tensors[0].last = -1;  // input: written by the input kernel before op 0
@@ -443,7 +465,16 @@ int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool ra
       p.out = (L.out == logits_tensor) ? (void*)logits_buf : tensor_ptr(L.out, nb);
       p.res0 = L.res0 >= 0 ? tensor_ptr(L.res0, nb) : nullptr;
       p.res1 = L.res1 >= 0 ? tensor_ptr(L.res1, nb) : nullptr;
-      if (conv_impl == 0 && L.tc_ok) {
+      if (conv_impl == 0 && L.pool_src >= 0) {
+        PoolConvParams pc;
+        pc.in = tensor_ptr(L.pool_src, nb); pc.out = p.out; pc.w = p.w; pc.bias = p.bias;
+        pc.H = H; pc.Win = tensors[L.pool_src].width; pc.Wout = p.Wout; pc.out_channels = p.out_channels;
+        pc.w_stride = p.cin_pad; pc.pad_left = L.pool_pad_left; pc.act = p.act; pc.n_strips = 0; pc.tiles_per_row = 0;
+        // (a 48 -> 64 padded output: contract the real 48 channels, write the pads as zeros)
+        const int S_real = (L.cout_logical + 15) / 16 * 16;
+        pc.zero_to = S_real < p.cout ? p.cout : 0;
+        rc = launch_pool_conv1x1<T>(pc, tensors[L.pool_src].channels, S_real, nb, s);
+      } else if (conv_impl == 0 && L.tc_ok) {
         // the final conv can run the segmentation head in its epilogue (every 32-pixel warp row must be contiguous
         // in memory: full-width tiles of 128 pixels)
         const bool fuse = L.out == logits_tensor && head_is_fused();
@@ -462,6 +493,7 @@ int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool ra
       else rc = launch_conv_direct<T>(p, nb, s);
     } else if (op.type == OP_POOL) {
       const PoolLayer& L = pools[op.index];
+      if (conv_impl == 0 && L.fused_conv >= 0) continue;   // pooled on the fly by the 1x1 conv behind it
       rc = launch_maxpool3x3_s2<T>((const T*)tensor_ptr(L.in, nb), (T*)tensor_ptr(L.out, nb), nb, H, tensors[L.in].width,
                                    tensors[L.out].width, tensors[L.in].stride, L.pad_left, s);
     } else {
@@ -630,13 +662,18 @@ int Net::op_info(int i, char* name, int* family, int64_t* flops, int64_t* bytes)
       // logits layer with the head in its epilogue: it writes probabilities (the same NC x 4 bytes) instead of logits,
       // plus the 4-byte prediction, and reads the mask byte
       if (L.out == logits_tensor && head_is_fused()) by += (int64_t)H * p.Wout * (4 + 1);
+      if (conv_impl == 0 && L.pool_src >= 0) {   // max-pool fused in: the kernel reads the un-pooled tensor instead of the pooled one
+        by += (int64_t)H * (tensors[L.pool_src].width - p.Win) * cin * 2;
+        snprintf(buf, sizeof(buf), "pool+%s_%dx%d_w%d", mode, (int)cin, (int)cout, p.Wout);
+      }
       if (L.res0 >= 0) by += (int64_t)H * p.Wout * cout * 2;
       if (L.res1 >= 0) by += (int64_t)H * p.Wout * cout * 2;
       fam = (conv_impl == 0 && L.tc_ok) ? 1 : 0;
     } else if (op.type == OP_POOL) {
       const PoolLayer& L = pools[op.index];
-      snprintf(buf, sizeof(buf), "maxpool3x3s2_c%d_w%d", tensors[L.in].channels, tensors[L.out].width);
-      by = (int64_t)H * (tensors[L.in].width + tensors[L.out].width) * tensors[L.in].channels * 2;
+      const bool fused = conv_impl == 0 && L.fused_conv >= 0;
+      snprintf(buf, sizeof(buf), fused ? "maxpool3x3s2_c%d_w%d(fused)" : "maxpool3x3s2_c%d_w%d", tensors[L.in].channels, tensors[L.out].width);
+      by = fused ? 0 : (int64_t)H * (tensors[L.in].width + tensors[L.out].width) * tensors[L.in].channels * 2;
     } else {
       const CamLayer& L = cams[op.index];
       snprintf(buf, sizeof(buf), "cam_c%d_w%d", L.C, tensors[L.in].width);
@@ -788,6 +825,10 @@ extern "C" int pcls_net_set_option(pcls_net* net, const char* name, int value) {
   if (!strcmp(name, "tc_res_tma")) { tc_res_tma_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_split")) { tc_split_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_vstream")) { tc_vstream_mode = value; return PCLS_OK; }
+  if (!strcmp(name, "fuse_pool")) {
+    PCLS_REQUIRE(!n->finalized, "fuse_pool must be set before pcls_net_finalize");
+    n->fuse_pool = value != 0; return PCLS_OK;
+  }
   if (!strcmp(name, "fuse_head")) { n->fuse_head = value != 0; n->drop_graphs(); return PCLS_OK; }
   if (!strcmp(name, "tc_debug")) {  // per-role wait-cycle counters of conv_tc_kernel (development aid)
     PCLS_REQUIRE(!value || tc_debug_compiled, "tc_debug needs a library built with PCLS_NVCC_FLAGS=-DPCLS_TC_DEBUG=1");

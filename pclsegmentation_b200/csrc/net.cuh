@@ -31,6 +31,7 @@ struct ConvLayer {
   bool tc_ok = false;
   TcPlan* tc = nullptr;
   HeadPlan* hp = nullptr;
+  int pool_src = -1, pool_pad_left = 0;   // >= 0: this 1x1 conv reads tensor pool_src through a fused 3x3/s2 max-pool
   // Pixel-pair view for the convolutions that read the 8-channel network input (tensor-core path only):
   // [B,H,W,8] is viewed as [B,H,W/2,16]; `ptc` / `w_tc` / `bias_tc` describe the equivalent convolution on pairs.
   bool pair_view = false;
@@ -40,7 +41,7 @@ struct ConvLayer {
   float* bias_tc_dev = nullptr;
 };
 
-struct PoolLayer { int in, out, pad_left; };
+struct PoolLayer { int in, out, pad_left; int fused_conv = -1; /* index of the 1x1 conv that pools on the fly (pool_conv.cu), -1: own kernel */ };
 
 struct CamLayer {
   int in, out, C, R;
@@ -70,6 +71,7 @@ struct Net {
   // execution knobs
   int conv_impl = 0;
   bool use_graph = true;
+  bool fuse_pool = true;   // max-pool + the squeeze 1x1 conv that consumes it as one kernel (pool_conv.cu)
   bool fuse_head = true;   // run softmax/argmax/mask in the epilogue of the final convolution (tcgen05 path)
   struct HeadArgs { int head = 0, none_index = 0; const uint8_t* mask = nullptr; float* probs = nullptr; int32_t* preds = nullptr; float* logits = nullptr; } head_args;
   int micro_batch = 0;

@@ -42,6 +42,18 @@ template <typename T> int launch_net_input(const float* lidar, int channels, con
 template <typename T> int launch_maxpool3x3_s2(const T* in, T* out, int B, int H, int Win, int Wout, int C,
                                                int pad_left, cudaStream_t s);
 
+// max-pool 3x3 / s[1,2] fused with the 1x1 conv that consumes it (pool_conv.cu)
+struct PoolConvParams {
+  const void* in;      // T [B,H,Win,C]
+  void* out;           // T [B,H,Wout,out_channels], channels [0,S) written
+  const void* w;       // T [S][w_stride] folded 1x1 weights (K-major), channels >= C are not read
+  const float* bias;   // [S]
+  int H, Win, Wout, out_channels, w_stride, pad_left, act, n_strips, tiles_per_row;
+  int zero_to;         // channels [S, zero_to) of the output are written as zeros (padded output tensors), 0: none
+};
+bool pool_conv1x1_supported(int C, int S);
+template <typename T> int launch_pool_conv1x1(const PoolConvParams& p, int C, int S, int B, cudaStream_t s);
+
 struct CamParams {
   int C, R;            // channels, reduced channels (C / 16)
   const float* w1;     // [C][R]   folded squeeze weights

@@ -270,6 +270,37 @@ def test_cam_and_pool(C, W):
   assert np.array_equal(got, _nhwc(O.max_pool_same(_nchw(ycam), 3, (1, 2))))   # the max-pool is exact on its own input
 
 
+@pytest.mark.parametrize("C,S,W,H", [(64, 16, 256, 9), (128, 32, 96, 20), (256, 48, 70, 5), (64, 16, 33, 3)])
+def test_maxpool_fused_into_squeeze_conv(C, S, W, H):
+  """pool_conv1x1_kernel: tf.nn.max_pool2d(3, [1,2], SAME) + the squeeze 1x1 conv behind it as one kernel (the pooled
+  tensor never reaches memory).  Shapes of pool1 / pool3 / pool5 -> fire2 / fire4 / fire6 squeeze, even and odd widths,
+  row segments; checked against the error model on the exact max-pool of the device's own input tensor, and against the
+  un-fused path (fuse_pool = 0), which must give bit-identical results."""
+  rng = np.random.default_rng(C + S + W)
+  B = 2
+  t = TinyNet(H, W)
+  g = t.g
+  a = L.relu(L.BatchNormalization("b0")(L.Conv2D("c0", C, 3)(g.input)))
+  pooled = L.max_pool2d(a)
+  sq = L.relu(L.BatchNormalization("b1")(L.Conv2D("c1", S, 1)(pooled)))
+  out = L.relu(L.BatchNormalization("b2")(L.Conv2D("c2", 32, 1)(sq)))    # a consumer (reads the 48 -> 64 padded tensor too)
+  _rand_vars(g, rng)
+  x = _input(rng, B, H, W)
+  p = _tp(g)
+  got = t.run(out, B, x, 0, keep=[a, sq])
+  ya, ysq = t.kept
+  ypool = _nhwc(O.max_pool_same(_nchw(ya), 3, (1, 2)))
+  _check_layer(ypool, ysq, p, "c1", "b1", act="relu", what="max-pool + squeeze %d -> %d" % (C, S))
+  _check_layer(ysq, got, p, "c2", "b2", act="relu", what="consumer of the squeeze output")
+  os.environ["PCLS_TEST_OPTS"] = "fuse_pool=0"
+  try:
+    got2 = t.run(out, B, x, 0, keep=[sq])
+  finally:
+    del os.environ["PCLS_TEST_OPTS"]
+  _check_layer(ypool, t.kept[0], p, "c1", "b1", act="relu", what="un-fused reference path")
+  assert np.abs(got2 - got).max() < 2e-2
+
+
 def _report(name, cfg, H, W, B, impl, err, lmax, agree, agree_decidable):
   """Appends the measured parity numbers to gpurun_out/parity_report.jsonl (quoted in DESIGN.md)."""
   import json
