@@ -123,6 +123,12 @@ int pcls_input_stage(const float* sample, int channels, int64_t n_pixels, const 
  * on the host.  in: n doubles (16-byte aligned), out: n floats. */
 int pcls_cast_f64_f32(const double* in, float* out, int64_t n, pcls_stream stream);
 
+/* nuScenes LiDAR records on the device: `rec5` [n,5] f32 (x, y, z, intensity, ring index - the 5-float .bin record of
+ * dataset_convert/laserscan_nuscenes.py:27-28, split at :139-145) -> `points4` [n,4] f32 (x,y,z,remission, 16-byte aligned),
+ * the layout pcls_project_scatter reads, and `ring` [n] i32 (= astype(np.int32); may be NULL).  KITTI .bin files are
+ * already [n,4] records and need no unpacking. */
+int pcls_unpack_xyzir(const float* rec5, int64_t n, float* points4, int32_t* ring, pcls_stream stream);
+
 /* Replaces tf.keras.metrics.MeanIoU.update_state (eval.py:41,48; tf.math.confusion_matrix +
  * assign_add): cm[label, pred] += 1 for every pixel (rows = label, cols = prediction).
  *   cm [NC*NC] i64 accumulated in place (the caller zeroes it once).  Pairs outside [0,NC) are an

@@ -41,6 +41,7 @@ SIGNATURES = {
                                    c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
   "pcls_head": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
   "pcls_cast_f64_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+  "pcls_unpack_xyzir": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
   "pcls_input_stage": (c_int, [c_void_p, c_int, c_int64, POINTER(c_double), POINTER(c_double), c_int, c_void_p,
                                c_void_p, c_void_p, POINTER(c_double), c_int, c_void_p, c_void_p]),
   "pcls_confusion_update": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),

@@ -57,7 +57,32 @@ cast_f64_f32_kernel(const double2* __restrict__ in, float2* __restrict__ out, in
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out1[n - 1] = (float)in1[n - 1];
 }
 
+// nuScenes LiDAR records (x, y, z, intensity, ring index: five float32 per point, laserscan_nuscenes.py:27-28, :139-145)
+// -> the [n,4] (x,y,z,remission) point array the projection reads + the int32 ring index (astype(np.int32): truncation).
+__global__ void __launch_bounds__(256)
+unpack_xyzir_kernel(const float* __restrict__ rec5, int64_t n, float4* __restrict__ points4, int32_t* __restrict__ ring) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float* r = rec5 + i * 5;
+    points4[i] = make_float4(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3));
+    if (ring) ring[i] = (int32_t)__ldg(r + 4);
+  }
+}
+
 }  // namespace pcls
+
+extern "C" int pcls_unpack_xyzir(const float* rec5, int64_t n, float* points4, int32_t* ring, pcls_stream stream) {
+  using namespace pcls;
+  PCLS_REQUIRE(n >= 0, "pcls_unpack_xyzir: negative n");
+  if (n == 0) return PCLS_OK;
+  PCLS_REQUIRE(rec5 != nullptr && points4 != nullptr, "pcls_unpack_xyzir: NULL buffer");
+  PCLS_REQUIRE(((uintptr_t)points4 & 15) == 0, "pcls_unpack_xyzir: points4 must be 16-byte aligned");
+  int64_t blocks = ceil_div(n, 256);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  unpack_xyzir_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(rec5, n, reinterpret_cast<float4*>(points4), ring);
+  return check_launch("unpack_xyzir_kernel");
+}
 
 extern "C" int pcls_cast_f64_f32(const double* in, float* out, int64_t n, pcls_stream stream) {
   using namespace pcls;

@@ -235,6 +235,18 @@ class PCLSegmentationNetwork:
     ready.record(torch.cuda.current_stream())
     return wrap(res["probabilities"], ready), wrap(res["predictions"], ready)
 
+  def predict_raw(self, samples):
+    """The per-sample body of inference.py (:47-78) for a batch, in one call: ``samples`` [B,H,W,5|6] RAW range images
+    (x, y, z, intensity, depth[, label]) as the converters store them (numpy float32 / float64 or a CUDA tensor) ->
+    ``(probabilities, predictions)``.  The mask / normalise / zero-fill stage runs on the device inside the forward, so
+    the host ships 20 bytes per pixel (5 float32 channels) instead of the 25 of the normalised [B,H,W,6] input + mask."""
+    from ..device import samples_to_device
+    x = samples_to_device(samples, self._pinned, "raw")
+    res = self.forward_device(x, None, mean=self.mc.INPUT_MEAN, std=self.mc.INPUT_STD)
+    ready = torch.cuda.Event()
+    ready.record(torch.cuda.current_stream())
+    return wrap(res["probabilities"], ready), wrap(res["predictions"], ready)
+
   def predict_step(self, data):
     (lidar_input, lidar_mask), _, _ = data
     return self([lidar_input, lidar_mask], training=False)
