@@ -311,13 +311,16 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+#ifndef PCLS_CAM_DIST
+#define PCLS_CAM_DIST 3
+#endif
 template <int C> struct CamGeom {
   static constexpr int CV = C / 8;              // 16-byte vectors per pixel (8 or 16)
   static constexpr int TW = 256 / CV;           // columns per CTA (32 or 16)
   static constexpr int PITCH = C * 2 + 64;      // bytes per ring pixel; = 64 mod 128: the (pixel, 4 vectors) reads of a
                                                 // quarter warp (2 pixels x 64 bytes) fall on disjoint banks
   static constexpr int ROWB = (TW + 6) * PITCH; // bytes per ring slot
-  static constexpr int NB = 9, DIST = 3;        // ring: rows r-5 .. r+3 resident
+  static constexpr int DIST = PCLS_CAM_DIST, NB = DIST + 6;   // ring: rows r-5 .. r+DIST resident (DIST rows of loads in flight)
   static constexpr int SMEM = NB * ROWB + (2 * (CV / 4) + 1) * TW * 8 * 4;
 };
 
@@ -467,7 +470,7 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
           sv.x += part.x; sv.y += part.y;
         }
         uint32_t sa[4] = {pack2<T>(fmaxf(sv.x, 0.0f), fmaxf(sv.y, 0.0f)), 0u, 0u, 0u};
-        const int sb = sc + 5 >= NB ? sc + 5 - NB : sc + 5;                // ring slot of input row r - 4
+        const int sb = sc + NB - 4 >= NB ? sc - 4 : sc + NB - 4;           // ring slot of input row r - 4
         const int4 xv = *reinterpret_cast<const int4*>(ring + sb * ROWB + a_off + 3 * PITCH);
         const uint32_t xw[4] = {(uint32_t)xv.x, (uint32_t)xv.y, (uint32_t)xv.z, (uint32_t)xv.w};
         uint32_t o[4];
@@ -488,6 +491,176 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
   }
 }
 
+// ---- two pixels per thread --------------------------------------------------------------------------------------------
+// Same algorithm and shared-memory layout as cam_kernel, but a thread owns TWO horizontally adjacent pixels x 8 channels
+// (CTA = 128 threads over the same TW-column strip).  ncu on cam_kernel: the LSU data pipe (shared-memory wavefronts) is
+// the busiest unit (64 %), 7 of its LDS.128 per pixel go to the horizontal 7-max; adjacent pixels share six of their seven
+// columns, so the pair needs 8 loads instead of 14, and the squeeze / excitation MMAs (m16n8k16) carry the second pixel in
+// fragment rows 8-15 that were idle: half the MMAs, address arithmetic and loop overhead per pixel.  Needs ~150 registers:
+// three 128-thread CTAs per SM.
+template <typename T, int C>
+__global__ void __launch_bounds__(128, 3)
+cam2_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int H, int W, int rows_per_seg) {
+  using G = CamGeom<C>;
+  constexpr int CV = G::CV, TW = G::TW, PITCH = G::PITCH, ROWB = G::ROWB, NB = G::NB, DIST = G::DIST;
+  constexpr int R = C / 16;
+  constexpr int NSTG = (TW + 6) * CV;
+  constexpr int LPT = (NSTG + 127) / 128;
+  constexpr int CVG = CV / 4;
+  constexpr int STILE = TW * 8 * 4;
+  extern __shared__ int4 cam_smem[];
+  unsigned char* const ring = reinterpret_cast<unsigned char*>(cam_smem);
+  unsigned char* const St = ring + NB * ROWB;
+
+  const int w0 = blockIdx.x * TW;
+  const int64_t b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int cvg = warp % CVG, pg = warp / CVG;
+  const int c0 = pg * 16 + 2 * g, cv = cvg * 4 + t;      // this thread's pixels c0, c0 + 1 (columns of the strip) and channel vector
+  const int4 NEG = neg_inf8<T>();
+  const int64_t rowv = (int64_t)W * CV;
+
+  uint32_t w1f[2][2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int ch = cv * 8 + 4 * u;
+    auto w1 = [&](int k) { return g < R ? p.w1[(ch + k) * R + g] : 0.0f; };
+    w1f[u][0] = pack2<T>(w1(0), w1(1));
+    w1f[u][1] = pack2<T>(w1(2), w1(3));
+  }
+  constexpr float NL2E = -1.4426950408889634f;
+  uint32_t w2f[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int chn = (cvg * 4 + (g >> 1)) * 8 + 2 * q + (g & 1);
+    auto w2 = [&](int j) { return j < R ? NL2E * p.w2[j * C + chn] : 0.0f; };
+    w2f[q] = pack2<T>(w2(2 * t), w2(2 * t + 1));
+  }
+  uint32_t w2b;
+  {
+    const float bias = NL2E * p.b2[(cvg * 4 + (g >> 1)) * 8 + 2 * t + (g & 1)];
+    const float hi = to_f32<T>(from_f32<T>(bias));
+    w2b = pack2<T>(hi, bias - hi);
+  }
+  const uint32_t one2 = pack2<T>(1.0f, 1.0f);
+
+  const int4* const fin = in + b * H * rowv;
+  int4* const fout = out + b * H * rowv;
+  unsigned sptr = (unsigned)((w0 - 3 + (int)threadIdx.x / CV) * CV + threadIdx.x % CV);
+  const unsigned soff = (unsigned)__cvta_generic_to_shared(ring) + (threadIdx.x / CV) * PITCH + (threadIdx.x % CV) * 16;
+  bool sok[LPT];
+#pragma unroll
+  for (int k = 0; k < LPT; ++k) {
+    const int i = threadIdx.x + k * 128;
+    const int col = w0 - 3 + i / CV;
+    sok[k] = i < NSTG && col >= 0 && col < W;
+    if (i < NSTG && !sok[k])
+      for (int sl = 0; sl < NB; ++sl) *reinterpret_cast<int4*>(ring + sl * ROWB + (i / CV) * PITCH + (i % CV) * 16) = NEG;
+  }
+  for (int i = threadIdx.x; i < TW * 8; i += 128)
+    reinterpret_cast<float*>(St + 2 * CVG * STILE)[i] = (i % 8) < R ? p.b1[i % 8] : 0.0f;
+  const int h0 = blockIdx.z * rows_per_seg, h1 = min(H, h0 + rows_per_seg);
+  const int a0 = h0 - 3 < 0 ? 0 : h0 - 3;
+  sptr += (unsigned)a0 * (unsigned)rowv;
+  auto stage_row = [&](int r, int slot) {
+    if (r < H && r <= h1 + 2) {
+#pragma unroll
+      for (int k = 0; k < LPT; ++k)
+        if (sok[k])
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(soff + k * (128 / CV) * PITCH + slot * ROWB),
+                       "l"(fin + (unsigned)(sptr + k * 128)) : "memory");
+      sptr += (unsigned)rowv;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const unsigned a_off = c0 * PITCH + cv * 16;            // ring: pixel c0 - 3 (+ d * PITCH), this vector
+  const unsigned s_off = (c0 * 8 + 2 * t) * 4;            // squeeze tile: pixel c0, columns 2t, 2t+1 (pixel c0 + 1: + 32 bytes)
+  const bool ok0 = (w0 + c0) < W, ok1 = (w0 + c0 + 1) < W;
+  unsigned optr = (unsigned)((w0 + c0) * CV + cv) + (unsigned)h0 * (unsigned)rowv;
+
+  int4 win0[7], win1[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) { win0[k] = NEG; win1[k] = NEG; }
+
+  for (int r = 0; r < DIST; ++r) stage_row(a0 + r, r);
+  int sc = 0;
+  for (int r0 = a0; r0 < h1 + 4; r0 += 7) {
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int r = r0 + j;
+      if (r >= h1 + 4) break;
+      stage_row(r + DIST, sc + DIST >= NB ? sc + DIST - NB : sc + DIST);
+      asm volatile("cp.async.wait_group %0;" ::"n"(DIST) : "memory");
+      __syncthreads();
+
+      // ---------------- phase A: pooled row r - 3 of both pixels, squeeze partial sums -> tiles [r & 1] ----------------
+      if (r < h1 + 3) {
+        int4 hm0 = NEG, hm1 = NEG;
+        if (r < H) {
+          const unsigned char* src = ring + sc * ROWB + a_off;
+          int4 m6 = *reinterpret_cast<const int4*>(src + PITCH);                     // columns shared by both windows
+#pragma unroll
+          for (int d = 2; d < 7; ++d) m6 = max8<T>(m6, *reinterpret_cast<const int4*>(src + d * PITCH));
+          hm0 = max8<T>(m6, *reinterpret_cast<const int4*>(src));
+          hm1 = max8<T>(m6, *reinterpret_cast<const int4*>(src + 7 * PITCH));
+        }
+        win0[j] = hm0; win1[j] = hm1;
+        if (r >= h0 + 3) {
+          int4 vm0 = win0[0], vm1 = win1[0];
+#pragma unroll
+          for (int k = 1; k < 7; ++k) { vm0 = max8<T>(vm0, win0[k]); vm1 = max8<T>(vm1, win1[k]); }
+          float sq[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // rows g / g + 8 of the fragment = pixels c0 / c0 + 1
+          const uint32_t fa0[4] = {(uint32_t)vm0.x, (uint32_t)vm1.x, (uint32_t)vm0.y, (uint32_t)vm1.y};
+          const uint32_t fa1[4] = {(uint32_t)vm0.z, (uint32_t)vm1.z, (uint32_t)vm0.w, (uint32_t)vm1.w};
+          mma16816<T>(sq, fa0, w1f[0]);
+          mma16816<T>(sq, fa1, w1f[1]);
+          unsigned char* tile = St + ((r & 1) * CVG + cvg) * STILE + s_off;
+          *reinterpret_cast<float2*>(tile) = make_float2(sq[0], sq[1]);
+          *reinterpret_cast<float2*>(tile + 32) = make_float2(sq[2], sq[3]);
+        }
+      }
+
+      // ---------------- phase B: gate and store row r - 4 (tiles [(r - 1) & 1]) ----------------
+      if (r >= h0 + 4) {
+        float2 sv0 = *reinterpret_cast<const float2*>(St + 2 * CVG * STILE + s_off);        // b1
+        float2 sv1 = *reinterpret_cast<const float2*>(St + 2 * CVG * STILE + s_off + 32);
+#pragma unroll
+        for (int k = 0; k < CVG; ++k) {
+          const unsigned char* tile = St + (((r - 1) & 1) * CVG + k) * STILE + s_off;
+          const float2 pa = *reinterpret_cast<const float2*>(tile), pb = *reinterpret_cast<const float2*>(tile + 32);
+          sv0.x += pa.x; sv0.y += pa.y; sv1.x += pb.x; sv1.y += pb.y;
+        }
+        uint32_t sa[4] = {pack2<T>(fmaxf(sv0.x, 0.0f), fmaxf(sv0.y, 0.0f)), pack2<T>(fmaxf(sv1.x, 0.0f), fmaxf(sv1.y, 0.0f)), 0u, 0u};
+        const int sb = sc + NB - 4 >= NB ? sc - 4 : sc + NB - 4;
+        const int4 xv0 = *reinterpret_cast<const int4*>(ring + sb * ROWB + a_off + 3 * PITCH);
+        const int4 xv1 = *reinterpret_cast<const int4*>(ring + sb * ROWB + a_off + 4 * PITCH);
+        const uint32_t xw0[4] = {(uint32_t)xv0.x, (uint32_t)xv0.y, (uint32_t)xv0.z, (uint32_t)xv0.w};
+        const uint32_t xw1[4] = {(uint32_t)xv1.x, (uint32_t)xv1.y, (uint32_t)xv1.z, (uint32_t)xv1.w};
+        uint32_t o0[4], o1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float e[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+          const uint32_t bq[2] = {w2f[q], w2b};
+          sa[2] = t == q ? one2 : 0u;
+          sa[3] = sa[2];
+          mma16816<T>(e, sa, bq);
+          const float2 x0 = unpack2<T>(xw0[q]), x1 = unpack2<T>(xw1[q]);
+          o0[q] = pack2<T>(x0.x * rcp_approx(1.0f + ex2_approx(e[0])), x0.y * rcp_approx(1.0f + ex2_approx(e[1])));
+          o1[q] = pack2<T>(x1.x * rcp_approx(1.0f + ex2_approx(e[2])), x1.y * rcp_approx(1.0f + ex2_approx(e[3])));
+        }
+        if (ok0) fout[optr] = make_int4((int)o0[0], (int)o0[1], (int)o0[2], (int)o0[3]);
+        if (ok1) fout[optr + CV] = make_int4((int)o1[0], (int)o1[1], (int)o1[2], (int)o1[3]);
+        optr += (unsigned)rowv;
+      }
+      sc = sc + 1 == NB ? 0 : sc + 1;
+    }
+  }
+}
+
+int cam_pixels_per_thread = 0;   // A/B switch (pcls_net_set_option "cam_px"): 1 = cam_kernel, 2 = cam2_kernel, 0 = per shape (measured at
+                                 // batch 32: C = 64 0.176 vs 0.184 ms with two pixels per thread, C = 128 0.191 vs 0.188 ms)
+
 template <typename T>
 int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, cudaStream_t s) {
   if (B == 0) return PCLS_OK;
@@ -496,7 +669,8 @@ int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, cud
   const int TW = 256 / (p.C / 8);
   // row segments (>= 8 rows each): minimise  waves x iterations per CTA  with two CTAs resident per SM; a segment of n
   // rows runs n + 7 iterations (three rows of halo above / below and the pipeline drain)
-  const int64_t strips = ceil_div(W, TW) * (int64_t)B, slots = (int64_t)sm_count() * PCLS_CAM_CTAS;
+  const bool two = cam_pixels_per_thread == 2 || (cam_pixels_per_thread == 0 && p.C == 64);
+  const int64_t strips = ceil_div(W, TW) * (int64_t)B, slots = (int64_t)sm_count() * (two ? 3 : PCLS_CAM_CTAS);
   int segs = 1;
   int64_t best = -1;
   for (int sgs = 1; sgs <= (H >= 8 ? H / 8 : 1); ++sgs) {
@@ -507,14 +681,14 @@ int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, cud
   segs = (int)ceil_div(H, rows_per_seg);
   dim3 grid((unsigned)ceil_div(W, TW), (unsigned)B, (unsigned)segs);
   const int smem = p.C == 64 ? CamGeom<64>::SMEM : CamGeom<128>::SMEM;   // ring + P/O tiles, see cam_kernel
-  auto kern = p.C == 64 ? cam_kernel<T, 64> : cam_kernel<T, 128>;
-  static bool configured[2] = {false, false};
-  if (!configured[p.C == 128]) {
+  auto kern = two ? (p.C == 64 ? cam2_kernel<T, 64> : cam2_kernel<T, 128>) : (p.C == 64 ? cam_kernel<T, 64> : cam_kernel<T, 128>);
+  static bool configured[2][2] = {{false, false}, {false, false}};
+  if (!configured[two][p.C == 128]) {
     PCLS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     PCLS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    configured[p.C == 128] = true;
+    configured[two][p.C == 128] = true;
   }
-  kern<<<grid, 256, smem, s>>>(reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), p, H, W, rows_per_seg);
+  kern<<<grid, two ? 128 : 256, smem, s>>>(reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), p, H, W, rows_per_seg);
   return check_launch("cam_kernel");
 }
 template int launch_cam<__half>(const __half*, __half*, const CamParams&, int, int, int, cudaStream_t);
