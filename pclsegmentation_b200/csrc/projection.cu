@@ -47,11 +47,18 @@ project_scatter_kernel(const float4* __restrict__ points, const int32_t* __restr
                        const int64_t* __restrict__ offsets, int B, int64_t total, ProjConsts c,
                        unsigned long long* __restrict__ keys, int32_t* __restrict__ proj_x,
                        int32_t* __restrict__ proj_y, float* __restrict__ unproj_range) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+  // Every CTA walks ONE contiguous chunk of the point list, so a thread's scan index only ever moves forward: one binary
+  // search at the start, then `while (i >= end of scan) ++b` (ncu on the grid-stride version: the kernel was issue-bound,
+  // 386 instructions per point, 40 of them the per-point search over the scan offsets).
+  const int64_t chunk = (total + gridDim.x - 1) / gridDim.x;
+  const int64_t i_lo = (int64_t)blockIdx.x * chunk, i_hi = min(total, i_lo + chunk);
+  if (i_lo >= i_hi) return;
+  int b = scan_of_point(offsets, B, i_lo + threadIdx.x < i_hi ? i_lo + threadIdx.x : i_lo);
+  int64_t off_b = __ldg(offsets + b), off_e = __ldg(offsets + b + 1);
+  for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
     const float4 p = __ldg(points + i);
-    const int b = scan_of_point(offsets, B, i);
-    const uint32_t local = (uint32_t)(i - __ldg(offsets + b));
+    while (i >= off_e) { ++b; off_b = off_e; off_e = __ldg(offsets + b + 1); }   // (empty scans: several steps)
+    const uint32_t local = (uint32_t)(i - off_b);
 
     const float depth = point_depth(p.x, p.y, p.z);
     // Column.  Reference: yaw = -arctan2(y, x); proj_x = 0.5 * (yaw / pi + 1.0); proj_x *= W; floor; clamp (:126-140).
@@ -171,9 +178,15 @@ extern "C" int pcls_project_scatter(const float* points, const int32_t* ring, co
   c.fov = (float)fov;
   c.pi = (float)pi;
   c.W = W; c.H = H; c.Wf = (float)W; c.Hf = (float)H;
-  // 2-ulp atan2f/asinf (CUDA math) + four float32 roundings move proj_x by < 0.5e-6 W and proj_y by < 4e-6 H / fov
-  c.thr_x = fmaxf(4e-3f, 4e-6f * (float)W);
-  c.thr_y = fmaxf(4e-3f, 3e-5f * (float)H / (float)fov);
+  // How far the float32 fast path can be from the correctly rounded one, in pixels:
+  //   column: atan2f <= 2 ulp of |yaw| <= pi (4.8e-7 rad) -> W / (2 pi) * 4.8e-7 = 7.6e-8 W, plus the roundings of yaw / pi,
+  //           + 1 and * W (<= 1.0e-7 W together): < 1.8e-7 W (3.7e-4 px at W = 2048);
+  //   row:    z / depth (0.5 ulp) and asinf (2 ulp of |pitch| < 0.6): < 1e-7 rad -> 1e-7 H / fov, plus three roundings of
+  //           values <= H: < 2.5e-7 H / fov + 2e-7 H (3e-5 px at H = 64, fov 28 deg).
+  // The float64 evaluation decides every point within thr of a pixel boundary, thr = 4x (column) / 6x (row) those bounds.
+  // (Round 1 used 8e-3 / 4e-3 px: 41 % / 23 % of the warps had a lane on the slow path and the whole warp paid for it.)
+  c.thr_x = fmaxf(1.5e-3f, 7.5e-7f * (float)W);
+  c.thr_y = fmaxf(2e-4f, 1.5e-6f * (float)H / (float)fov + 1.2e-6f * (float)H);
   project_scatter_kernel<<<grid_for(total_points, 256), 256, 0, s>>>(
       reinterpret_cast<const float4*>(points), ring, offsets, B, total_points, c,
       reinterpret_cast<unsigned long long*>(keys), proj_x, proj_y, unproj_range);

@@ -1,20 +1,26 @@
 #!/bin/bash
-# Regenerates the measured artefacts under profiles/ (run on a B200 box through gpurun; outputs land in gpurun_out/r1/).
+# Regenerates the measured artefacts under profiles/ (run on a B200 box through gpurun; outputs land in gpurun_out/r2/,
+# copy them to profiles/ afterwards - tools/ncu_summarize.py turns the .ncu-rep into the committed CSV / JSON).
 set -u
-O=gpurun_out/r1; mkdir -p $O
-timeout 400 python bench.py --steps 20 --warmup 5 --op-table $O/optable_squeezesegv2_r1.json > $O/bench_r1.json 2> $O/bench_r1.err
-timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference_r1.json 2> $O/bench_reference_r1.err
-: > $O/bench_other_workloads_r1.jsonl
-for w in darknet21_kitti_64x2048_b32 darknet53_kitti_64x2048_b16 squeezesegv2_nuscenes_32x1024_b32; do
-  timeout 300 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline --op-table $O/optable_${w%%_*}_${w#*_}.json 2>/dev/null | tail -1 >> $O/bench_other_workloads_r1.jsonl
-done
-for w in projection_kitti_64x2048_b64 darknet53_projection_64x2048_b64; do
-  timeout 300 python bench.py --workload $w --steps 10 --warmup 5 --no-cpu-baseline 2>/dev/null | tail -1 >> $O/bench_other_workloads_r1.jsonl
-done
+O=gpurun_out/r2; mkdir -p $O
+rm -f gpurun_out/parity_report.jsonl
+timeout 700 python -m pytest tests -m gpu -q > $O/pytest_gpu_r2.log 2>&1; tail -2 $O/pytest_gpu_r2.log
+cp gpurun_out/parity_report.jsonl $O/parity_report_r2.jsonl
+timeout 500 python bench.py --steps 20 --warmup 5 --op-table $O/optable_squeezesegv2_kitti_64x2048_b32.json > $O/bench_r2.json 2> $O/bench_r2.err
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference_r2.json 2> $O/bench_reference_r2.err
 # launch list of the bench command (per-launch times are cold-cache and serialised: compare shares)
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/ncu_launches_r1.csv \
-  python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/ncu_launches.log 2>&1
-# full capture of the three heaviest kernels of one forward (conv14+head, fire13 expand, first CAM)
-timeout 400 ncu --set full --clock-control none -k regex:'conv_tc_kernel|cam_kernel' --launch-skip 35 -c 38 --csv --page raw \
-  --log-file $O/ncu_full_r1_forward.csv python tools/ncu_forward.py > $O/ncu_full.log 2>&1
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/ncu_launches_r2.csv \
+  python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras --no-eval > $O/ncu_launches.log 2>&1
+# full capture of every kernel of one plain forward (second forward of tools/ncu_forward.py: 39 launches)
+timeout 600 ncu --set full --clock-control none -k regex:'conv_tc|conv_head|cam|pool_conv|net_input' \
+  --launch-skip 39 -c 39 -o $O/ncu_full_r2_forward python tools/ncu_forward.py > $O/ncu_full.log 2>&1
+# the report is > 64 MiB (gpurun's limit for what travels back): reduce it here, keep only the summaries
+python tools/ncu_summarize.py $O/ncu_full_r2_forward.ncu-rep $O/optable_squeezesegv2_kitti_64x2048_b32.json \
+  $O/ncu_full_r2_forward_summary.csv $O/ncu_traffic_r2.json 32 && rm -f $O/ncu_full_r2_forward.ncu-rep
+# projection kernels (config 4 shape) 
+timeout 300 ncu --set full --clock-control none -k regex:'project_' --launch-skip 2 -c 2 -o $O/ncu_full_r2_projection \
+  python tools/projection_run.py 64 2 > $O/ncu_proj.log 2>&1
+ncu -i $O/ncu_full_r2_projection.ncu-rep --page raw --csv > $O/ncu_full_r2_projection_raw.csv 2>/dev/null
+timeout 60 tools/_build/umma_bench > $O/umma_bench_r2.txt 2>&1
+timeout 120 tools/_build/tma_bench > $O/tma_bench_r2.txt 2>&1
 ls -la $O
