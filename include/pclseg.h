@@ -92,6 +92,16 @@ int pcls_project_resolve(const float* points, const uint32_t* labels, const int6
                          float empty_fill, float* image, int32_t* proj_idx, int32_t* proj_sem_label,
                          pcls_stream stream);
 
+/* Fused scan -> labels pipeline (dataset_convert/semantic_kitti.py:152-173 + inference.py:47-78 without the [H,W,6] file
+ * in between): turns the winner keys straight into the NETWORK INPUT - per pixel the winning point's x, y, z, remission,
+ * range, masked (range > 0) and normalised in float64 with h_mean5 / h_std5 like inference.py:50-62, stored as the
+ * 16-bit [B,H,W,8] pixel (5 channels + mask + 2 zeros) and the u8 mask that pcls_net_forward reads.  `input8` / `mask`
+ * are the net's own buffers (pcls_net_input_buffers); then call pcls_net_forward(net, NULL, 0, NULL, NULL, NULL, B, ...).
+ * precision = the net's (PCLS_F16 | PCLS_BF16); proj_idx [B,H,W] i32 or NULL. */
+int pcls_project_resolve_net_input(const float* points, const int64_t* offsets, int B, int H, int W,
+                                   const uint64_t* keys, const double* h_mean5, const double* h_std5, int precision,
+                                   void* input8, uint8_t* mask, int32_t* proj_idx, pcls_stream stream);
+
 /* =====================================================================================
  * Segmentation head, input stage, confusion matrix
  * ===================================================================================== */
@@ -217,7 +227,8 @@ int pcls_net_cam(pcls_net* net, const pcls_cam_desc* desc);
 int pcls_net_finalize(pcls_net* net, int logits_tensor, int num_classes, int none_index);
 
 /* Runs the graph on a batch.
- *   lidar    [B,H,W,channels] f32.  channels == 6 and h_mean5 == NULL: the already normalised
+ *   lidar    [B,H,W,channels] f32 (NULL with channels == 0: the input was staged in place, see pcls_net_input_buffers).
+ *            channels == 6 and h_mean5 == NULL: the already normalised
  *            reference input (inference.py:56-62), channel 5 = mask.  channels == 5 or 6 with
  *            h_mean5/h_std5 given: RAW x,y,z,i,d(,label) - the input stage (inference.py:50-62) is
  *            fused into the load (mask = depth > 0).
@@ -227,6 +238,11 @@ int pcls_net_finalize(pcls_net* net, int logits_tensor, int num_classes, int non
 int pcls_net_forward(pcls_net* net, const float* lidar, int channels, const uint8_t* mask,
                      const double* h_mean5, const double* h_std5, int B, float* logits, float* probs,
                      int32_t* preds, pcls_stream stream);
+
+/* The net's input buffers, for producers that write the network input in place (pcls_project_resolve_net_input):
+ * *input8 = tensor 0, [frames,H,W,8] 16-bit; *mask = [frames,H,W] u8; *frames = frames per pass (max_batch, or the micro
+ * batch).  A forward over such a staged input is pcls_net_forward(net, NULL, 0, NULL, NULL, NULL, B <= frames, ...). */
+int pcls_net_input_buffers(pcls_net* net, void** input8, uint8_t** mask, int* frames);
 
 /* Debug / test access: copies activation tensor `tensor` of the last forward as float32 NHWC into
  * `out` ([B,H,width,channels] f32, device). */

@@ -39,6 +39,9 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
   "pcls_project_resolve": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                    c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+  "pcls_project_resolve_net_input": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, POINTER(c_double),
+                                             POINTER(c_double), c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+  "pcls_net_input_buffers": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int)]),
   "pcls_head": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
   "pcls_cast_f64_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
   "pcls_unpack_xyzir": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),

@@ -452,7 +452,9 @@ int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool ra
   uint8_t* mask_buf = (uint8_t*)arena + mask_offset * (size_t)frames_per_pass;
   int evi = 0;
   if (ev) cudaEventRecord(ev[evi++], s);
-  int rc = launch_net_input<T>(lidar, channels, mask, raw, mean5, std5, n_pixels, (T*)tensor_ptr(0, nb), mask_buf, s);
+  int rc = PCLS_OK;
+  if (lidar != nullptr)   // (NULL: tensor 0 and the mask were written in place, e.g. by pcls_project_resolve_net_input)
+    rc = launch_net_input<T>(lidar, channels, mask, raw, mean5, std5, n_pixels, (T*)tensor_ptr(0, nb), mask_buf, s);
   if (rc) return rc;
   float* logits_buf = logits ? logits : (float*)tensor_ptr(logits_tensor, nb);
   bool head_done = false;
@@ -543,6 +545,11 @@ static int check_forward_args(const Net& n, const float* lidar, int channels, co
   PCLS_REQUIRE(n.finalized, "pcls_net_forward: call pcls_net_finalize first");
   PCLS_REQUIRE(B >= 0 && B <= n.max_batch, "pcls_net_forward: batch %d exceeds max_batch %d", B, n.max_batch);
   const bool raw = mean5 != nullptr;
+  if (lidar == nullptr && channels == 0) {   // input already staged in the net's own buffers (pcls_net_input_buffers)
+    PCLS_REQUIRE(B <= n.frames_per_pass, "pcls_net_forward: a staged input must fit one pass (%d frames)", n.frames_per_pass);
+    PCLS_REQUIRE(B == 0 || preds != nullptr, "pcls_net_forward: preds must not be NULL");
+    return PCLS_OK;
+  }
   PCLS_REQUIRE(raw ? (channels == 5 || channels == 6) : channels == 6,
                "pcls_net_forward: channels must be 6 (normalised input) or 5/6 with mean/std (raw input), got %d", channels);
   PCLS_REQUIRE(!raw || std5 != nullptr, "pcls_net_forward: std is NULL");
@@ -762,6 +769,15 @@ extern "C" int pcls_net_forward(pcls_net* net, const float* lidar, int channels,
   PCLS_REQUIRE(net != nullptr, "pcls_net_forward: NULL net");
   return reinterpret_cast<Net*>(net)->forward(lidar, channels, mask, h_mean5, h_std5, B, logits, probs, preds,
                                               (cudaStream_t)stream);
+}
+
+extern "C" int pcls_net_input_buffers(pcls_net* net, void** input8, uint8_t** mask, int* frames) {
+  Net* n = reinterpret_cast<Net*>(net);
+  PCLS_REQUIRE(n != nullptr && n->finalized, "pcls_net_input_buffers: net is NULL or not finalized");
+  if (input8) *input8 = n->tensor_ptr(0, n->frames_per_pass);
+  if (mask) *mask = (uint8_t*)n->arena + n->mask_offset * (size_t)n->frames_per_pass;
+  if (frames) *frames = n->frames_per_pass;
+  return PCLS_OK;
 }
 
 extern "C" int pcls_net_read_tensor(pcls_net* net, int tensor, int B, float* out, pcls_stream stream) {

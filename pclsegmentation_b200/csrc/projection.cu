@@ -17,6 +17,8 @@
 // mul+add into FMA - numpy evaluates each ufunc with its own rounding.
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace pcls {
 
 struct ProjConsts {
@@ -144,6 +146,43 @@ project_resolve_kernel(const float4* __restrict__ points, const uint32_t* __rest
   }
 }
 
+// Winner keys -> the NETWORK INPUT itself (fused scan -> labels pipeline): per pixel the winning point's (x, y, z,
+// remission, range) goes through the input stage of inference.py:50-62 (mask = range > 0, float64 normalise, zero where
+// empty, mask as channel 5) and is stored as the 16-byte [B,H,W,8] 16-bit pixel conv1 reads, plus the mask byte the head
+// reads: no float32 [B,H,W,6] image round trip and no separate input kernel.
+struct NormD { double mean[5], std[5]; };
+template <typename T>
+__global__ void __launch_bounds__(256)
+project_resolve_net_input_kernel(const float4* __restrict__ points, const int64_t* __restrict__ offsets, int64_t n_pixels,
+                                 int HW, const unsigned long long* __restrict__ keys, NormD nrm, int4* __restrict__ input8,
+                                 uint8_t* __restrict__ mask, int32_t* __restrict__ proj_idx) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < n_pixels; pix += stride) {
+    const unsigned long long key = __ldg(keys + pix);
+    float v[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    int idx = -1;
+    if (key != ~0ull) {
+      idx = (int)(uint32_t)(key & 0xffffffffull);
+      const float4 p = __ldg(points + __ldg(offsets + (int)(pix / HW)) + idx);
+      v[0] = p.x; v[1] = p.y; v[2] = p.z; v[3] = p.w;
+      v[4] = point_depth(p.x, p.y, p.z);
+    }
+    const bool m = v[4] > 0.0f;
+    T h[8];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      const float f = m ? (float)(((double)v[c] - nrm.mean[c]) / nrm.std[c]) : 0.0f;
+      h[c] = sizeof(T) == 2 && std::is_same<T, __half>::value ? (T)__float2half_rn(f) : (T)__float2bfloat16_rn(f);
+    }
+    const float one = m ? 1.0f : 0.0f;
+    h[5] = std::is_same<T, __half>::value ? (T)__float2half_rn(one) : (T)__float2bfloat16_rn(one);
+    h[6] = h[7] = std::is_same<T, __half>::value ? (T)__float2half_rn(0.0f) : (T)__float2bfloat16_rn(0.0f);
+    input8[pix] = *reinterpret_cast<const int4*>(h);
+    mask[pix] = m ? 1 : 0;
+    if (proj_idx) proj_idx[pix] = idx;
+  }
+}
+
 static int grid_for(int64_t n, int threads) {
   int64_t blocks = ceil_div(n, threads);
   int64_t cap = (int64_t)sm_count() * 16;  // 16 resident 256-thread CTAs... grid-stride beyond that
@@ -206,4 +245,28 @@ extern "C" int pcls_project_resolve(const float* points, const uint32_t* labels,
       reinterpret_cast<const unsigned long long*>(keys), label_lut, lut_len, empty_fill, image, proj_idx,
       proj_sem_label);
   return check_launch("project_resolve_kernel");
+}
+
+extern "C" int pcls_project_resolve_net_input(const float* points, const int64_t* offsets, int B, int H, int W,
+                                              const uint64_t* keys, const double* h_mean5, const double* h_std5,
+                                              int precision, void* input8, uint8_t* mask, int32_t* proj_idx,
+                                              pcls_stream stream) {
+  PCLS_REQUIRE(B >= 0 && H > 0 && W > 0, "pcls_project_resolve_net_input: bad sizes");
+  PCLS_REQUIRE(keys != nullptr && offsets != nullptr && input8 != nullptr && mask != nullptr && h_mean5 != nullptr && h_std5 != nullptr,
+               "pcls_project_resolve_net_input: NULL argument");
+  PCLS_REQUIRE(precision == PCLS_F16 || precision == PCLS_BF16, "pcls_project_resolve_net_input: bad precision %d", precision);
+  const int64_t n_pixels = (int64_t)B * H * W;
+  if (n_pixels == 0) return PCLS_OK;
+  NormD nrm;
+  for (int c = 0; c < 5; ++c) { nrm.mean[c] = h_mean5[c]; nrm.std[c] = h_std5[c]; }
+  const int grid = grid_for(n_pixels, 256);
+  if (precision == PCLS_F16)
+    project_resolve_net_input_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(points), offsets, n_pixels, H * W, reinterpret_cast<const unsigned long long*>(keys), nrm,
+        reinterpret_cast<int4*>(input8), mask, proj_idx);
+  else
+    project_resolve_net_input_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(points), offsets, n_pixels, H * W, reinterpret_cast<const unsigned long long*>(keys), nrm,
+        reinterpret_cast<int4*>(input8), mask, proj_idx);
+  return check_launch("project_resolve_net_input_kernel");
 }

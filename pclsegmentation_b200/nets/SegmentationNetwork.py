@@ -217,6 +217,41 @@ class PCLSegmentationNetwork:
       res["logits"] = logits
     return res
 
+  def input_buffers(self, batch):
+    """(input8 pointer, mask pointer, frames): the device buffers a producer may write the network input into in place
+    (pcls_net_input_buffers; used by the fused projection -> forward pipeline).  Builds the device net for `batch`."""
+    net = self._ensure_net(batch)
+    inp, msk, frames = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int()
+    _lib.check(_lib.load().pcls_net_input_buffers(net, ctypes.byref(inp), ctypes.byref(msk), ctypes.byref(frames)),
+               "pcls_net_input_buffers")
+    return inp, msk, frames.value
+
+  def forward_staged(self, batch, want_probabilities=True, want_logits=False, out=None):
+    """Forward over an input that was written into ``input_buffers`` in place (no input kernel)."""
+    H, W = self.ZENITH_LEVEL, self.AZIMUTH_LEVEL
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out = out or {}
+    preds = out.get("predictions")
+    if preds is None:
+      preds = torch.empty((batch, H, W), dtype=torch.int32, device=dev)
+    probs = logits = None
+    if want_probabilities:
+      probs = out.get("probabilities")
+      if probs is None:
+        probs = torch.empty((batch, H, W, self.NUM_CLASS), dtype=torch.float32, device=dev)
+    if want_logits:
+      logits = out.get("logits")
+      if logits is None:
+        logits = torch.empty((batch, H, W, self.NUM_CLASS), dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().pcls_net_forward(self._ensure_net(batch), None, 0, None, None, None, batch, ptr(logits), ptr(probs),
+                                            ptr(preds), stream_handle()), "pcls_net_forward(staged)")
+    res = {"predictions": preds}
+    if probs is not None:
+      res["probabilities"] = probs
+    if logits is not None:
+      res["logits"] = logits
+    return res
+
   def __call__(self, inputs, training=False, mask=None):
     """``probabilities, predictions = model([lidar, mask])`` (inference.py:75, eval.py:47).
     lidar [B,H,W,6] (numpy or torch, any float dtype), mask [B,H,W] bool.  Returns CUDA tensors whose ``.numpy()``

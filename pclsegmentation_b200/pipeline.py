@@ -24,14 +24,42 @@ class ScanSegmenter:
     self.model, self.mc = model, mc
     self.projector = SphericalProjector(mc.ZENITH_LEVEL, mc.AZIMUTH_LEVEL, fov_up, fov_down, label_lut=label_lut)
 
-  def segment_device(self, points, offsets, labels=None, want_probabilities=False, out=None):
-    """points [total,4] float32 CUDA (x,y,z,remission), offsets [B+1] int64 CUDA -> dict(image, proj_idx, predictions,
-    probabilities?) - projection keys/images and activations stay on the device."""
-    proj = self.projector.project(points, offsets, labels=labels, empty_fill=0.0)
-    res = self.model.forward_device(proj["image"], None, mean=self.mc.INPUT_MEAN, std=self.mc.INPUT_STD,
-                                    want_probabilities=want_probabilities, out=out)
-    res.update(image=proj["image"], proj_idx=proj["proj_idx"])
+  def segment_device(self, points, offsets, labels=None, want_probabilities=False, out=None, want_image=False,
+                     want_logits=False):
+    """points [total,4] float32 CUDA (x,y,z,remission), offsets [B+1] int64 CUDA -> dict(predictions, proj_idx,
+    probabilities?, logits?, image?) - keys and activations stay on the device.
+
+    Default (no image, no labels wanted): the resolve pass writes the NORMALISED 16-bit network input and the mask
+    straight into the net's own buffers (pcls_project_resolve_net_input): no float32 [B,H,W,6] range image is written
+    and read back, and the forward runs without its input kernel.  With want_image / labels the range image is
+    materialised (the converters' output) and the forward reads it."""
+    B = int(offsets.numel()) - 1
+    if want_image or labels is not None or B > self._staged_capacity(B):
+      proj = self.projector.project(points, offsets, labels=labels, empty_fill=0.0)
+      res = self.model.forward_device(proj["image"], None, mean=self.mc.INPUT_MEAN, std=self.mc.INPUT_STD,
+                                      want_probabilities=want_probabilities, want_logits=want_logits, out=out)
+      res.update(image=proj["image"], proj_idx=proj["proj_idx"])
+      return res
+    lib = _lib.load()
+    H, W = self.projector.H, self.projector.W
+    inp, msk, _ = self.model.input_buffers(B)
+    keys = torch.empty((B, H, W), dtype=torch.int64, device=points.device)
+    idx = torch.empty((B, H, W), dtype=torch.int32, device=points.device)
+    s = stream_handle()
+    _lib.check(lib.pcls_project_scatter(ptr(points), None, ptr(offsets), B, int(points.shape[0]), H, W,
+                                        float(self.projector.fov_up), float(self.projector.fov_down), ptr(keys), None, None,
+                                        None, s), "pcls_project_scatter")
+    mean = (ctypes.c_double * 5)(*np.asarray(self.mc.INPUT_MEAN, np.float64).reshape(-1))
+    std = (ctypes.c_double * 5)(*np.asarray(self.mc.INPUT_STD, np.float64).reshape(-1))
+    _lib.check(lib.pcls_project_resolve_net_input(ptr(points), ptr(offsets), B, H, W, ptr(keys), mean, std,
+                                                  self.model.precision, inp, msk, ptr(idx), s),
+               "pcls_project_resolve_net_input")
+    res = self.model.forward_staged(B, want_probabilities=want_probabilities, want_logits=want_logits, out=out)
+    res.update(proj_idx=idx)
     return res
+
+  def _staged_capacity(self, B):
+    return self.model.input_buffers(B)[2]
 
   def segment(self, scans, labels=None, **kw):
     """scans: list of [N_i,4] float32 numpy arrays."""
@@ -42,6 +70,7 @@ class ScanSegmenter:
     lab = None
     if labels is not None:
       lab = to_device(np.concatenate(labels).astype(np.uint32).view(np.int32), torch.int32)
+    kw.setdefault("want_image", True)     # host convenience: the projected range images come back with the labels
     return self.segment_device(pts, offsets, labels=lab, **kw)
 
   def point_labels(self, res, points_per_scan):

@@ -105,3 +105,27 @@ def test_projection_to_labels_pipeline():
   lg, pr, pd = O.forward("darknet", model.variables, np.stack(lid), np.stack(msk), none, num_layers=21, output_stride=16)
   agree = (res["predictions"].cpu().numpy() == pd)[np.stack(msk)].mean()
   assert agree >= 0.999, agree
+
+
+def test_fused_projection_into_network_input_equals_two_step_path():
+  """ScanSegmenter.segment_device default: the resolve pass writes the normalised 16-bit network input in place
+  (pcls_project_resolve_net_input) and the forward skips its input kernel - same arithmetic, so logits and labels are
+  IDENTICAL to projecting to a float32 [B,H,W,6] image first."""
+  from pclsegmentation_b200.pipeline import ScanSegmenter
+  from pclsegmentation_b200.utils.args_loader import load_model_config
+  mc, model = load_model_config("squeezesegv2", "squeezesegv2kitti")
+  mc.AZIMUTH_LEVEL = 512
+  mc, model = mc, type(model)(mc)
+  model.randomize_batch_norm(2)
+  rng = np.random.default_rng(8)
+  sizes = [20000, 0, 15000]
+  scans = [synth_scan(rng, n) for n in sizes]
+  pts = torch.from_numpy(np.concatenate(scans)).cuda()
+  offsets = torch.as_tensor(np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)).cuda()
+  seg = ScanSegmenter(model, 3.0, -25.0)
+  two = seg.segment_device(pts, offsets, want_image=True, want_logits=True)
+  one = seg.segment_device(pts, offsets, want_logits=True)
+  assert "image" not in one
+  assert torch.equal(one["proj_idx"], two["proj_idx"])
+  assert torch.equal(one["logits"], two["logits"]) and torch.equal(one["predictions"], two["predictions"])
+  assert (one["predictions"][1] == mc.CLASSES.index("None")).all()        # the empty scan
