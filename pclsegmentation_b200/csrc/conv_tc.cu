@@ -64,6 +64,8 @@ struct TcParams {
   // K walk: per tile, n_groups A loads per K chunk; each A tile feeds `sub` tap MMAs that start `sub_row[s]` rows into it
   int n_groups, sub;
   int kchunks;                // cin_pad / KC
+  int ksteps;                 // UMMA K steps (16 channels) worth issuing per K chunk: KC / 16, fewer when the chunk's tail is
+                              // zero padding (48 channels stored with a 64-channel stride: 3).  Host-side: selects the kernel.
   int KC, BN;
   int grp_dh[2][TC_MAX_TAPS], grp_dw[2][TC_MAX_TAPS], grp_par[2][TC_MAX_TAPS];  // TMA coordinate offsets of the A box
   int grp_w[2][TC_MAX_TAPS][3];                                                  // weight tap index per (group, sub)
@@ -183,7 +185,7 @@ __device__ __forceinline__ int4 epilogue_vec8(const uint32_t* acc, const float* 
   return pack8<T>(v);
 }
 
-template <typename T, int KC, int SUB, int G, bool RES, bool LEAKY>
+template <typename T, int KC, int SUB, int G, bool RES, bool LEAKY, int KS = KC / 16>
 __global__ void __launch_bounds__(tc_threads(RES), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
@@ -393,7 +395,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const uint64_t b_desc = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_addr >> 4) & 0x3FFFu) | 0x10000u);
               if (n1 == 0u) {
 #pragma unroll
-                for (int j = 0; j < KC / 16; ++j) {  // +32 bytes along K inside the swizzle atom per UMMA_K = 16
+                for (int j = 0; j < KS; ++j) {  // +32 bytes along K inside the swizzle atom per UMMA_K = 16
                   umma_f16_elect(d_tmem, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j), idesc, accumulate);
                   accumulate = 1u;
                 }
@@ -845,7 +847,15 @@ static TcKernelFn tc_kernel_for_tt(int KC, int SUB, int G, int res, int leaky) {
   if (res) return leaky ? tc_kernel_for_t<T, true, true>(KC, SUB, G) : tc_kernel_for_t<T, true, false>(KC, SUB, G);
   return leaky ? tc_kernel_for_t<T, false, true>(KC, SUB, G) : tc_kernel_for_t<T, false, false>(KC, SUB, G);
 }
-static TcKernelFn tc_kernel_for(int KC, int SUB, int G, int is_bf16, int res, int leaky) {
+// ks = UMMA K steps per chunk; the one shape with a zero-padded K tail (48 channels in a 64-channel chunk: 3x3 halo
+// kernel, ReLU, no residual) has its own instantiation, every other combination issues all KC / 16 steps (a run-time
+// bound or predicate in the issue loop cost the issue-bound N-split layers 30 %).
+static bool tc_kskip_kernel(int KC, int SUB, int G, int res, int leaky, int ks) {
+  return ks == 3 && KC == 64 && SUB == 3 && G == 1 && !res && !leaky;
+}
+static TcKernelFn tc_kernel_for(int KC, int SUB, int G, int is_bf16, int res, int leaky, int ks = 0) {
+  if (tc_kskip_kernel(KC, SUB, G, res, leaky, ks))
+    return is_bf16 ? conv_tc_kernel<__nv_bfloat16, 64, 3, 1, false, false, 3> : conv_tc_kernel<__half, 64, 3, 1, false, false, 3>;
   return is_bf16 ? tc_kernel_for_tt<__nv_bfloat16>(KC, SUB, G, res, leaky) : tc_kernel_for_tt<__half>(KC, SUB, G, res, leaky);
 }
 
@@ -921,6 +931,7 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
     // K chunk / swizzle: the widest of 64/32/16 channels that divides cin_pad
     q.KC = (cp.cin_pad % 64 == 0) ? 64 : (cp.cin_pad % 32 == 0) ? 32 : 16;
     q.kchunks = cp.cin_pad / q.KC;
+    q.ksteps = q.KC / 16;
     q.BN = cp.cout_pad <= 256 ? cp.cout_pad : 256;
     q.n_nt = cp.cout_pad / q.BN;
     // Pixel-group view for narrow inputs (Cin = 16 / 32): TMA moves about one box row per ~8 cycles whatever its
@@ -957,6 +968,11 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
       z = z / 16 * 16;
       if (z >= 16 && q.BN - z >= 16) q.n1 = z;
     }
+#ifndef PCLS_TC_KSKIP
+#define PCLS_TC_KSKIP 1
+#endif
+    // zero-padded K tail (48 logical channels in a 64-channel chunk): the MMAs of the all-zero K steps are not issued
+    if (PCLS_TC_KSKIP && G == 1 && q.kchunks == 1 && q.n1 == 0) q.ksteps = std::min(q.KC / 16, (cp.cin + 15) / 16);
     // N-split across CTAs: a 3x3 layer whose weights do not fit in smem next to the pipeline (fire10's merged expand: 160 KB;
     // fire6 / fire7's 64(48) -> 192 expand3x3: 216 KB) streams them from L2 for every tile - 10 x the bytes of the A tile,
     // L2 -> smem bound (wait-cycle counters: issuer 50 % on FULL).  Cutting N in two and giving every CTA one half keeps the
@@ -1244,6 +1260,8 @@ int Net::tc_prepare() {
               for (int lk = 0; lk < 2; ++lk)
                 PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(kc, sub, g, bf, rs, lk), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         }
+    for (int bf = 0; bf < 2; ++bf)
+      PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(64, 3, 1, bf, 0, 0, 3), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_set = true;
   }
   return PCLS_OK;
@@ -1271,7 +1289,7 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
   }
   int grid = work < sm_count() ? work : sm_count();
   if (prm.nsplit) grid -= grid % prm.n_nt;   // every CTA sees one N tile only (tile % n_nt == blockIdx.x % n_nt)
-  tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0, prm.act == PCLS_ACT_LEAKY ? 1 : 0)<<<grid, tc_threads(prm.res0 || prm.res1), plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, plan->map_r, plan->map_b2, prm, num_tiles);
+  tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0, prm.act == PCLS_ACT_LEAKY ? 1 : 0, prm.ksteps)<<<grid, tc_threads(prm.res0 || prm.res1), plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, plan->map_r, plan->map_b2, prm, num_tiles);
   return check_launch("conv_tc_kernel");
 }
 

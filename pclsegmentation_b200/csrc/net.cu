@@ -292,6 +292,7 @@ void Net::op_tensors(const OpRef& op, std::vector<int>& reads, std::vector<int>&
     const ConvLayer& L = convs[op.index];
     reads.push_back(L.in);
     if (L.pool_src >= 0) reads.push_back(L.pool_src);   // (fused max-pool: the un-pooled tensor is what the kernel reads)
+    if (L.up_squeeze >= 0) reads.push_back(convs[L.up_squeeze].in);   // (fused squeeze conv: its input is what the kernel reads)
     if (L.res0 >= 0) reads.push_back(L.res0);
     if (L.res1 >= 0) reads.push_back(L.res1);
     writes.push_back(L.out);
@@ -333,6 +334,32 @@ int Net::finalize(int logits_tensor_, int num_classes_, int none_index_) {
       if (other_reader) continue;
       P.fused_conv = ops[i + 1].index;
       L.pool_src = P.in; L.pool_pad_left = P.pad_left;
+    }
+  // squeeze 1x1 + transposed conv fusion (squeeze_upconv.cu): the squeeze output has ONE reader, the [1,4]/s[1,2] transposed
+  // conv right behind it (FIREUP).  Not with keep_tensors: the squeeze tensor is then never written.
+  if (fuse_up && !keep_tensors)
+    for (int i = 0; i + 1 < n_ops; ++i) {
+      if (ops[i].type != OP_CONV || ops[i + 1].type != OP_CONV) continue;
+      ConvLayer& Q = convs[ops[i].index];
+      ConvLayer& U = convs[ops[i + 1].index];
+      const ConvParams &q = Q.p, &u = U.p;
+      if (q.mode != MODE_1x1 || u.mode != MODE_DECONV || U.in != Q.out || Q.pool_src >= 0) continue;
+      if (Q.res0 >= 0 || Q.res1 >= 0 || U.res0 >= 0 || U.res1 >= 0 || q.out_f32 || u.out_f32 || q.out_coff != 0 || u.out_coff != 0) continue;
+      const int C = q.cin_pad, S = q.cout;
+      if (tensors[Q.in].stride != C || tensors[Q.in].channels != C || Q.cin_logical != C) continue;
+      if (q.cout != q.cout_pad || q.out_channels != S || Q.cout_logical != S) continue;
+      if (u.cin_pad != S || u.cout != S || u.cout_pad != S || u.out_channels != S || U.cin_logical != S) continue;
+      if (!squeeze_upconv_supported(C, S)) continue;
+      bool other_reader = false;
+      std::vector<int> rd, wr;
+      for (int k = 0; k < n_ops; ++k) {
+        if (k == i + 1) continue;
+        op_tensors(ops[k], rd, wr);
+        for (int r : rd) other_reader = other_reader || r == Q.out;
+      }
+      if (other_reader || Q.out == logits_tensor) continue;
+      U.up_squeeze = ops[i].index;
+      Q.fused_into_up = ops[i + 1].index;
     }
   // liveness: first write .. last read (op order); the logits tensor lives to the end (head reads it)
   std::vector<int> reads, writes;
@@ -467,7 +494,16 @@ int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool ra
       p.out = (L.out == logits_tensor) ? (void*)logits_buf : tensor_ptr(L.out, nb);
       p.res0 = L.res0 >= 0 ? tensor_ptr(L.res0, nb) : nullptr;
       p.res1 = L.res1 >= 0 ? tensor_ptr(L.res1, nb) : nullptr;
-      if (conv_impl == 0 && L.pool_src >= 0) {
+      if (conv_impl == 0 && L.fused_into_up >= 0) continue;   // computed by the transposed conv behind it
+      if (conv_impl == 0 && L.up_squeeze >= 0) {
+        const ConvLayer& Q = convs[L.up_squeeze];
+        SqueezeUpconvParams su;
+        su.in = tensor_ptr(Q.in, nb); su.out = p.out;
+        su.w1 = Q.p.w; su.b1 = Q.p.bias; su.w1_stride = Q.p.cin_pad; su.act1 = Q.p.act;
+        su.w2 = p.w; su.b2 = p.bias; su.w2_cout_pad = p.cout_pad; su.w2_cin_pad = p.cin_pad; su.act2 = p.act;
+        su.H = H; su.W = p.Win; su.rows = 0; su.tiles_per_row = 0;
+        rc = launch_squeeze_upconv<T>(su, Q.p.cin_pad, Q.p.cout, nb, s);
+      } else if (conv_impl == 0 && L.pool_src >= 0) {
         PoolConvParams pc;
         pc.in = tensor_ptr(L.pool_src, nb); pc.out = p.out; pc.w = p.w; pc.bias = p.bias;
         pc.H = H; pc.Win = tensors[L.pool_src].width; pc.Wout = p.Wout; pc.out_channels = p.out_channels;
@@ -500,7 +536,7 @@ int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool ra
                                    tensors[L.out].width, tensors[L.in].stride, L.pad_left, s);
     } else {
       const CamLayer& L = cams[op.index];
-      rc = launch_cam<T>((const T*)tensor_ptr(L.in, nb), (T*)tensor_ptr(L.out, nb), L.p, nb, H, tensors[L.in].width, s);
+      rc = launch_cam<T>((const T*)tensor_ptr(L.in, nb), (T*)tensor_ptr(L.out, nb), L.p, nb, H, tensors[L.in].width, cam_px, s);
     }
     if (rc) return rc;
     if (tc_debug_buf && ev && op.type == OP_CONV) {  // development aid: print the counters of this launch
@@ -676,6 +712,18 @@ int Net::op_info(int i, char* name, int* family, int64_t* flops, int64_t* bytes)
       if (L.res0 >= 0) by += (int64_t)H * p.Wout * cout * 2;
       if (L.res1 >= 0) by += (int64_t)H * p.Wout * cout * 2;
       fam = (conv_impl == 0 && L.tc_ok) ? 1 : 0;
+      if (conv_impl == 0 && L.fused_into_up >= 0) {          // runs inside the transposed conv behind it
+        snprintf(buf, sizeof(buf), "%s_%dx%d_w%d(fused)", mode, (int)cin, (int)cout, p.Wout);
+        fl = 0; by = 0; fam = 0;
+      }
+      if (conv_impl == 0 && L.up_squeeze >= 0) {             // squeeze input -> up-sampled output, the squeeze tensor stays on chip
+        const ConvLayer& Q = convs[L.up_squeeze];
+        snprintf(buf, sizeof(buf), "conv1x1_%dx%d+%s_w%d", Q.cin_logical, Q.cout_logical, mode, p.Wout);
+        fl += 2 * (int64_t)H * p.Win * Q.cin_logical * Q.cout_logical;
+        by = (int64_t)H * p.Win * Q.cin_logical * 2 + (int64_t)H * p.Wout * cout * 2 +
+             ((int64_t)Q.cin_logical * Q.cout_logical + (int64_t)p.ntaps * cin * cout) * 2;
+        fam = 0;
+      }
     } else if (op.type == OP_POOL) {
       const PoolLayer& L = pools[op.index];
       const bool fused = conv_impl == 0 && L.fused_conv >= 0;
@@ -830,7 +878,7 @@ extern "C" int pcls_net_set_option(pcls_net* net, const char* name, int value) {
     n->keep_tensors = value != 0; return PCLS_OK;
   }
   if (!strcmp(name, "tc_head")) { tc_head_mode = value; return PCLS_OK; }
-  if (!strcmp(name, "cam_px")) { PCLS_REQUIRE(value >= 0 && value <= 2, "cam_px must be 0 (per shape), 1 or 2"); cam_pixels_per_thread = value; n->drop_graphs(); return PCLS_OK; }
+  if (!strcmp(name, "cam_px")) { PCLS_REQUIRE(value >= 0 && value <= 2, "cam_px must be 0 (default), 1 or 2"); n->cam_px = value; n->drop_graphs(); return PCLS_OK; }
   if (!strcmp(name, "tc_nsplit")) { tc_nsplit_mode = value; return PCLS_OK; }
   if (!strcmp(name, "pad48")) {
     PCLS_REQUIRE(n->convs.empty(), "pad48 must be set before the first pcls_net_conv");
@@ -842,6 +890,10 @@ extern "C" int pcls_net_set_option(pcls_net* net, const char* name, int value) {
   if (!strcmp(name, "tc_res_tma")) { tc_res_tma_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_split")) { tc_split_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_vstream")) { tc_vstream_mode = value; return PCLS_OK; }
+  if (!strcmp(name, "fuse_up")) {
+    PCLS_REQUIRE(!n->finalized, "fuse_up must be set before pcls_net_finalize");
+    n->fuse_up = value != 0; return PCLS_OK;
+  }
   if (!strcmp(name, "fuse_pool")) {
     PCLS_REQUIRE(!n->finalized, "fuse_pool must be set before pcls_net_finalize");
     n->fuse_pool = value != 0; return PCLS_OK;

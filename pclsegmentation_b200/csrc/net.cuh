@@ -18,7 +18,6 @@ struct TcPlan;    // tcgen05 launch plan of one conv layer (conv_tc.cu)
 struct HeadPlan;  // launch plan of the logits layer + fused segmentation head (conv_head.cu)
 extern int tc_head_mode;
 extern int tc_halo_mode, tc_resident_mode, tc_base_offset_mode, tc_tma_store_mode, tc_group_mode, tc_res_tma_mode, tc_split_mode, tc_vstream_mode, tc_nsplit_mode;
-extern int cam_pixels_per_thread;
 extern int pad48_mode;  // 48-channel tensors written by one conv are stored with a 64-channel pixel stride (zero pads)
 extern const int tc_debug_compiled;
 extern unsigned long long* tc_debug_buf;  // A/B measurement switches (process-wide)
@@ -33,6 +32,8 @@ struct ConvLayer {
   TcPlan* tc = nullptr;
   HeadPlan* hp = nullptr;
   int pool_src = -1, pool_pad_left = 0;   // >= 0: this 1x1 conv reads tensor pool_src through a fused 3x3/s2 max-pool
+  int up_squeeze = -1;     // transposed conv: index of the squeeze 1x1 conv computed in front of it by the same kernel (squeeze_upconv.cu)
+  int fused_into_up = -1;  // that squeeze conv: index of the transposed conv that runs it (no launch of its own)
   // Pixel-pair view for the convolutions that read the 8-channel network input (tensor-core path only):
   // [B,H,W,8] is viewed as [B,H,W/2,16]; `ptc` / `w_tc` / `bias_tc` describe the equivalent convolution on pairs.
   bool pair_view = false;
@@ -72,10 +73,12 @@ struct Net {
   // execution knobs
   int conv_impl = 0;
   bool use_graph = true;
+  bool fuse_up = true;     // FireDeconv squeeze 1x1 + transposed conv as one kernel (squeeze_upconv.cu)
   bool fuse_pool = true;   // max-pool + the squeeze 1x1 conv that consumes it as one kernel (pool_conv.cu)
   bool fuse_head = true;   // run softmax/argmax/mask in the epilogue of the final convolution (tcgen05 path)
   struct HeadArgs { int head = 0, none_index = 0; const uint8_t* mask = nullptr; float* probs = nullptr; int32_t* preds = nullptr; float* logits = nullptr; } head_args;
   int micro_batch = 0;
+  int cam_px = 0;             // CAM pixels per thread: 0 = default (2), 1 = cam_kernel, 2 = cam2_kernel
   bool keep_tensors = false;  // test aid: no arena reuse, every intermediate stays readable after the forward
   // device state
   int frames_per_pass = 0;

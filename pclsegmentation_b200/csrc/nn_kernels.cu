@@ -314,11 +314,13 @@ __device__ __forceinline__ float rcp_approx(float x) {
 #ifndef PCLS_CAM_DIST
 #define PCLS_CAM_DIST 3
 #endif
-template <int C> struct CamGeom {
+template <int C, int PX = 1> struct CamGeom {     // PX = pixels per thread (cam_kernel 1, cam2_kernel 2)
   static constexpr int CV = C / 8;              // 16-byte vectors per pixel (8 or 16)
   static constexpr int TW = 256 / CV;           // columns per CTA (32 or 16)
-  static constexpr int PITCH = C * 2 + 64;      // bytes per ring pixel; = 64 mod 128: the (pixel, 4 vectors) reads of a
-                                                // quarter warp (2 pixels x 64 bytes) fall on disjoint banks
+  static constexpr int PITCH = C * 2 + 64 / PX; // bytes per ring pixel; PX * PITCH = 64 mod 128: the (pixel, 4 vectors) reads
+                                                // of a quarter warp (2 threads' pixels x 64 bytes) fall on disjoint banks.
+                                                // (cam2 with the 1-pixel pitch: every LDS.128 took two wavefronts, ncu
+                                                // l1tex shared wavefronts 70 M vs 36 M ideal)
   static constexpr int ROWB = (TW + 6) * PITCH; // bytes per ring slot
   static constexpr int DIST = PCLS_CAM_DIST, NB = DIST + 6;   // ring: rows r-5 .. r+DIST resident (DIST rows of loads in flight)
   static constexpr int SMEM = NB * ROWB + (2 * (CV / 4) + 1) * TW * 8 * 4;
@@ -501,7 +503,7 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
 template <typename T, int C>
 __global__ void __launch_bounds__(128, 3)
 cam2_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int H, int W, int rows_per_seg) {
-  using G = CamGeom<C>;
+  using G = CamGeom<C, 2>;
   constexpr int CV = G::CV, TW = G::TW, PITCH = G::PITCH, ROWB = G::ROWB, NB = G::NB, DIST = G::DIST;
   constexpr int R = C / 16;
   constexpr int NSTG = (TW + 6) * CV;
@@ -557,8 +559,7 @@ cam2_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, in
     if (i < NSTG && !sok[k])
       for (int sl = 0; sl < NB; ++sl) *reinterpret_cast<int4*>(ring + sl * ROWB + (i / CV) * PITCH + (i % CV) * 16) = NEG;
   }
-  for (int i = threadIdx.x; i < TW * 8; i += 128)
-    reinterpret_cast<float*>(St + 2 * CVG * STILE)[i] = (i % 8) < R ? p.b1[i % 8] : 0.0f;
+  const float b1x = 2 * t < R ? p.b1[2 * t] : 0.0f, b1y = 2 * t + 1 < R ? p.b1[2 * t + 1] : 0.0f;
   const int h0 = blockIdx.z * rows_per_seg, h1 = min(H, h0 + rows_per_seg);
   const int a0 = h0 - 3 < 0 ? 0 : h0 - 3;
   sptr += (unsigned)a0 * (unsigned)rowv;
@@ -575,7 +576,8 @@ cam2_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, in
   };
 
   const unsigned a_off = c0 * PITCH + cv * 16;            // ring: pixel c0 - 3 (+ d * PITCH), this vector
-  const unsigned s_off = (c0 * 8 + 2 * t) * 4;            // squeeze tile: pixel c0, columns 2t, 2t+1 (pixel c0 + 1: + 32 bytes)
+  const unsigned s_off = ((pg * 8 + g) * 4 + t) * 16;     // squeeze tile [pixel pair][t]: {c0: columns 2t, 2t+1 | c0 + 1: same} = one
+                                                          // conflict-free 16-byte access per lane
   const bool ok0 = (w0 + c0) < W, ok1 = (w0 + c0 + 1) < W;
   unsigned optr = (unsigned)((w0 + c0) * CV + cv) + (unsigned)h0 * (unsigned)rowv;
 
@@ -615,21 +617,17 @@ cam2_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, in
           const uint32_t fa1[4] = {(uint32_t)vm0.z, (uint32_t)vm1.z, (uint32_t)vm0.w, (uint32_t)vm1.w};
           mma16816<T>(sq, fa0, w1f[0]);
           mma16816<T>(sq, fa1, w1f[1]);
-          unsigned char* tile = St + ((r & 1) * CVG + cvg) * STILE + s_off;
-          *reinterpret_cast<float2*>(tile) = make_float2(sq[0], sq[1]);
-          *reinterpret_cast<float2*>(tile + 32) = make_float2(sq[2], sq[3]);
+          *reinterpret_cast<float4*>(St + ((r & 1) * CVG + cvg) * STILE + s_off) = make_float4(sq[0], sq[1], sq[2], sq[3]);
         }
       }
 
       // ---------------- phase B: gate and store row r - 4 (tiles [(r - 1) & 1]) ----------------
       if (r >= h0 + 4) {
-        float2 sv0 = *reinterpret_cast<const float2*>(St + 2 * CVG * STILE + s_off);        // b1
-        float2 sv1 = *reinterpret_cast<const float2*>(St + 2 * CVG * STILE + s_off + 32);
+        float2 sv0 = make_float2(b1x, b1y), sv1 = sv0;
 #pragma unroll
         for (int k = 0; k < CVG; ++k) {
-          const unsigned char* tile = St + (((r - 1) & 1) * CVG + k) * STILE + s_off;
-          const float2 pa = *reinterpret_cast<const float2*>(tile), pb = *reinterpret_cast<const float2*>(tile + 32);
-          sv0.x += pa.x; sv0.y += pa.y; sv1.x += pb.x; sv1.y += pb.y;
+          const float4 pa = *reinterpret_cast<const float4*>(St + (((r - 1) & 1) * CVG + k) * STILE + s_off);
+          sv0.x += pa.x; sv0.y += pa.y; sv1.x += pa.z; sv1.y += pa.w;
         }
         uint32_t sa[4] = {pack2<T>(fmaxf(sv0.x, 0.0f), fmaxf(sv0.y, 0.0f)), pack2<T>(fmaxf(sv1.x, 0.0f), fmaxf(sv1.y, 0.0f)), 0u, 0u};
         const int sb = sc + NB - 4 >= NB ? sc - 4 : sc + NB - 4;
@@ -658,18 +656,17 @@ cam2_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, in
   }
 }
 
-int cam_pixels_per_thread = 0;   // A/B switch (pcls_net_set_option "cam_px"): 1 = cam_kernel, 2 = cam2_kernel, 0 = per shape (measured at
-                                 // batch 32: C = 64 0.176 vs 0.184 ms with two pixels per thread, C = 128 0.191 vs 0.188 ms)
-
+// px: pixels per thread (pcls_net_set_option "cam_px"): 1 = cam_kernel, 2 = cam2_kernel, 0 = default = 2 (measured at batch 32:
+// C = 64 0.138 vs 0.185 ms, C = 128 0.143 vs 0.189 ms)
 template <typename T>
-int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, cudaStream_t s) {
+int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, int px, cudaStream_t s) {
   if (B == 0) return PCLS_OK;
   PCLS_REQUIRE(p.C == 64 || p.C == 128, "CAM: channels must be 64 or 128, got %d", p.C);
   PCLS_REQUIRE(p.R == p.C / 16, "CAM: reduced channels must be C/16");
   const int TW = 256 / (p.C / 8);
   // row segments (>= 8 rows each): minimise  waves x iterations per CTA  with two CTAs resident per SM; a segment of n
   // rows runs n + 7 iterations (three rows of halo above / below and the pipeline drain)
-  const bool two = cam_pixels_per_thread == 2 || (cam_pixels_per_thread == 0 && p.C == 64);
+  const bool two = px != 1;
   const int64_t strips = ceil_div(W, TW) * (int64_t)B, slots = (int64_t)sm_count() * (two ? 3 : PCLS_CAM_CTAS);
   int segs = 1;
   int64_t best = -1;
@@ -680,7 +677,8 @@ int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, cud
   const int rows_per_seg = (int)ceil_div(H, segs);
   segs = (int)ceil_div(H, rows_per_seg);
   dim3 grid((unsigned)ceil_div(W, TW), (unsigned)B, (unsigned)segs);
-  const int smem = p.C == 64 ? CamGeom<64>::SMEM : CamGeom<128>::SMEM;   // ring + P/O tiles, see cam_kernel
+  const int smem = two ? (p.C == 64 ? CamGeom<64, 2>::SMEM : CamGeom<128, 2>::SMEM)
+                       : (p.C == 64 ? CamGeom<64>::SMEM : CamGeom<128>::SMEM);   // ring + squeeze tiles, see cam_kernel
   auto kern = two ? (p.C == 64 ? cam2_kernel<T, 64> : cam2_kernel<T, 128>) : (p.C == 64 ? cam_kernel<T, 64> : cam_kernel<T, 128>);
   static bool configured[2][2] = {{false, false}, {false, false}};
   if (!configured[two][p.C == 128]) {
@@ -691,8 +689,8 @@ int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, cud
   kern<<<grid, two ? 128 : 256, smem, s>>>(reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), p, H, W, rows_per_seg);
   return check_launch("cam_kernel");
 }
-template int launch_cam<__half>(const __half*, __half*, const CamParams&, int, int, int, cudaStream_t);
-template int launch_cam<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, const CamParams&, int, int, int, cudaStream_t);
+template int launch_cam<__half>(const __half*, __half*, const CamParams&, int, int, int, int, cudaStream_t);
+template int launch_cam<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, const CamParams&, int, int, int, int, cudaStream_t);
 
 // --------------------------------------------------------------------------------------------------
 // n dense output elements [pixels][channels]; the input holds `stride` >= channels values per pixel (padded tensors)

@@ -54,6 +54,20 @@ struct PoolConvParams {
 bool pool_conv1x1_supported(int C, int S);
 template <typename T> int launch_pool_conv1x1(const PoolConvParams& p, int C, int S, int B, cudaStream_t s);
 
+// squeeze 1x1 conv fused with the transposed [1,4] / stride [1,2] conv that consumes it (squeeze_upconv.cu)
+struct SqueezeUpconvParams {
+  const void* in;      // T [B,H,W,C]
+  void* out;           // T [B,H,2W,S]
+  const void* w1;      // T [S][w1_stride] folded squeeze weights (K-major)
+  const float* b1;     // [S]
+  const void* w2;      // T [4][w2_cout_pad][w2_cin_pad] folded transposed-conv taps (out channel major, K-major rows)
+  const float* b2;     // [S]
+  int H, W, w1_stride, w2_cout_pad, w2_cin_pad, act1, act2;
+  int rows, tiles_per_row;   // filled by the launcher
+};
+bool squeeze_upconv_supported(int C, int S);
+template <typename T> int launch_squeeze_upconv(const SqueezeUpconvParams& p, int C, int S, int B, cudaStream_t s);
+
 struct CamParams {
   int C, R;            // channels, reduced channels (C / 16)
   const float* w1;     // [C][R]   folded squeeze weights
@@ -61,7 +75,7 @@ struct CamParams {
   const float* w2;     // [R][C]   folded excitation weights
   const float* b2;     // [C]
 };
-template <typename T> int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, cudaStream_t s);
+template <typename T> int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, int px, cudaStream_t s);
 template <typename T> int launch_tensor_to_f32(const T* in, float* out, int64_t n, int channels, int stride, cudaStream_t s);
 
 int launch_head(const float* logits, const uint8_t* mask, int64_t n_pixels, int nc, int none_index, float* probs,

@@ -122,7 +122,7 @@ def _fold64(p, conv, bn, transpose=False):
   return k, b
 
 
-def _check_layer(x_dev, y_dev, p, conv, bn=None, strides=(1, 1), act=None, transpose=False, residuals=(), what=""):
+def _check_layer(x_dev, y_dev, p, conv, bn=None, strides=(1, 1), act=None, transpose=False, residuals=(), what="", slack=1.5):
   """x_dev / y_dev / residuals: NHWC float32 arrays read back from the device (exact 16-bit values)."""
   k, b = _fold64(p, conv, bn, transpose)
   x = _nchw(x_dev).double()
@@ -135,7 +135,7 @@ def _check_layer(x_dev, y_dev, p, conv, bn=None, strides=(1, 1), act=None, trans
   y = pre if act is None else (torch.relu(pre) if act == "relu" else O.leaky(pre))
   for r in residuals:
     y = y + _nchw(r).double()
-  bound = U16 * (1.5 * S + y.abs()) + 1e-6
+  bound = U16 * (slack * S + y.abs()) + 1e-6
   d = (_nchw(y_dev).double() - y).abs()
   worst = float((d / bound).max())
   assert tuple(y.shape) == tuple(_nchw(y_dev).shape), what
@@ -252,8 +252,11 @@ def test_residual_and_skip_adds(impl):
   _check_layer(ys, got, p, "c2", "b2", act="leaky", residuals=[ys, ya], what="block 3x3 + residual + skip")
 
 
+@pytest.mark.parametrize("px", [2, 1])
 @pytest.mark.parametrize("C,W", [(64, 70), (128, 33)])
-def test_cam_and_pool(C, W):
+def test_cam_and_pool(C, W, px, monkeypatch):
+  """Both CAM kernels: two pixels per thread (the default) and one (option cam_px = 1)."""
+  monkeypatch.setenv("PCLS_TEST_OPTS", "cam_px=%d" % px)
   rng = np.random.default_rng(C)
   B, H = 2, 11
   t = TinyNet(H, W)
@@ -268,6 +271,38 @@ def test_cam_and_pool(C, W):
   ya, ycam = t.kept
   _check_cam(ya, ycam, p, "cam", "C %d W %d" % (C, W))
   assert np.array_equal(got, _nhwc(O.max_pool_same(_nchw(ycam), 3, (1, 2))))   # the max-pool is exact on its own input
+
+
+@pytest.mark.parametrize("C,S,W,H", [(64, 16, 256, 3), (64, 16, 70, 5), (128, 16, 33, 4), (256, 32, 14, 3), (128, 16, 15, 2)])
+def test_squeeze_fused_into_transposed_conv(C, S, W, H):
+  """squeeze_upconv_kernel: FIREUP's squeeze 1x1 conv (+BN, ReLU) and the [1,4] / stride [1,2] transposed conv (+bias,
+  ReLU) behind it as one kernel (the squeeze tensor stays on chip).  Shapes of fire13 / fire12 / fire11, widths that are
+  and are not multiples of the 14-pixel tile.  The un-fused run (keep_tensors switches the fusion off) gives the squeeze
+  tensor; the fused output is checked against the error model on it.  The kernel's internal squeeze values may differ
+  from that tensor by one 16-bit ulp where the accumulation order decides a rounding: 2 x 2^-11 x S more slack."""
+  rng = np.random.default_rng(C + S + W)
+  B = 2
+  t = TinyNet(H, W)
+  g = t.g
+  a = L.relu(L.BatchNormalization("b0")(L.Conv2D("c0", C, 3)(g.input)))
+  sq = L.relu(L.BatchNormalization("b1")(L.Conv2D("c1", S, 1)(a)))
+  up = L.relu(L.Conv2DTranspose("c2", S, kernel_size=[1, 4], strides=[1, 2])(sq))
+  _rand_vars(g, rng)
+  x = _input(rng, B, H, W)
+  p = _tp(g)
+  ref = t.run(up, B, x, 0, keep=[a, sq])          # un-fused: two tcgen05 launches
+  ya, ysq = t.kept
+  _check_layer(ya, ysq, p, "c1", "b1", act="relu", what="squeeze %d -> %d" % (C, S))
+  _check_layer(ysq, ref, p, "c2", None, act="relu", transpose=True, what="transposed conv (un-fused)")
+  got = t.run(up, B, x, 0)                        # fused
+  assert got.shape == ref.shape
+  _check_layer(ysq, got, p, "c2", None, act="relu", transpose=True, slack=3.5, what="squeeze %d -> %d + transposed conv, fused" % (C, S))
+  os.environ["PCLS_TEST_OPTS"] = "fuse_up=0"
+  try:
+    got2 = t.run(up, B, x, 0)
+  finally:
+    del os.environ["PCLS_TEST_OPTS"]
+  assert np.array_equal(got2, ref)                # the switch restores the two-op path
 
 
 @pytest.mark.parametrize("C,S,W,H", [(64, 16, 256, 9), (128, 32, 96, 20), (256, 48, 70, 5), (64, 16, 33, 3)])
