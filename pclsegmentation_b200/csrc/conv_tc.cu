@@ -189,7 +189,8 @@ template <typename T, int KC, int SUB, int G, bool RES, bool LEAKY, int KS = KC 
 __global__ void __launch_bounds__(tc_threads(RES), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
-               const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ TcParams p, const int num_tiles) {
+               const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ CUtensorMap map_c2,
+               const __grid_constant__ TcParams p, const int num_tiles) {
   constexpr bool PRELOAD = !RES;   // bias pre-loaded into the TMEM accumulators (see preload_bias)
   constexpr int TC_NG = tc_ng(RES);
   extern __shared__ uint8_t smem_raw[];
@@ -769,12 +770,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // two staging buffers per group: block k is written while the TMA store of block k-1 drains the other one
             buf = cstage_base + (uint32_t)(grp * 2 + (int)(blk & 1u)) * c_stage_bytes;
           }
-          const uint32_t row_addr = buf + (uint32_t)(m * 128);
+          // a 32-channel tail block (N tile = 64 k + 32, kernels without residuals): 64-byte rows, SWIZZLE_64B, map_c2
+          const bool narrow = !RES && BN - cb < 64;
+          const uint32_t row_addr = buf + (uint32_t)(m * (narrow ? 64 : 128));
           res_row = row_addr;
+          if (narrow) {
+            chunk(cb, [&](int g, const int4& o) { st_shared_v4(row_addr + (uint32_t)((g ^ ((m >> 1) & 3)) << 4), o); });
+          } else {
 #pragma unroll 1
-          for (int ci = 0; ci < 2; ++ci)
-            chunk(cb + ci * 32, [&](int g, const int4& o) {
-              st_shared_v4(row_addr + (uint32_t)(((ci * 4 + g) ^ (m & 7)) << 4), o); });
+            for (int ci = 0; ci < 2; ++ci)
+              chunk(cb + ci * 32, [&](int g, const int4& o) {
+                st_shared_v4(row_addr + (uint32_t)(((ci * 4 + g) ^ (m & 7)) << 4), o); });
+          }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> visible to the TMA engine
           if (!res_tma) { DBG_T0; if (issuer) bulk_wait_read0(); DBG_ADD(4); }   // store k-1 has finished reading the OTHER buffer
           { DBG_T0; group_barrier(bar_id); DBG_ADD(5); }
@@ -782,7 +789,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int pp = G > 1 ? (n0 + cb) >> blk_shift : 0;
             const int c0 = out_coff + (p.perm ? p.cblk_off[(n0 + cb) >> 6] : ((n0 + cb) & blk_mask));
             if (c_is_5d) tma_store_5d(&map_c, buf, c0, G > 1 ? pp : ph, wt * BW, ht * BH, b);
-            else tma_store_4d(&map_c, buf, c0, wt * BW, ht * BH, b);
+            else tma_store_4d(narrow ? &map_c2 : &map_c, buf, c0, wt * BW, ht * BH, b);
             bulk_commit();
           }
         }
@@ -831,7 +838,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #undef RFULL_BAR
 }
 
-typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const int);
+typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const int);
 template <typename T, bool RES, bool LEAKY>
 static TcKernelFn tc_kernel_for_t(int KC, int SUB, int G) {
   if (G == 4) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 4, RES, LEAKY> : conv_tc_kernel<T, 64, 1, 4, RES, LEAKY>;
@@ -860,7 +867,7 @@ static TcKernelFn tc_kernel_for(int KC, int SUB, int G, int is_bf16, int res, in
 }
 
 struct TcPlan {
-  CUtensorMap map_a, map_b, map_c, map_r, map_b2;
+  CUtensorMap map_a, map_b, map_c, map_r, map_b2, map_c2;
   TcParams prm;
   size_t smem_bytes;
   void* w_dev;       // plan-owned copies with permuted rows (N-split across CTAs of a merged Fire expand), else NULL
@@ -1080,7 +1087,10 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
     // TMA-store epilogue: 16-bit outputs whose N tile splits into blocks of <= 64 channels
     q.tma_store = 0; q.cbw = 0; q.c_stage_bytes = 0; q.c_is_5d = (deconv || G > 1) ? 1 : 0;
     // (measured: for N tiles narrower than 64 channels the direct 16-byte stores are faster than staging)
-    if (tc_tma_store_mode && !cp.out_f32 && cp.cout == cp.cout_pad && q.BN % 64 == 0 &&
+    // (N tile = 64 k + 32, e.g. the halves of fire6 / fire7's 192-channel expand3x3: the tail block is stored through a
+    // second map with 64-byte rows - with per-thread stores that epilogue took 50 cycles per column instead of 24)
+    const bool narrow_tail = q.BN % 64 == 32 && q.BN > 64 && G == 1 && !deconv && L.res0 < 0 && L.res1 < 0;
+    if (tc_tma_store_mode && !cp.out_f32 && cp.cout == cp.cout_pad && (q.BN % 64 == 0 || narrow_tail) &&
         (G == 1 || cp.cout_pad % 64 == 0) &&
         (cp.out_channels * 2) % 16 == 0) {
       q.tma_store = 1;
@@ -1209,8 +1219,17 @@ int Net::tc_plan_layer(ConvLayer& L, bool allow_group, bool* retry) {
         rc = make_map(&plan->map_c, bf16, c_base, 4, dims, str, box, csw);
       }
       if (rc) { delete plan; return rc; }
+      plan->map_c2 = plan->map_c;
+      if (q.BN % 64 == 32) {      // 32-channel tail block of the N tile
+        const uint64_t dims[4] = {Co, Wo, Hh, F};
+        const uint64_t str[3] = {Co * 2, Wo * Co * 2, Hh * Wo * Co * 2};
+        const uint32_t box[4] = {32u, (uint32_t)q.BW, (uint32_t)q.BH, 1};
+        rc = make_map(&plan->map_c2, bf16, c_base, 4, dims, str, box, 64);
+        if (rc) { delete plan; return rc; }
+      }
     } else {
       plan->map_c = plan->map_a;  // unused
+      plan->map_c2 = plan->map_a;
     }
     plan->map_r = plan->map_c;
     if (q.res_tma) {  // R: the residual tensor, same view as C
@@ -1289,7 +1308,7 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
   }
   int grid = work < sm_count() ? work : sm_count();
   if (prm.nsplit) grid -= grid % prm.n_nt;   // every CTA sees one N tile only (tile % n_nt == blockIdx.x % n_nt)
-  tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0, prm.act == PCLS_ACT_LEAKY ? 1 : 0, prm.ksteps)<<<grid, tc_threads(prm.res0 || prm.res1), plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, plan->map_r, plan->map_b2, prm, num_tiles);
+  tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0, prm.act == PCLS_ACT_LEAKY ? 1 : 0, prm.ksteps)<<<grid, tc_threads(prm.res0 || prm.res1), plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, plan->map_r, plan->map_b2, plan->map_c2, prm, num_tiles);
   return check_launch("conv_tc_kernel");
 }
 
