@@ -239,6 +239,14 @@ int pcls_net_forward(pcls_net* net, const float* lidar, int channels, const uint
                      const double* h_mean5, const double* h_std5, int B, float* logits, float* probs,
                      int32_t* preds, pcls_stream stream);
 
+/* The same forward for a 16-bit host contract: `lidar16` is the normalised reference input (inference.py:56-62) already
+ * in the net's storage type (IEEE half for PCLS_F16, bfloat16 for PCLS_BF16), [B,H,W,6] (5 channels + mask channel) or
+ * [B,H,W,8] (tensor 0's own layout, channels 6-7 ignored).  The host ships 12 / 16 bytes per pixel instead of 24; the
+ * results are bit-identical to pcls_net_forward on the float32 input these values were rounded from.
+ *   mask  [B,H,W] u8 or NULL = derive (channel 5 != 0). */
+int pcls_net_forward_in16(pcls_net* net, const void* lidar16, int channels, const uint8_t* mask, int B,
+                          float* logits, float* probs, int32_t* preds, pcls_stream stream);
+
 /* The net's input buffers, for producers that write the network input in place (pcls_project_resolve_net_input):
  * *input8 = tensor 0, [frames,H,W,8] 16-bit; *mask = [frames,H,W] u8; *frames = frames per pass (max_batch, or the micro
  * batch).  A forward over such a staged input is pcls_net_forward(net, NULL, 0, NULL, NULL, NULL, B <= frames, ...). */

@@ -61,6 +61,7 @@ SIGNATURES = {
   "pcls_net_finalize": (c_int, [c_void_p, c_int, c_int, c_int]),
   "pcls_net_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, POINTER(c_double), POINTER(c_double), c_int,
                                c_void_p, c_void_p, c_void_p, c_void_p]),
+  "pcls_net_forward_in16": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
   "pcls_net_read_tensor": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
   "pcls_net_num_ops": (c_int, [c_void_p]),
   "pcls_net_profile_ops": (c_int, [c_void_p, c_void_p, c_int, c_void_p, POINTER(c_double), POINTER(c_double), c_int,

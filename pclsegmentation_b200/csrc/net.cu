@@ -480,8 +480,10 @@ int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool ra
   int evi = 0;
   if (ev) cudaEventRecord(ev[evi++], s);
   int rc = PCLS_OK;
-  if (lidar != nullptr)   // (NULL: tensor 0 and the mask were written in place, e.g. by pcls_project_resolve_net_input)
-    rc = launch_net_input<T>(lidar, channels, mask, raw, mean5, std5, n_pixels, (T*)tensor_ptr(0, nb), mask_buf, s);
+  if (lidar != nullptr) {  // (NULL: tensor 0 and the mask were written in place, e.g. by pcls_project_resolve_net_input)
+    if (channels & kIn16) rc = launch_net_input16(lidar, channels & ~kIn16, mask, n_pixels, tensor_ptr(0, nb), mask_buf, s);
+    else rc = launch_net_input<T>(lidar, channels, mask, raw, mean5, std5, n_pixels, (T*)tensor_ptr(0, nb), mask_buf, s);
+  }
   if (rc) return rc;
   float* logits_buf = logits ? logits : (float*)tensor_ptr(logits_tensor, nb);
   bool head_done = false;
@@ -564,7 +566,9 @@ int Net::run_all(const float* lidar, int channels, const uint8_t* mask, bool raw
   const size_t px = (size_t)H * W;
   for (int b0 = 0; b0 < B; b0 += frames_per_pass) {
     const int nb = std::min(frames_per_pass, B - b0);
-    const float* l = lidar + (size_t)b0 * px * channels;
+    const float* l = (channels & kIn16)   // 16-bit host contract: the pointer walks 2-byte elements
+        ? (const float*)((const uint16_t*)lidar + (size_t)b0 * px * (channels & ~kIn16))
+        : lidar + (size_t)b0 * px * channels;
     const uint8_t* m = mask ? mask + (size_t)b0 * px : nullptr;
     float* lg = logits ? logits + (size_t)b0 * px * num_classes : nullptr;
     float* pr = probs ? probs + (size_t)b0 * px * num_classes : nullptr;
@@ -584,6 +588,12 @@ static int check_forward_args(const Net& n, const float* lidar, int channels, co
   if (lidar == nullptr && channels == 0) {   // input already staged in the net's own buffers (pcls_net_input_buffers)
     PCLS_REQUIRE(B <= n.frames_per_pass, "pcls_net_forward: a staged input must fit one pass (%d frames)", n.frames_per_pass);
     PCLS_REQUIRE(B == 0 || preds != nullptr, "pcls_net_forward: preds must not be NULL");
+    return PCLS_OK;
+  }
+  if (channels & kIn16) {
+    PCLS_REQUIRE(!raw && ((channels & ~kIn16) == 6 || (channels & ~kIn16) == 8),
+                 "pcls_net_forward_in16: channels must be 6 or 8 (normalised 16-bit input), got %d", channels & ~kIn16);
+    PCLS_REQUIRE(B == 0 || (lidar != nullptr && preds != nullptr), "pcls_net_forward_in16: lidar/preds must not be NULL");
     return PCLS_OK;
   }
   PCLS_REQUIRE(raw ? (channels == 5 || channels == 6) : channels == 6,
@@ -817,6 +827,15 @@ extern "C" int pcls_net_forward(pcls_net* net, const float* lidar, int channels,
   PCLS_REQUIRE(net != nullptr, "pcls_net_forward: NULL net");
   return reinterpret_cast<Net*>(net)->forward(lidar, channels, mask, h_mean5, h_std5, B, logits, probs, preds,
                                               (cudaStream_t)stream);
+}
+
+extern "C" int pcls_net_forward_in16(pcls_net* net, const void* lidar16, int channels, const uint8_t* mask, int B,
+                                     float* logits, float* probs, int32_t* preds, pcls_stream stream) {
+  PCLS_REQUIRE(net != nullptr, "pcls_net_forward_in16: NULL net");
+  PCLS_REQUIRE(channels == 6 || channels == 8, "pcls_net_forward_in16: channels must be 6 or 8, got %d", channels);
+  PCLS_REQUIRE(B == 0 || lidar16 != nullptr, "pcls_net_forward_in16: lidar16 is NULL");
+  return reinterpret_cast<Net*>(net)->forward((const float*)lidar16, channels | kIn16, mask, nullptr, nullptr, B, logits,
+                                              probs, preds, (cudaStream_t)stream);
 }
 
 extern "C" int pcls_net_input_buffers(pcls_net* net, void** input8, uint8_t** mask, int* frames) {

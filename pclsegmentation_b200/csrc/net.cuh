@@ -54,6 +54,8 @@ struct CamLayer {
 enum OpType { OP_CONV = 0, OP_POOL = 1, OP_CAM = 2 };
 struct OpRef { int type, index; };
 
+constexpr int kIn16 = 0x100;   // OR-ed into `channels` inside the library: the input is 16-bit (pcls_net_forward_in16)
+
 struct GraphKey {
   const void *lidar, *mask, *logits, *probs, *preds;
   int channels, B, raw, conv_impl;

@@ -184,6 +184,39 @@ template int launch_net_input<__half>(const float*, int, const uint8_t*, bool, c
 template int launch_net_input<__nv_bfloat16>(const float*, int, const uint8_t*, bool, const double*, const double*,
                                              int64_t, __nv_bfloat16*, uint8_t*, cudaStream_t);
 
+// 16-bit host contract (pcls_net_forward_in16): the normalised reference input already in the net's storage type,
+// [.,6] (5 channels + mask channel, the reference's lidar_input layout) or [.,8] (tensor 0's own layout).  A pure
+// re-pack: 12 / 16 B read, 16 + 1 B written per pixel, bit-identical to what net_input_kernel makes of the f32 input
+// rounded to 16 bits.
+__global__ void __launch_bounds__(256)
+net_input16_kernel(const uint32_t* __restrict__ in, int channels, const uint8_t* __restrict__ mask_in, int64_t n_pixels,
+                   int4* __restrict__ out8, uint8_t* __restrict__ mask_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pixels; p += stride) {
+    int4 v;
+    if (channels == 8) {
+      v = __ldg(reinterpret_cast<const int4*>(in) + p);
+      v.w = 0;
+    } else {
+      const uint32_t* s = in + p * 3;
+      v.x = (int)__ldg(s); v.y = (int)__ldg(s + 1); v.z = (int)__ldg(s + 2); v.w = 0;
+    }
+    const bool m = mask_in ? (mask_in[p] != 0) : (((uint32_t)v.z >> 16) & 0x7FFFu) != 0;   // channel 5 != +-0
+    out8[p] = v;
+    mask_out[p] = m ? 1 : 0;
+  }
+}
+
+int launch_net_input16(const void* lidar16, int channels, const uint8_t* mask_in, int64_t n_pixels, void* out8,
+                       uint8_t* mask_out, cudaStream_t s) {
+  if (n_pixels == 0) return PCLS_OK;
+  int64_t blocks = ceil_div(n_pixels, 256);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  net_input16_kernel<<<(int)blocks, 256, 0, s>>>((const uint32_t*)lidar16, channels, mask_in, n_pixels, (int4*)out8, mask_out);
+  return check_launch("net_input16_kernel");
+}
+
 // --------------------------------------------------------------------------------------------------
 // tf.nn.max_pool2d(ksize=3, strides=[1,2], padding='SAME'): rows h-1..h+1, cols 2wo-pl .. 2wo-pl+2
 // one thread = one output pixel x 8 channels (128-bit loads/stores); padding never wins the max

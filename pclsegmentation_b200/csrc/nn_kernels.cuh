@@ -39,6 +39,8 @@ template <typename T> int launch_conv_direct(const ConvParams& p, int B, cudaStr
 template <typename T> int launch_net_input(const float* lidar, int channels, const uint8_t* mask_in, bool raw,
                                            const double* mean5, const double* std5, int64_t n_pixels, T* out8,
                                            uint8_t* mask_out, cudaStream_t s);
+int launch_net_input16(const void* lidar16, int channels, const uint8_t* mask_in, int64_t n_pixels, void* out8,
+                       uint8_t* mask_out, cudaStream_t s);
 template <typename T> int launch_maxpool3x3_s2(const T* in, T* out, int B, int H, int Win, int Wout, int C,
                                                int pad_left, cudaStream_t s);
 

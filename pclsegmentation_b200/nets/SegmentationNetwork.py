@@ -181,8 +181,9 @@ class PCLSegmentationNetwork:
   def forward_device(self, lidar, mask=None, mean=None, std=None, want_probabilities=True, want_logits=False,
                      out=None):
     """Runs pcls_net_forward on device tensors.  lidar: float32 CUDA tensor [B,H,W,6] (normalised, mask in channel 5)
-    or, with mean/std, RAW [B,H,W,5|6] (input stage fused).  mask: uint8/bool CUDA tensor [B,H,W] or None.
-    Returns dict(predictions, probabilities?, logits?) of CUDA tensors."""
+    or, with mean/std, RAW [B,H,W,5|6] (input stage fused), or a 16-bit tensor [B,H,W,6|8] in the net's storage type
+    (pcls_net_forward_in16: the normalised input already rounded, 12 / 16 bytes per pixel).  mask: uint8/bool CUDA tensor
+    [B,H,W] or None.  Returns dict(predictions, probabilities?, logits?) of CUDA tensors."""
     lib = _lib.load()
     B, H, W, C = lidar.shape
     if (H, W) != (self.ZENITH_LEVEL, self.AZIMUTH_LEVEL):
@@ -208,8 +209,15 @@ class PCLSegmentationNetwork:
       std_p = (ctypes.c_double * 5)(*[float(v) for v in np.asarray(std).reshape(-1)[:5]])
     if mask is not None and mask.dtype == torch.bool:
       mask = mask.view(torch.uint8)
-    _lib.check(lib.pcls_net_forward(net, ptr(lidar), C, ptr(mask), mean_p, std_p, B, ptr(logits), ptr(probs),
-                                    ptr(preds), stream_handle()), "pcls_net_forward")
+    if lidar.dtype in (torch.float16, torch.bfloat16):
+      want = torch.float16 if self.precision == _lib.PCLS_F16 else torch.bfloat16
+      if lidar.dtype != want or mean is not None:
+        raise ValueError("a 16-bit input must be the normalised input in the net's storage type (%s)" % want)
+      _lib.check(lib.pcls_net_forward_in16(net, ptr(lidar), C, ptr(mask), B, ptr(logits), ptr(probs), ptr(preds),
+                                           stream_handle()), "pcls_net_forward_in16")
+    else:
+      _lib.check(lib.pcls_net_forward(net, ptr(lidar), C, ptr(mask), mean_p, std_p, B, ptr(logits), ptr(probs),
+                                      ptr(preds), stream_handle()), "pcls_net_forward")
     res = {"predictions": preds}
     if probs is not None:
       res["probabilities"] = probs
@@ -259,7 +267,11 @@ class PCLSegmentationNetwork:
     if training:
       raise NotImplementedError("training is outside the scope of this inference path")
     lidar_input, lidar_mask = inputs[0], inputs[1]
-    lidar = to_device(lidar_input, torch.float32, self._pinned, "lidar")
+    # a float16 / bfloat16 lidar_input ([B,H,W,6], or [B,H,W,8] = tensor 0's layout) is shipped as it is: 12 / 16 bytes
+    # per pixel over the host link instead of 24, same results as the float32 input it was rounded from
+    in16 = str(getattr(lidar_input, "dtype", "")).replace("torch.", "") in ("float16", "bfloat16")
+    lidar = to_device(lidar_input, lidar_input.dtype if in16 and torch.is_tensor(lidar_input) else
+                      torch.float16 if in16 else torch.float32, self._pinned, "lidar")
     m = None
     if lidar_mask is not None:
       m = to_device(lidar_mask, torch.uint8 if not (torch.is_tensor(lidar_mask) and lidar_mask.dtype == torch.bool)

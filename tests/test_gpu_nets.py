@@ -460,3 +460,29 @@ def test_micro_batch_and_graph_replay_are_equivalent():
     for _ in range(3):  # replays
       out = model.forward_device(torch.from_numpy(lidar).cuda(), torch.from_numpy(mask).cuda(), want_logits=True)
     assert torch.equal(out["predictions"], base["predictions"]) and torch.equal(out["logits"], base["logits"])
+
+
+@pytest.mark.parametrize("channels,with_mask", [(6, True), (6, False), (8, True), (8, False)])
+def test_16bit_host_input_gives_identical_results(channels, with_mask):
+  """model([lidar.astype(float16), mask]) - the 12 / 16 bytes-per-pixel host contract (pcls_net_forward_in16) - must be
+  bit-identical to the float32 call: the device rounds the float32 input to the same 16-bit values first."""
+  mc, model = _model("squeezesegv2", "squeezesegv2", 32, 240)
+  rng = np.random.default_rng(11)
+  raw = synth_range_images(rng, 5, 32, 240, num_classes=11)
+  lidar, mask = _prep(mc, raw)
+  base = model.forward_device(torch.from_numpy(lidar).cuda(), torch.from_numpy(mask).cuda(), want_logits=True)
+  base = {k: v.clone() for k, v in base.items()}
+  l16 = lidar.astype(np.float16)
+  if channels == 8:
+    l16 = np.concatenate([l16, rng.standard_normal(l16.shape[:3] + (2,)).astype(np.float16)], -1)  # pads are ignored
+  m = torch.from_numpy(mask).cuda() if with_mask else None
+  for _ in range(2):  # capture + replay
+    out = model.forward_device(torch.from_numpy(l16).cuda(), m, want_logits=True)
+  assert torch.equal(out["logits"], base["logits"]) and torch.equal(out["predictions"], base["predictions"])
+  assert torch.equal(out["probabilities"], base["probabilities"])
+  # through the reference-facing call with host arrays, micro-batched (the pointer must walk 2-byte elements)
+  model.set_option("micro_batch", 2)
+  probabilities, predictions = model([l16, mask if with_mask else None])
+  assert np.array_equal(predictions.numpy(), base["predictions"].cpu().numpy())
+  with pytest.raises(ValueError):
+    model.forward_device(torch.from_numpy(l16).cuda().to(torch.bfloat16), m)
