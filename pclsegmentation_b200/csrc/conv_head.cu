@@ -33,6 +33,7 @@ constexpr int HD_THREADS = 64 + 128 * HD_NG;
 constexpr int HD_TILE = 126;   // output pixels per tile (128 input pixels incl. the one-pixel halo on both sides)
 
 struct HeadParams {
+  int pdl_early;               // trigger the dependent grid at the start (common.cuh)
   int H, W, n_wt;
   int kchunks;                 // Cin / KC
   int N, cout;                 // MMA N (multiple of 16 >= 3 CS), classes
@@ -93,6 +94,8 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int n_wt = p.n_wt, H = p.H, W = p.W, kchunks = p.kchunks;
   const uint32_t N = (uint32_t)p.N;
+  pdl_trigger(p.pdl_early);     // PDL (common.cuh): prologue and weight loads overlap the tail of the layer in front
+  if (warp != 0) pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -100,6 +103,7 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     for (int g = 0; g < 3; ++g)
       for (int kc = 0; kc < kchunks; ++kc)
         tma_load_3d_elect(bres_base + (uint32_t)(g * kchunks + kc) * b_tile_bytes, &map_b, BRES_BAR, kc * KC, 0, g);
+    pdl_wait();
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -426,6 +430,7 @@ int Net::head_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) 
   HeadParams prm = plan->prm;
   prm.head = head_args.head;
   prm.none_index = head_args.none_index; prm.mask = head_args.mask;
+  prm.pdl_early = pdl_early_now;
   prm.preds = head_args.preds;
   prm.probs = head_args.head ? head_args.probs : nullptr;
   // fused head: logits travel to HBM only when the caller asks for them; unfused: this layer's output IS the logits tensor
@@ -433,7 +438,8 @@ int Net::head_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) 
   const int num_tiles = prm.n_wt * prm.H * nb;
   if (num_tiles == 0) return PCLS_OK;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  head_kernel_for(plan->KC, plan->CS, plan->is_bf16)<<<grid, HD_THREADS, plan->smem_bytes, s>>>(plan->map_a, plan->map_b, prm, num_tiles);
+  PCLS_CHECK_CUDA(launch_pdl(head_kernel_for(plan->KC, plan->CS, plan->is_bf16), dim3(grid), dim3(HD_THREADS), plan->smem_bytes, s,
+                             plan->map_a, plan->map_b, prm, num_tiles));
   return check_launch("conv_head_kernel");
 }
 

@@ -55,6 +55,7 @@ constexpr int tc_ng(bool res) { return res ? 2 : PCLS_TC_NG_NORES; }
 constexpr int tc_threads(bool res) { return 64 + 128 * tc_ng(res); }   // warp 0 TMA producer, warp 1 MMA issuer, then the groups
 
 struct TcParams {
+  int pdl_early;              // trigger the dependent grid at the start (common.cuh)
   // tile geometry
   int BW, BH, bw_shift;       // BW * BH = 128, BW = 1 << bw_shift
   int n_wt, n_ht, n_nt, n_phase, num_tiles;
@@ -247,6 +248,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // PDL (common.cuh): the layer behind this one may start its prologue now; everything above (and the resident weight
+  // loads of warp 0 below) is independent of the layer in front, all activation traffic comes after pdl_wait()
+  pdl_trigger(p.pdl_early);
+  if (warp != 0) pdl_wait();
 
   const int n_groups = p.n_groups, kchunks = p.kchunks, n_nt = p.n_nt, n_phase = p.n_phase, n_wt = p.n_wt, n_ht = p.n_ht;
   const int BN = p.BN;
@@ -275,6 +280,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
               }
       }
+      pdl_wait();   // weights are in flight; the activations need the producing layer to have finished
       const uint32_t a_tx_bytes = (uint32_t)(p.a_rows * KC * 2);
       const int BW = p.BW, BH = p.BH;
       const bool is5d = p.a_is_5d != 0;
@@ -1292,6 +1298,7 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
   TcParams prm = plan->prm;
   prm.out = p.out; prm.res0 = p.res0; prm.res1 = p.res1;
   prm.dbg = tc_debug_buf;
+  prm.pdl_early = pdl_early_now;
   prm.head = (prm.out_f32 && head_args.head) ? 1 : 0;
   prm.none_index = head_args.none_index; prm.mask = head_args.mask;
   prm.probs = head_args.probs; prm.preds = head_args.preds; prm.logits = head_args.logits;
@@ -1308,7 +1315,9 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
   }
   int grid = work < sm_count() ? work : sm_count();
   if (prm.nsplit) grid -= grid % prm.n_nt;   // every CTA sees one N tile only (tile % n_nt == blockIdx.x % n_nt)
-  tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0, prm.act == PCLS_ACT_LEAKY ? 1 : 0, prm.ksteps)<<<grid, tc_threads(prm.res0 || prm.res1), plan->smem_bytes, s>>>(plan->map_a, plan->map_b, plan->map_c, plan->map_r, plan->map_b2, plan->map_c2, prm, num_tiles);
+  PCLS_CHECK_CUDA(launch_pdl(tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0, prm.act == PCLS_ACT_LEAKY ? 1 : 0, prm.ksteps),
+                             dim3(grid), dim3(tc_threads(prm.res0 || prm.res1)), plan->smem_bytes, s,
+                             plan->map_a, plan->map_b, plan->map_c, plan->map_r, plan->map_b2, plan->map_c2, prm, num_tiles));
   return check_launch("conv_tc_kernel");
 }
 

@@ -476,6 +476,7 @@ int Net::run_pass(const float* lidar, int channels, const uint8_t* mask, bool ra
                   const double* std5, int nb, float* logits, float* probs, int32_t* preds, cudaStream_t s,
                   cudaEvent_t* ev) {
   const int64_t n_pixels = (int64_t)nb * H * W;
+  pdl_early_now = (pdl_mode && n_pixels <= pdl_early_px) ? 1 : 0;   // small passes: latency mode (common.cuh)
   uint8_t* mask_buf = (uint8_t*)arena + mask_offset * (size_t)frames_per_pass;
   int evi = 0;
   if (ev) cudaEventRecord(ev[evi++], s);

@@ -143,8 +143,10 @@ struct Norm5f { double mean[5]; double std[5]; };
 template <typename T>
 __global__ void __launch_bounds__(256)
 net_input_kernel(const float* __restrict__ lidar, int channels, const uint8_t* __restrict__ mask_in, int raw, Norm5f nrm,
-                 int64_t n_pixels, T* __restrict__ out8, uint8_t* __restrict__ mask_out) {
+                 int64_t n_pixels, T* __restrict__ out8, uint8_t* __restrict__ mask_out, int pdl_early) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  pdl_trigger(pdl_early);   // first kernel of the forward: tensor 0 / the mask buffer may still be read by the previous forward
+  pdl_wait();
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pixels; p += stride) {
     const float* s = lidar + p * channels;
     float f[8];
@@ -176,7 +178,8 @@ int launch_net_input(const float* lidar, int channels, const uint8_t* mask_in, b
   int64_t blocks = ceil_div(n_pixels, 256);
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  net_input_kernel<T><<<(int)blocks, 256, 0, s>>>(lidar, channels, mask_in, raw ? 1 : 0, nrm, n_pixels, out8, mask_out);
+  PCLS_CHECK_CUDA(launch_pdl(net_input_kernel<T>, dim3((unsigned)blocks), dim3(256), 0, s, lidar, channels, mask_in, raw ? 1 : 0, nrm,
+                             n_pixels, out8, mask_out, pdl_early_now));
   return check_launch("net_input_kernel");
 }
 template int launch_net_input<__half>(const float*, int, const uint8_t*, bool, const double*, const double*, int64_t,
@@ -190,8 +193,10 @@ template int launch_net_input<__nv_bfloat16>(const float*, int, const uint8_t*, 
 // rounded to 16 bits.
 __global__ void __launch_bounds__(256)
 net_input16_kernel(const uint32_t* __restrict__ in, int channels, const uint8_t* __restrict__ mask_in, int64_t n_pixels,
-                   int4* __restrict__ out8, uint8_t* __restrict__ mask_out) {
+                   int4* __restrict__ out8, uint8_t* __restrict__ mask_out, int pdl_early) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  pdl_trigger(pdl_early);
+  pdl_wait();
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pixels; p += stride) {
     int4 v;
     if (channels == 8) {
@@ -213,7 +218,8 @@ int launch_net_input16(const void* lidar16, int channels, const uint8_t* mask_in
   int64_t blocks = ceil_div(n_pixels, 256);
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  net_input16_kernel<<<(int)blocks, 256, 0, s>>>((const uint32_t*)lidar16, channels, mask_in, n_pixels, (int4*)out8, mask_out);
+  PCLS_CHECK_CUDA(launch_pdl(net_input16_kernel, dim3((unsigned)blocks), dim3(256), 0, s, (const uint32_t*)lidar16, channels, mask_in,
+                             n_pixels, (int4*)out8, mask_out, pdl_early_now));
   return check_launch("net_input16_kernel");
 }
 
@@ -434,6 +440,8 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
     reinterpret_cast<float*>(St + 2 * CVG * STILE)[i] = (i % 8) < R ? p.b1[i % 8] : 0.0f;
   // blockIdx.z = row segment [h0, h1) of the strip (small batches: more CTAs than SMs; a segment re-reads three rows
   // above and below).  The walk starts at input row a0 = max(h0 - 3, 0).
+  pdl_trigger(p.pdl_early);   // PDL (common.cuh): the weight fragments above are independent of the producing layer
+  pdl_wait();
   const int h0 = blockIdx.z * rows_per_seg, h1 = min(H, h0 + rows_per_seg);
   const int a0 = h0 - 3 < 0 ? 0 : h0 - 3;
   sptr += (unsigned)a0 * (unsigned)rowv;
@@ -593,6 +601,8 @@ cam2_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, in
       for (int sl = 0; sl < NB; ++sl) *reinterpret_cast<int4*>(ring + sl * ROWB + (i / CV) * PITCH + (i % CV) * 16) = NEG;
   }
   const float b1x = 2 * t < R ? p.b1[2 * t] : 0.0f, b1y = 2 * t + 1 < R ? p.b1[2 * t + 1] : 0.0f;
+  pdl_trigger(p.pdl_early);   // PDL (common.cuh): the weight fragments above are independent of the producing layer
+  pdl_wait();
   const int h0 = blockIdx.z * rows_per_seg, h1 = min(H, h0 + rows_per_seg);
   const int a0 = h0 - 3 < 0 ? 0 : h0 - 3;
   sptr += (unsigned)a0 * (unsigned)rowv;
@@ -713,13 +723,18 @@ int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, int
   const int smem = two ? (p.C == 64 ? CamGeom<64, 2>::SMEM : CamGeom<128, 2>::SMEM)
                        : (p.C == 64 ? CamGeom<64>::SMEM : CamGeom<128>::SMEM);   // ring + squeeze tiles, see cam_kernel
   auto kern = two ? (p.C == 64 ? cam2_kernel<T, 64> : cam2_kernel<T, 128>) : (p.C == 64 ? cam_kernel<T, 64> : cam_kernel<T, 128>);
-  static bool configured[2][2] = {{false, false}, {false, false}};
-  if (!configured[two][p.C == 128]) {
+  static bool configured[64][2][2] = {};   // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63][two][p.C == 128]) {
     PCLS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     PCLS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    configured[two][p.C == 128] = true;
+    configured[dev & 63][two][p.C == 128] = true;
   }
-  kern<<<grid, two ? 128 : 256, smem, s>>>(reinterpret_cast<const int4*>(in), reinterpret_cast<int4*>(out), p, H, W, rows_per_seg);
+  CamParams q = p;
+  q.pdl_early = pdl_early_now;
+  PCLS_CHECK_CUDA(launch_pdl(kern, grid, dim3(two ? 128 : 256), (size_t)smem, s, reinterpret_cast<const int4*>(in),
+                             reinterpret_cast<int4*>(out), q, H, W, rows_per_seg));
   return check_launch("cam_kernel");
 }
 template int launch_cam<__half>(const __half*, __half*, const CamParams&, int, int, int, int, cudaStream_t);

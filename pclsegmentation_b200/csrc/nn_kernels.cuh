@@ -52,6 +52,7 @@ struct PoolConvParams {
   const float* bias;   // [S]
   int H, Win, Wout, out_channels, w_stride, pad_left, act, n_strips, tiles_per_row;
   int zero_to;         // channels [S, zero_to) of the output are written as zeros (padded output tensors), 0: none
+  int pdl_early;       // filled by the launcher (common.cuh)
 };
 bool pool_conv1x1_supported(int C, int S);
 template <typename T> int launch_pool_conv1x1(const PoolConvParams& p, int C, int S, int B, cudaStream_t s);
@@ -66,6 +67,7 @@ struct SqueezeUpconvParams {
   const float* b2;     // [S]
   int H, W, w1_stride, w2_cout_pad, w2_cin_pad, act1, act2;
   int rows, tiles_per_row;   // filled by the launcher
+  int pdl_early;             // filled by the launcher (common.cuh)
 };
 bool squeeze_upconv_supported(int C, int S);
 template <typename T> int launch_squeeze_upconv(const SqueezeUpconvParams& p, int C, int S, int B, cudaStream_t s);
@@ -76,6 +78,7 @@ struct CamParams {
   const float* b1;     // [R]
   const float* w2;     // [R][C]   folded excitation weights
   const float* b2;     // [C]
+  int pdl_early;       // filled by the launcher (common.cuh)
 };
 template <typename T> int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, int px, cudaStream_t s);
 template <typename T> int launch_tensor_to_f32(const T* in, float* out, int64_t n, int channels, int stride, cudaStream_t s);

@@ -85,6 +85,8 @@ pool_conv1x1_kernel(const PoolConvParams p) {
       }
     if constexpr (W_SMEM) __syncthreads();
   }
+  pdl_trigger(p.pdl_early);   // PDL (common.cuh): the weight fragments are loaded, the activations need the producing layer
+  pdl_wait();
   const float lo = p.act == PCLS_ACT_RELU ? 0.0f : -INFINITY;
   const bool leaky = p.act == PCLS_ACT_LEAKY;
   T* const outp = reinterpret_cast<T*>(p.out);
@@ -229,6 +231,7 @@ template <typename T, int C, int S>
 static int launch_pc(const PoolConvParams& p, int B, cudaStream_t s) {
   constexpr int SLABS = C / 64, PG = 8 / SLABS;
   PoolConvParams q = p;
+  q.pdl_early = pdl_early_now;
   q.tiles_per_row = (int)ceil_div(p.Wout, 16 * PG);
   q.n_strips = q.tiles_per_row * B;
   const size_t smem = SLABS > 1 ? (size_t)2 * PG * SLABS * 16 * S * sizeof(float) + (size_t)SLABS * 4 * (S / 8) * 32 * 8 : 0;
@@ -244,7 +247,7 @@ static int launch_pc(const PoolConvParams& p, int B, cudaStream_t s) {
   const long long total_rows = (long long)q.n_strips * p.H;
   if (grid > total_rows / 6) grid = total_rows / 6;
   if (grid < 1) grid = 1;
-  pool_conv1x1_kernel<T, C, S><<<(unsigned)grid, 256, smem, s>>>(q);
+  PCLS_CHECK_CUDA(launch_pdl(pool_conv1x1_kernel<T, C, S>, dim3((unsigned)grid), dim3(256), (size_t)smem, s, q));
   return check_launch("pool_conv1x1_kernel");
 }
 

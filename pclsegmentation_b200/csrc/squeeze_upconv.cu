@@ -110,6 +110,8 @@ squeeze_upconv_kernel(const SqueezeUpconvParams p) {
     }
   }
 
+  pdl_trigger(p.pdl_early);   // PDL (common.cuh): weights are staged, the activations need the producing layer
+  pdl_wait();
   // ---- tiles: (image row, tile of SU_TP pixels), consecutive warps take consecutive tiles ----
   const long long total = (long long)p.rows * p.tiles_per_row;
   const long long wstep = (long long)gridDim.x * SU_WARPS;
@@ -223,6 +225,7 @@ template <typename T, int C, int S>
 static int launch_su(const SqueezeUpconvParams& p, int B, cudaStream_t s) {
   using G = SuGeom<C, S>;
   SqueezeUpconvParams q = p;
+  q.pdl_early = pdl_early_now;
   q.rows = B * p.H;
   q.tiles_per_row = (int)ceil_div(p.W, SU_TP);
   auto kern = squeeze_upconv_kernel<T, C, S>;
@@ -236,7 +239,7 @@ static int launch_su(const SqueezeUpconvParams& p, int B, cudaStream_t s) {
   long long grid = (long long)sm_count() * ctas_per_sm;
   if (grid > ceil_div(total, SU_WARPS)) grid = ceil_div(total, SU_WARPS);
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, SU_WARPS * 32, G::SMEM, s>>>(q);
+  PCLS_CHECK_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(SU_WARPS * 32), (size_t)G::SMEM, s, q));
   return check_launch("squeeze_upconv_kernel");
 }
 
