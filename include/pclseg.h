@@ -146,6 +146,20 @@ int pcls_unpack_xyzir(const float* rec5, int64_t n, float* points4, int32_t* rin
 int pcls_confusion_update(const int32_t* label, const int32_t* pred, int64_t n, int num_classes,
                           int64_t* cm, int64_t* dropped, pcls_stream stream);
 
+/* test_step on the device, forward only (nets/SegmentationNetwork.py:118-131): ONE pass over the forward's outputs
+ * accumulates the loss sums and the class-weighted confusion matrix.
+ *   probs [n,NC] f32, label [n] i32, pred [n] i32 (NULL when cm_w is NULL), mask [n] u8 or NULL (= all valid),
+ *   weight [n] f32 or NULL (= 1)
+ *   loss_kind 0: none; 1: focal loss (:71-91) - loss_acc[0] += sum((1 - p)^gamma * -log(p) * weight * mask) with
+ *             p = probs[label] + eps, loss_acc[1] += sum(mask); 2: Keras SparseCategoricalCrossentropy on probabilities
+ *             (:49, :125) - loss_acc[0] += sum(-(log clip(p[label]) - log sum_c clip(p_c)) * weight), loss_acc[1] += n
+ *             (clip to [1e-7, 1 - 1e-7]).  The caller divides (and applies CLS_LOSS_COEF).
+ *   loss_acc [2] f64 accumulated in place; cm_w [NC*NC] f64 accumulated in place or NULL: cm_w[label, pred] += weight
+ *   (tf.math.confusion_matrix(..., weights), :129); pairs outside [0,NC) are counted in *dropped (may be NULL).  NC <= 32. */
+int pcls_validation_update(const float* probs, const int32_t* label, const int32_t* pred, const uint8_t* mask,
+                           const float* weight, int64_t n, int num_classes, int loss_kind, double eps, double gamma,
+                           double* loss_acc, double* cm_w, int64_t* dropped, pcls_stream stream);
+
 /* Multi-GPU exchange step (no reference call site - the reference is single-device): sums the
  * per-GPU matrices in place with one ncclAllReduce(int64, sum) on `stream`.
  * The communicator helpers wrap the NCCL the process already has loaded (dlopen libnccl.so.2). */

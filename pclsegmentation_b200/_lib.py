@@ -48,6 +48,8 @@ SIGNATURES = {
   "pcls_input_stage": (c_int, [c_void_p, c_int, c_int64, POINTER(c_double), POINTER(c_double), c_int, c_void_p,
                                c_void_p, c_void_p, POINTER(c_double), c_int, c_void_p, c_void_p]),
   "pcls_confusion_update": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+  "pcls_validation_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_double,
+                                     c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
   "pcls_comm_unique_id": (c_int, [c_char_p]),
   "pcls_comm_init": (c_int, [POINTER(c_void_p), c_int, c_char_p, c_int]),
   "pcls_comm_destroy": (c_int, [c_void_p]),

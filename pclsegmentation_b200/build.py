@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 _SUFFIX = os.environ.get("PCLS_LIB_SUFFIX", "")
 LIB = os.path.join(HERE, "libpclseg%s.so" % _SUFFIX)
 OBJ_DIR = os.path.join(HERE, "build%s" % _SUFFIX)
-SOURCES = ["error.cu", "projection.cu", "head.cu", "input_stage.cu", "confusion.cu", "nn_kernels.cu", "conv_tc.cu",
+SOURCES = ["error.cu", "projection.cu", "head.cu", "input_stage.cu", "confusion.cu", "validation.cu", "nn_kernels.cu", "conv_tc.cu",
            "conv_head.cu", "pool_conv.cu", "squeeze_upconv.cu", "net.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]

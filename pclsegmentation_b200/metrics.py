@@ -37,21 +37,24 @@ class MeanIoU:
     if label.numel() != pred.numel():
       raise ValueError("label and prediction sizes differ: %d vs %d" % (label.numel(), pred.numel()))
     if sample_weight is not None:
-      # test_step (nets/SegmentationNetwork.py:129): tf.math.confusion_matrix(..., weights=w) sums the weights per cell.
-      # Not on the inference hot path: float64 accumulation with torch.bincount on the device.
-      w = to_device(sample_weight, torch.float32).reshape(-1).to(torch.float64)
+      # test_step (nets/SegmentationNetwork.py:129): tf.math.confusion_matrix(..., weights=w) sums the weights per cell
+      # (float64 shared-memory histogram, csrc/validation.cu)
+      w = to_device(sample_weight, torch.float32).reshape(-1)
       if w.numel() != label.numel():
         raise ValueError("weights and label sizes differ: %d vs %d" % (w.numel(), label.numel()))
-      nc = self.num_classes
-      ok = (label >= 0) & (label < nc) & (pred >= 0) & (pred < nc)
-      idx = label.to(torch.int64) * nc + pred.to(torch.int64)
-      if self._cmw is None:
-        self._cmw = torch.zeros((nc, nc), dtype=torch.float64, device=cm.device)
-      self._cmw += torch.bincount(idx[ok], weights=w[ok], minlength=nc * nc).reshape(nc, nc)
-      self._dropped += (~ok).sum()
+      _lib.check(_lib.load().pcls_validation_update(None, ptr(label), ptr(pred), None, ptr(w), label.numel(),
+                                                    self.num_classes, 0, 0.0, 0.0, None, ptr(self.weighted_cm()),
+                                                    ptr(self._dropped), stream_handle()), "pcls_validation_update")
       return
     _lib.check(_lib.load().pcls_confusion_update(ptr(label), ptr(pred), label.numel(), self.num_classes, ptr(cm),
                                                  ptr(self._dropped), stream_handle()), "pcls_confusion_update")
+
+  def weighted_cm(self):
+    """The float64 [NC,NC] matrix of weighted updates (created on first use)."""
+    cm = self._ensure()
+    if self._cmw is None:
+      self._cmw = torch.zeros((self.num_classes, self.num_classes), dtype=torch.float64, device=cm.device)
+    return self._cmw
 
   @property
   def total_cm(self):

@@ -298,41 +298,56 @@ class PCLSegmentationNetwork:
     (lidar_input, lidar_mask), _, _ = data
     return self([lidar_input, lidar_mask], training=False)
 
-  # ---- validation-side losses (forward only; nets/SegmentationNetwork.py:71-91, :49).  Not on the inference hot path:
-  # a handful of elementwise torch ops on the device tensors the forward produced. ----
+  # ---- validation side, forward only (nets/SegmentationNetwork.py:71-91, :49, :118-131): one kernel
+  # (csrc/validation.cu, pcls_validation_update) reads the forward's outputs once and accumulates the loss sums and the
+  # class-weighted confusion matrix in float64 ----
+  def _validation_update(self, loss_kind, probabilities, label, lidar_mask=None, weight=None, predictions=None, cm=None,
+                         dropped=None):
+    """-> float64 CUDA tensor [2] = (loss numerator, loss denominator) of this call."""
+    nc = self.NUM_CLASS
+    probs = _dev(probabilities, torch.float32).reshape(-1, nc).contiguous()
+    y = _dev(label, torch.int32).reshape(-1).contiguous()
+    n = y.numel()
+    if probs.shape[0] != n:
+      raise ValueError("label and probabilities sizes differ: %d vs %d" % (n, probs.shape[0]))
+    m = None if lidar_mask is None else _dev(lidar_mask, torch.uint8).reshape(-1).contiguous()
+    w = None if weight is None else _dev(weight, torch.float32).reshape(-1).contiguous()
+    q = None if predictions is None else _dev(predictions, torch.int32).reshape(-1).contiguous()
+    for name, t in (("mask", m), ("weight", w), ("predictions", q)):
+      if t is not None and t.numel() != n:
+        raise ValueError("%s and label sizes differ: %d vs %d" % (name, t.numel(), n))
+    acc = torch.zeros(2, dtype=torch.float64, device=y.device)
+    _lib.check(_lib.load().pcls_validation_update(ptr(probs), ptr(y), ptr(q), ptr(m), ptr(w), n, nc, loss_kind,
+                                                  float(self.mc.DENOM_EPSILON), float(self.mc.FOCAL_GAMMA), ptr(acc),
+                                                  ptr(cm), ptr(dropped), stream_handle()), "pcls_validation_update")
+    return acc
+
   def focal_loss(self, probabilities, lidar_mask, label, loss_weight):
     """sum((1 - p)^gamma * onehot * -log(p) * w * mask) / sum(mask) * CLS_LOSS_COEF with p = probabilities +
     DENOM_EPSILON (nets/SegmentationNetwork.py:71-91)."""
-    nc = self.NUM_CLASS
-    prob = _dev(probabilities, torch.float32).reshape(-1, nc) + float(self.mc.DENOM_EPSILON)
-    mask = _dev(lidar_mask, torch.float32).reshape(-1, 1)
-    onehot = torch.nn.functional.one_hot(_dev(label, torch.int64).reshape(-1), nc).to(torch.float32)
-    ce = onehot * -torch.log(prob) * _dev(loss_weight, torch.float32).reshape(-1, 1) * mask
-    fl = (1.0 - prob) ** float(self.mc.FOCAL_GAMMA) * ce
-    return fl.sum() / mask.sum() * float(self.mc.CLS_LOSS_COEF)
+    acc = self._validation_update(1, probabilities, label, lidar_mask, loss_weight)
+    return acc[0] / acc[1] * float(self.mc.CLS_LOSS_COEF)
 
   def scc_loss(self, label, probabilities, weight):
     """tf.keras.losses.SparseCategoricalCrossentropy() on probabilities with sample weights (:49, :125): Keras clips
     the probabilities to [1e-7, 1 - 1e-7], takes -log_softmax(log p)[label] (i.e. renormalises the clipped row),
     multiplies by the weight and averages over ALL elements (SUM_OVER_BATCH_SIZE)."""
-    nc = self.NUM_CLASS
-    p = _dev(probabilities, torch.float32).reshape(-1, nc).clamp(1e-7, 1.0 - 1e-7)
-    logp = torch.log(p) - torch.log(p.sum(dim=1, keepdim=True))
-    picked = logp.gather(1, _dev(label, torch.int64).reshape(-1, 1)).reshape(-1)
-    return (-picked * _dev(weight, torch.float32).reshape(-1)).sum() / picked.numel()
+    acc = self._validation_update(2, probabilities, label, None, weight)
+    return acc[0] / acc[1]
 
   def test_step(self, data):
-    """Forward, loss and weighted MeanIoU update (nets/SegmentationNetwork.py:118-131)."""
+    """Forward, loss and weighted MeanIoU update (nets/SegmentationNetwork.py:118-131): the forward, then ONE kernel
+    over its outputs for the loss sums and the weighted confusion matrix."""
     (lidar_input, lidar_mask), label, weight = data
     probabilities, predictions = self([lidar_input, lidar_mask], training=False)
-    if self.mc.USE_FOCAL_LOSS:
-      loss = self.focal_loss(probabilities, lidar_mask, label, weight)
-    else:
-      loss = self.scc_loss(label, probabilities, weight)
+    focal = bool(self.mc.USE_FOCAL_LOSS)
+    tracker = self.miou_tracker
+    acc = self._validation_update(1 if focal else 2, probabilities, label, lidar_mask if focal else None, weight,
+                                  predictions, tracker.weighted_cm(), tracker._dropped)
+    loss = acc[0] / acc[1] * (float(self.mc.CLS_LOSS_COEF) if focal else 1.0)
     self._loss_sum += float(loss)
     self._loss_count += 1
-    self.miou_tracker.update_state(label, predictions, weight)
-    return {'loss': np.float32(self._loss_sum / self._loss_count), 'miou': self.miou_tracker.result()}
+    return {'loss': np.float32(self._loss_sum / self._loss_count), 'miou': tracker.result()}
 
   @property
   def metrics(self):

@@ -187,3 +187,60 @@ def test_cast_f64_f32_is_numpy_astype(n):
   if n > 0:
     t = samples_to_device(x.reshape(1, 1, 1, n))
     assert t.dtype == torch.float32 and np.array_equal(t.cpu().numpy().reshape(-1).view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,nc", [(32 * 240 * 2 + 5, 11), (64 * 2048 + 1, 20), (31, 3), (1, 32), (0, 11)])
+def test_validation_kernel_against_float64_numpy(n, nc):
+  """pcls_validation_update (csrc/validation.cu): focal / sparse-CE loss sums and the weighted confusion matrix in one
+  pass, vs float64 numpy on the same float32 inputs; out-of-range labels / predictions (a zero one-hot row, a dropped
+  pair), ragged sizes, absent mask / weights."""
+  from pclsegmentation_b200 import _lib
+  lib = _lib.load()
+  rng = np.random.default_rng(n + nc)
+  logits = rng.normal(0, 3, (n, nc)).astype(np.float32)
+  e = np.exp(logits - logits.max(1, keepdims=True)) if n else logits
+  probs = (e / e.sum(1, keepdims=True)).astype(np.float32) if n else logits
+  label = rng.integers(0, nc, n).astype(np.int32)
+  pred = rng.integers(0, nc, n).astype(np.int32)
+  if n > 8:
+    label[3], pred[5], label[7] = nc, -1, -2
+  mask = (rng.random(n) < 0.7).astype(np.uint8)
+  weight = rng.uniform(0.2, 3.0, n).astype(np.float32)
+  eps, gamma = 1e-12, 2.0
+  s = torch.cuda.current_stream().cuda_stream
+  d = lambda a: torch.from_numpy(a).cuda()
+  P, Y, Q, M, Wt = d(probs), d(label), d(pred), d(mask), d(weight)
+
+  def run(kind, use_mask, use_w, with_cm):
+    acc = torch.zeros(2, dtype=torch.float64, device="cuda")
+    cm = torch.zeros((nc, nc), dtype=torch.float64, device="cuda") if with_cm else None
+    dropped = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _lib.check(lib.pcls_validation_update(P.data_ptr(), Y.data_ptr(), Q.data_ptr() if with_cm else None,
+                                          M.data_ptr() if use_mask else None, Wt.data_ptr() if use_w else None, n, nc, kind,
+                                          eps, gamma, acc.data_ptr(), cm.data_ptr() if with_cm else None, dropped.data_ptr(),
+                                          s), "pcls_validation_update")
+    return acc.cpu().numpy(), None if cm is None else cm.cpu().numpy(), int(dropped.item())
+
+  p64, w64 = probs.astype(np.float64), weight.astype(np.float64)
+  ok_y = (label >= 0) & (label < nc)
+  yc = np.where(ok_y, label, 0)
+  rows = np.arange(n)
+  for use_mask in (True, False):
+    for use_w in (True, False):
+      m = mask.astype(np.float64) if use_mask else np.ones(n)
+      w = w64 if use_w else np.ones(n)
+      # focal: p = float32(probs + eps) like the TF graph
+      pe = (probs[rows, yc] + np.float32(eps)).astype(np.float64) if n else np.zeros(0)
+      num = ((1.0 - pe) ** gamma * -np.log(pe) * w * m * ok_y).sum()
+      acc, cm, dr = run(1, use_mask, use_w, True)
+      assert abs(acc[0] - num) <= 2e-6 * max(1.0, abs(num)) and acc[1] == m.sum()
+      okp = ok_y & (pred >= 0) & (pred < nc)
+      ref = np.zeros((nc, nc))
+      np.add.at(ref, (label[okp], pred[okp]), w[okp])
+      assert np.allclose(cm, ref, rtol=1e-12, atol=1e-9) and dr == int((~okp).sum())
+      # sparse CE
+      pc = np.clip(p64, 1e-7, 1 - 1e-7)
+      num = (-(np.log(pc[rows, yc]) - np.log(pc.sum(1))) * w * ok_y).sum() if n else 0.0
+      acc, _, _ = run(2, False, use_w, False)
+      assert abs(acc[0] - num) <= 2e-6 * max(1.0, abs(num)) and acc[1] == n
