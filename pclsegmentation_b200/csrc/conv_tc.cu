@@ -134,6 +134,23 @@ template <> __device__ __forceinline__ uint32_t pack2_relu<__nv_bfloat16>(float 
   return d;
 }
 
+// packed 16-bit add (one instruction per two outputs)
+template <typename T> __device__ __forceinline__ uint32_t add2_16(uint32_t a, uint32_t b);
+template <> __device__ __forceinline__ uint32_t add2_16<__half>(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+template <> __device__ __forceinline__ uint32_t add2_16<__nv_bfloat16>(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+
+#ifndef PCLS_TC_PACKED_SKIP
+#define PCLS_TC_PACKED_SKIP 1
+#endif
+
 // 8 accumulator columns (the bias is already in them: the epilogue pre-loads every TMEM accumulator with the bias row
 // before its MMAs run, see preload_bias) -> activation, +residuals -> one 16-byte vector of 16-bit outputs.
 // Without residuals ReLU rides in the float -> 16-bit conversion: 4 instructions per 8 outputs.  With residuals
@@ -155,6 +172,34 @@ __device__ __forceinline__ int4 epilogue_vec8(const uint32_t* acc, const float* 
                             __uint_as_float(acc[4]), __uint_as_float(acc[5]), __uint_as_float(acc[6]), __uint_as_float(acc[7])};
         o = pack8<T>(f);
       }
+      return o;
+    }
+  }
+  if constexpr (PCLS_TC_PACKED_SKIP && !LEAKY) {
+    // ReLU + ONE skip tensor (the FireDeconv expands of SqueezeSegV2: x = relu(bn(conv)) + skip): the activation value is
+    // rounded to 16 bits by the converting ReLU and the skip is added with packed 16-bit adds - 8 + 4 + 4 instructions per
+    // 8 outputs instead of 8 + 8 + 8 (unpack) + 8 + 4; one more 16-bit rounding than the float32 add.  ncu source view of
+    // fire13's expand: the epilogue warps (two per scheduler) run a serial chain at ~7 cycles per instruction, 80 % of
+    // their samples are wait / selected / short_sb / no_inst / branch_resolving - the instruction count IS the run time:
+    // 0.284 -> 0.269 ms.  (Also tried: the bias through one extra K = 16 MMA per pixel block, ones x (hi, lo) bias tile -
+    // correct, but 3 % slower: the accumulator's MMAs sit on the critical path of its epilogue group.)
+    if (has_r0 && !has_r1 && lo == 0.0f) {
+      float v[8];
+      if constexpr (BIAS) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias8 + 4);
+        v[0] = __uint_as_float(acc[0]) + b0.x; v[1] = __uint_as_float(acc[1]) + b0.y; v[2] = __uint_as_float(acc[2]) + b0.z;
+        v[3] = __uint_as_float(acc[3]) + b0.w; v[4] = __uint_as_float(acc[4]) + b1.x; v[5] = __uint_as_float(acc[5]) + b1.y;
+        v[6] = __uint_as_float(acc[6]) + b1.z; v[7] = __uint_as_float(acc[7]) + b1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[j]);
+      }
+      int4 o;
+      o.x = (int)add2_16<T>(pack2_relu<T>(v[0], v[1]), (uint32_t)r0.x);
+      o.y = (int)add2_16<T>(pack2_relu<T>(v[2], v[3]), (uint32_t)r0.y);
+      o.z = (int)add2_16<T>(pack2_relu<T>(v[4], v[5]), (uint32_t)r0.z);
+      o.w = (int)add2_16<T>(pack2_relu<T>(v[6], v[7]), (uint32_t)r0.w);
       return o;
     }
   }
@@ -630,18 +675,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const unsigned long long _te = dbg ? clk() : 0ull;
       tc_fence_after();
       if (res_smem) cp_async_wait_all();
-      // one 32-column chunk: TMEM -> registers -> 4 output vectors, handed to `sink(g, vector)`
-      auto chunk = [&](int cc, auto&& sink) {
-        uint32_t v[32];
-        if (cc + 32 <= BN) {
-          tmem_ld32(t_row + (uint32_t)cc, v);
-        } else {  // BN % 32 == 16 tail
-          uint32_t v16[16];
-          tmem_ld16(t_row + (uint32_t)cc, v16);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0u; }
-        }
-        tmem_ld_wait();
+      // one 32-column chunk of accumulator registers -> 4 output vectors, handed to `sink(g, vector)`
+      auto process = [&](const uint32_t* v, int cc, auto&& sink) {
         if constexpr (RES) {
           if (res_smem && cc > 0 && (cc & 63) == 0) { prefetch_r0(cc); cp_async_wait_all(); }  // next 64-column batch
         }
@@ -655,6 +690,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           sink(g, epilogue_vec8<T, LEAKY, !PRELOAD>(v + g * 8, bias_s + n0 + cc + g * 8, act_lo, RES && has_r0, r0v, RES && has_r1, r1[g]));
         }
         if (reg_res && cc + 32 < BN) load_r1(cc + 32);
+      };
+      // TMEM -> registers -> process, one chunk at a time (direct-store path)
+      auto chunk = [&](int cc, auto&& sink) {
+        uint32_t v[32];
+        if (cc + 32 <= BN) {
+          tmem_ld32(t_row + (uint32_t)cc, v);
+        } else {  // BN % 32 == 16 tail
+          uint32_t v16[16];
+          tmem_ld16(t_row + (uint32_t)cc, v16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { v[j] = v16[j]; v[16 + j] = 0u; }
+        }
+        tmem_ld_wait();
+        process(v, cc, sink);
+      };
+      // hands the accumulator back to the MMA issuer (PRELOAD: after writing the next tile's bias row into it)
+      bool released = false;
+      auto release_acc = [&]() {
+        released = true;
+        if constexpr (PRELOAD) {
+          preload_bias(acc, tile_at(tl + n_acc));
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(TEMPTY_BAR(acc));
+        }
       };
       if (out_f32) {
         // float32 logits (conv14 / head layer), cout <= 32.  With the fused head the softmax / argmax / mask of
@@ -755,7 +816,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       } else if (tma_store) {
         // ---- TMEM -> registers -> swizzled smem tile -> TMA bulk tensor store (full lines, edges clipped by TMA) ----
-        // blocks of 64 channels (128-byte rows, SWIZZLE_128B)
+        // blocks of 64 channels (128-byte rows, SWIZZLE_128B).  The accumulator reads are double-buffered: the tcgen05.ld
+        // of chunk c + 1 is in flight while chunk c is processed, and the accumulator goes back to the MMA issuer as soon
+        // as its LAST chunk sits in registers - one chunk of processing (1/8 of the drain of a 256-column tile) earlier,
+        // which covers the ~2000 cycles the next tile's MMAs take (n_acc = 2 with two groups: each group waits for ITS
+        // accumulator, so that latency sat on the group's critical path: wait-tfull was 10-12 % of fire11-13's expands).
+        // (Not for the residual kernels of the plain view - fire10's N-split expand, Darknet's blocks: 168 registers are
+        // the cap, the second buffer spills there: fire10 0.170 -> 0.186 ms.)
+        constexpr bool DBUF = !(RES && G == 1);
+        uint32_t va[32], vb[DBUF ? 32 : 1];
+        if constexpr (DBUF) tmem_ld32(t_row, va);
         for (int cb = 0; cb < BN; cb += 64, ++blk) {
           uint32_t buf;
           if (res_tma) {
@@ -780,13 +850,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const bool narrow = !RES && BN - cb < 64;
           const uint32_t row_addr = buf + (uint32_t)(m * (narrow ? 64 : 128));
           res_row = row_addr;
-          if (narrow) {
-            chunk(cb, [&](int g, const int4& o) { st_shared_v4(row_addr + (uint32_t)((g ^ ((m >> 1) & 3)) << 4), o); });
-          } else {
+          if constexpr (!DBUF) {
 #pragma unroll 1
             for (int ci = 0; ci < 2; ++ci)
               chunk(cb + ci * 32, [&](int g, const int4& o) {
                 st_shared_v4(row_addr + (uint32_t)(((ci * 4 + g) ^ (m & 7)) << 4), o); });
+          } else if (narrow) {   // (always the last block of the tile)
+            tmem_ld_wait();
+            release_acc();
+            process(va, cb, [&](int g, const int4& o) { st_shared_v4(row_addr + (uint32_t)((g ^ ((m >> 1) & 3)) << 4), o); });
+          } else {
+            tmem_ld_wait();
+            tmem_ld32(t_row + (uint32_t)(cb + 32), vb);
+            process(va, cb, [&](int g, const int4& o) { st_shared_v4(row_addr + (uint32_t)((g ^ (m & 7)) << 4), o); });
+            tmem_ld_wait();
+            if (cb + 64 < BN) tmem_ld32(t_row + (uint32_t)(cb + 64), va);
+            else release_acc();
+            process(vb, cb + 32, [&](int g, const int4& o) { st_shared_v4(row_addr + (uint32_t)(((4 + g) ^ (m & 7)) << 4), o); });
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> visible to the TMA engine
           if (!res_tma) { DBG_T0; if (issuer) bulk_wait_read0(); DBG_ADD(4); }   // store k-1 has finished reading the OTHER buffer
@@ -808,13 +888,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (off >= 0) *reinterpret_cast<int4*>(outp + off) = o;
           });
       }
-      if constexpr (PRELOAD) {
-        preload_bias(acc, tile_at(tl + n_acc));   // (+ hands the accumulator back to the MMA issuer)
-      } else {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(TEMPTY_BAR(acc));
-      }
+      if (!released) release_acc();
       if (dbg) { dbg_acc[6] += clk() - _te; dbg_acc[7] += 1; }
     }
     if (p.tma_store && q == 2 && lane == 0) bulk_wait_all();  // smem must outlive the last stores
