@@ -656,7 +656,7 @@ def run_ours(args):
     "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
     "dtype": "f16 storage / f32 accumulate", "data": "synthetic",
     "config": {"workload": args.workload, "per_gpu_batch": B, "global_batch": B * world, "H": H, "W": W,
-               "input": "raw [B,H,W,5] f32 resident in HBM; input stage (mask / normalise) inside pcls_net_forward",
+               "input": "raw [B,H,W,5] f32 resident in HBM; input stage (mask / normalise) inside pcls_net_forward (its own kernel)",
                "outputs": "predictions i32 + probabilities f32",
                "weights": "Keras-default init seed 0 + randomised BN", "l2_policy":
                "inputs rotate over %d resident batches (%.0f MB) and each step streams > 1 GB of activations, far above "

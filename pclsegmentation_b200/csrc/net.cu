@@ -875,7 +875,16 @@ extern "C" int pcls_net_op_info(const pcls_net* net, int i, char* h_name, int* f
 extern "C" int pcls_net_launches_per_forward(const pcls_net* net) {
   const Net* n = reinterpret_cast<const Net*>(net);
   if (!n) return 0;
-  return (int)n->ops.size() + 2;  // + input kernel + head kernel (per pass)
+  // kernels one pass really launches: the input kernel, every op that is not folded into a neighbour (squeeze convs
+  // computed by the transposed conv behind them, max-pools computed by the 1x1 conv behind them), and the standalone
+  // head kernel unless the logits layer runs it in its epilogue
+  int launches = 1;
+  for (const OpRef& op : n->ops) {
+    if (op.type == OP_CONV && n->conv_impl == 0 && n->convs[op.index].fused_into_up >= 0) continue;
+    if (op.type == OP_POOL && n->conv_impl == 0 && n->pools[op.index].fused_conv >= 0) continue;
+    ++launches;
+  }
+  return launches + (n->head_is_fused() ? 0 : 1);
 }
 
 extern "C" int64_t pcls_net_workspace_bytes(const pcls_net* net) {
