@@ -231,7 +231,11 @@ __device__ __forceinline__ int4 epilogue_vec8(const uint32_t* acc, const float* 
   return pack8<T>(v);
 }
 
-template <typename T, int KC, int SUB, int G, bool RES, bool LEAKY, int KS = KC / 16>
+// RM = 1: the residual kernel specialised at compile time for ONE skip tensor that is TMA-loaded into the output staging
+// buffers, TMA-store epilogue, ReLU (the FireDeconv expands of SqueezeSegV2).  The generic residual kernel carries the
+// code of every residual mode (cp.async staging, per-chunk LDG, second residual) behind run-time flags that are tested per
+// 8 outputs; the epilogue's instruction chain is what bounds these layers.
+template <typename T, int KC, int SUB, int G, bool RES, bool LEAKY, int KS = KC / 16, int RM = 0>
 __global__ void __launch_bounds__(tc_threads(RES), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
@@ -239,6 +243,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const __grid_constant__ TcParams p, const int num_tiles) {
   constexpr bool PRELOAD = !RES;   // bias pre-loaded into the TMEM accumulators (see preload_bias)
   constexpr int TC_NG = tc_ng(RES);
+  constexpr bool RTMA = RES && RM == 1;
   extern __shared__ uint8_t smem_raw[];
   // carve: [stages x (A tile | B tiles)] 1024-aligned, resident weights, barriers, TMEM base slot, bias
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -526,12 +531,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int blk_shift = p.cout_blk_shift;              // pixel-group view: column n -> pixel n >> blk_shift
     const int blk_mask = G > 1 ? (1 << blk_shift) - 1 : -1;
     const float slope = p.act == PCLS_ACT_RELU ? 0.0f : (p.act == PCLS_ACT_LEAKY ? 0.1f : 1.0f);   // (float32 logits path)
-    const float act_lo = p.act == PCLS_ACT_RELU ? 0.0f : -INFINITY;
+    const float act_lo = (RTMA || p.act == PCLS_ACT_RELU) ? 0.0f : -INFINITY;
     const uint16_t* res0 = reinterpret_cast<const uint16_t*>(p.res0);
     const uint16_t* res1 = reinterpret_cast<const uint16_t*>(p.res1);
     const int res0_channels = p.res0_channels, res1_channels = p.res1_channels;
-    const bool has_r0 = res0 != nullptr, has_r1 = res1 != nullptr;
-    const bool tma_store = p.tma_store != 0, out_f32 = p.out_f32 != 0, c_is_5d = p.c_is_5d != 0;
+    const bool has_r0 = RTMA || res0 != nullptr, has_r1 = !RTMA && res1 != nullptr;
+    const bool tma_store = RTMA || p.tma_store != 0, out_f32 = !RTMA && p.out_f32 != 0, c_is_5d = p.c_is_5d != 0;
     const uint32_t c_stage_bytes = (uint32_t)p.c_stage_bytes;
     T* const outp = reinterpret_cast<T*>(p.out);
     const bool issuer = (q == 2) && lane == 0;            // first warp of the group (warp 2 or 6) issues the TMA stores
@@ -638,8 +643,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // The second residual (Darknet decoder only, compute-bound layers) is fetched one chunk ahead.
       const uint32_t rslot = rstage_base + (uint32_t)grp * 16384u + (uint32_t)(m & 127) * 16u;  // + i * 2048 per vector
       int4 r0[4], r1[4];
-      const bool res_smem = RES && p.res_smem != 0 && has_r0;
-      const bool res_tma = RES && p.res_tma != 0 && has_r0;
+      const bool res_smem = !RTMA && RES && p.res_smem != 0 && has_r0;
+      const bool res_tma = RTMA || (RES && p.res_tma != 0 && has_r0);
       uint32_t res_row = 0;     // res_tma: this thread's row of the staging buffer that holds the residual block
       auto prefetch_r0 = [&](int cs) {
         if constexpr (RES) {
@@ -940,7 +945,16 @@ static TcKernelFn tc_kernel_for_tt(int KC, int SUB, int G, int res, int leaky) {
 static bool tc_kskip_kernel(int KC, int SUB, int G, int res, int leaky, int ks) {
   return ks == 3 && KC == 64 && SUB == 3 && G == 1 && !res && !leaky;
 }
-static TcKernelFn tc_kernel_for(int KC, int SUB, int G, int is_bf16, int res, int leaky, int ks = 0) {
+// the compile-time specialised residual kernel (RM = 1) exists for the shapes of SqueezeSegV2's FireDeconv expands
+static bool tc_rtma_kernel(int KC, int SUB, int G, int res, int leaky, int rtma) {
+  return rtma && res && !leaky && KC == 64 && SUB == 3 && (G == 1 || G == 2 || G == 4);
+}
+static TcKernelFn tc_kernel_for(int KC, int SUB, int G, int is_bf16, int res, int leaky, int ks = 0, int rtma = 0) {
+  if (tc_rtma_kernel(KC, SUB, G, res, leaky, rtma)) {
+    if (G == 4) return is_bf16 ? conv_tc_kernel<__nv_bfloat16, 64, 3, 4, true, false, 4, 1> : conv_tc_kernel<__half, 64, 3, 4, true, false, 4, 1>;
+    if (G == 2) return is_bf16 ? conv_tc_kernel<__nv_bfloat16, 64, 3, 2, true, false, 4, 1> : conv_tc_kernel<__half, 64, 3, 2, true, false, 4, 1>;
+    return is_bf16 ? conv_tc_kernel<__nv_bfloat16, 64, 3, 1, true, false, 4, 1> : conv_tc_kernel<__half, 64, 3, 1, true, false, 4, 1>;
+  }
   if (tc_kskip_kernel(KC, SUB, G, res, leaky, ks))
     return is_bf16 ? conv_tc_kernel<__nv_bfloat16, 64, 3, 1, false, false, 3> : conv_tc_kernel<__half, 64, 3, 1, false, false, 3>;
   return is_bf16 ? tc_kernel_for_tt<__nv_bfloat16>(KC, SUB, G, res, leaky) : tc_kernel_for_tt<__half>(KC, SUB, G, res, leaky);
@@ -990,6 +1004,7 @@ int make_map(CUtensorMap* map, bool bf16, void* base, int rank, const uint64_t* 
 }
 
 // A/B switches for measurement (pcls_net_set_option before finalize): halo reuse, resident weights, base offset
+int tc_rtma_mode = 1;   // A/B switch "tc_rtma"
 int tc_tma_store_mode = 1, tc_group_mode = 1, tc_res_tma_mode = 1, tc_split_mode = 1, tc_vstream_mode = 0, tc_nsplit_mode = 1;
 const int tc_debug_compiled = PCLS_TC_DEBUG;
 unsigned long long* tc_debug_buf = nullptr;  // [148][24] counters of the most recent launch when enabled
@@ -1359,8 +1374,11 @@ int Net::tc_prepare() {
               for (int lk = 0; lk < 2; ++lk)
                 PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(kc, sub, g, bf, rs, lk), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         }
-    for (int bf = 0; bf < 2; ++bf)
+    for (int bf = 0; bf < 2; ++bf) {
       PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(64, 3, 1, bf, 0, 0, 3), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      for (int g = 1; g <= 4; g *= 2)
+        PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(64, 3, g, bf, 1, 0, 0, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    }
     attr_set = true;
   }
   return PCLS_OK;
@@ -1389,7 +1407,10 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
   }
   int grid = work < sm_count() ? work : sm_count();
   if (prm.nsplit) grid -= grid % prm.n_nt;   // every CTA sees one N tile only (tile % n_nt == blockIdx.x % n_nt)
-  PCLS_CHECK_CUDA(launch_pdl(tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0, prm.act == PCLS_ACT_LEAKY ? 1 : 0, prm.ksteps),
+  // one skip tensor, TMA-loaded into the staging buffers, TMA-store epilogue, ReLU: the specialised residual kernel
+  const int rtma = (tc_rtma_mode && prm.res_tma && prm.res0 && !prm.res1 && prm.tma_store && !prm.out_f32 && prm.act == PCLS_ACT_RELU &&
+                    !(PCLS_TC_VSTREAM && prm.vstream)) ? 1 : 0;
+  PCLS_CHECK_CUDA(launch_pdl(tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0, prm.act == PCLS_ACT_LEAKY ? 1 : 0, prm.ksteps, rtma),
                              dim3(grid), dim3(tc_threads(prm.res0 || prm.res1)), plan->smem_bytes, s,
                              plan->map_a, plan->map_b, plan->map_c, plan->map_r, plan->map_b2, plan->map_c2, prm, num_tiles));
   return check_launch("conv_tc_kernel");

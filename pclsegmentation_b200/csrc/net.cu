@@ -914,6 +914,7 @@ extern "C" int pcls_net_set_option(pcls_net* net, const char* name, int value) {
     pad48_mode = value; return PCLS_OK;
   }
   if (!strcmp(name, "tc_halo")) { tc_halo_mode = value; return PCLS_OK; }
+  if (!strcmp(name, "tc_rtma")) { tc_rtma_mode = value; n->drop_graphs(); return PCLS_OK; }
   if (!strcmp(name, "tc_tma_store")) { tc_tma_store_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_group")) { tc_group_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_res_tma")) { tc_res_tma_mode = value; return PCLS_OK; }

@@ -17,7 +17,7 @@ struct TensorInfo {
 struct TcPlan;    // tcgen05 launch plan of one conv layer (conv_tc.cu)
 struct HeadPlan;  // launch plan of the logits layer + fused segmentation head (conv_head.cu)
 extern int tc_head_mode;
-extern int tc_halo_mode, tc_resident_mode, tc_base_offset_mode, tc_tma_store_mode, tc_group_mode, tc_res_tma_mode, tc_split_mode, tc_vstream_mode, tc_nsplit_mode;
+extern int tc_rtma_mode, tc_halo_mode, tc_resident_mode, tc_base_offset_mode, tc_tma_store_mode, tc_group_mode, tc_res_tma_mode, tc_split_mode, tc_vstream_mode, tc_nsplit_mode;
 extern int pad48_mode;  // 48-channel tensors written by one conv are stored with a 64-channel pixel stride (zero pads)
 extern const int tc_debug_compiled;
 extern unsigned long long* tc_debug_buf;  // A/B measurement switches (process-wide)
