@@ -244,6 +244,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   constexpr bool PRELOAD = !RES;   // bias pre-loaded into the TMEM accumulators (see preload_bias)
   constexpr int TC_NG = tc_ng(RES);
   constexpr bool RTMA = RES && RM == 1;
+  constexpr bool PTMA = !RES && RM == 2;   // no residual, 16-bit outputs through the TMA-store epilogue (known at compile time)
   extern __shared__ uint8_t smem_raw[];
   // carve: [stages x (A tile | B tiles)] 1024-aligned, resident weights, barriers, TMEM base slot, bias
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -536,7 +537,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint16_t* res1 = reinterpret_cast<const uint16_t*>(p.res1);
     const int res0_channels = p.res0_channels, res1_channels = p.res1_channels;
     const bool has_r0 = RTMA || res0 != nullptr, has_r1 = !RTMA && res1 != nullptr;
-    const bool tma_store = RTMA || p.tma_store != 0, out_f32 = !RTMA && p.out_f32 != 0, c_is_5d = p.c_is_5d != 0;
+    const bool tma_store = RTMA || PTMA || p.tma_store != 0, out_f32 = !RTMA && !PTMA && p.out_f32 != 0, c_is_5d = p.c_is_5d != 0;
     const uint32_t c_stage_bytes = (uint32_t)p.c_stage_bytes;
     T* const outp = reinterpret_cast<T*>(p.out);
     const bool issuer = (q == 2) && lane == 0;            // first warp of the group (warp 2 or 6) issues the TMA stores
@@ -949,7 +950,21 @@ static bool tc_kskip_kernel(int KC, int SUB, int G, int res, int leaky, int ks) 
 static bool tc_rtma_kernel(int KC, int SUB, int G, int res, int leaky, int rtma) {
   return rtma && res && !leaky && KC == 64 && SUB == 3 && (G == 1 || G == 2 || G == 4);
 }
+// RM = 2: kernels without residuals whose 16-bit outputs leave through the TMA-store epilogue (every SqueezeSegV2 layer
+// of that kind): the float32 logits / fused-head path and the direct-store path are compiled out
+template <typename T>
+static TcKernelFn tc_ptma_kernel_for(int KC, int SUB, int G, int ks) {
+  if (ks == 3 && KC == 64 && SUB == 3 && G == 1) return conv_tc_kernel<T, 64, 3, 1, false, false, 3, 2>;
+  if (G == 4) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 4, false, false, 4, 2> : conv_tc_kernel<T, 64, 1, 4, false, false, 4, 2>;
+  if (G == 2) {
+    if (KC == 64) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 2, false, false, 4, 2> : conv_tc_kernel<T, 64, 1, 2, false, false, 4, 2>;
+    return SUB == 3 ? conv_tc_kernel<T, 32, 3, 2, false, false, 2, 2> : conv_tc_kernel<T, 32, 1, 2, false, false, 2, 2>;
+  }
+  if (SUB == 3) return KC == 64 ? conv_tc_kernel<T, 64, 3, 1, false, false, 4, 2> : KC == 32 ? conv_tc_kernel<T, 32, 3, 1, false, false, 2, 2> : conv_tc_kernel<T, 16, 3, 1, false, false, 1, 2>;
+  return KC == 64 ? conv_tc_kernel<T, 64, 1, 1, false, false, 4, 2> : KC == 32 ? conv_tc_kernel<T, 32, 1, 1, false, false, 2, 2> : conv_tc_kernel<T, 16, 1, 1, false, false, 1, 2>;
+}
 static TcKernelFn tc_kernel_for(int KC, int SUB, int G, int is_bf16, int res, int leaky, int ks = 0, int rtma = 0) {
+  if (rtma == 2 && !res && !leaky && !is_bf16) return tc_ptma_kernel_for<__half>(KC, SUB, G, ks);
   if (tc_rtma_kernel(KC, SUB, G, res, leaky, rtma)) {
     if (G == 4) return is_bf16 ? conv_tc_kernel<__nv_bfloat16, 64, 3, 4, true, false, 4, 1> : conv_tc_kernel<__half, 64, 3, 4, true, false, 4, 1>;
     if (G == 2) return is_bf16 ? conv_tc_kernel<__nv_bfloat16, 64, 3, 2, true, false, 4, 1> : conv_tc_kernel<__half, 64, 3, 2, true, false, 4, 1>;
@@ -1004,7 +1019,7 @@ int make_map(CUtensorMap* map, bool bf16, void* base, int rank, const uint64_t* 
 }
 
 // A/B switches for measurement (pcls_net_set_option before finalize): halo reuse, resident weights, base offset
-int tc_rtma_mode = 1;   // A/B switch "tc_rtma"
+int tc_rtma_mode = 3;   // A/B switch "tc_rtma"
 int tc_tma_store_mode = 1, tc_group_mode = 1, tc_res_tma_mode = 1, tc_split_mode = 1, tc_vstream_mode = 0, tc_nsplit_mode = 1;
 const int tc_debug_compiled = PCLS_TC_DEBUG;
 unsigned long long* tc_debug_buf = nullptr;  // [148][24] counters of the most recent launch when enabled
@@ -1378,6 +1393,13 @@ int Net::tc_prepare() {
       PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(64, 3, 1, bf, 0, 0, 3), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
       for (int g = 1; g <= 4; g *= 2)
         PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(64, 3, g, bf, 1, 0, 0, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      for (int kc = 16; kc <= 64; kc *= 2)
+        for (int sub = 1; sub <= 3; sub += 2)
+          for (int g = 1; g <= 4; g *= 2) {
+            if ((g == 2 && kc < 32) || (g == 4 && kc < 64)) continue;
+            PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(kc, sub, g, bf, 0, 0, 0, 2), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+          }
+      PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(64, 3, 1, bf, 0, 0, 3, 2), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     }
     attr_set = true;
   }
@@ -1409,7 +1431,8 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
   if (prm.nsplit) grid -= grid % prm.n_nt;   // every CTA sees one N tile only (tile % n_nt == blockIdx.x % n_nt)
   // one skip tensor, TMA-loaded into the staging buffers, TMA-store epilogue, ReLU: the specialised residual kernel
   const int rtma = (tc_rtma_mode && prm.res_tma && prm.res0 && !prm.res1 && prm.tma_store && !prm.out_f32 && prm.act == PCLS_ACT_RELU &&
-                    !(PCLS_TC_VSTREAM && prm.vstream)) ? 1 : 0;
+                    !(PCLS_TC_VSTREAM && prm.vstream)) ? 1
+                 : ((tc_rtma_mode & 2) && !prm.res0 && !prm.res1 && prm.tma_store && !prm.out_f32 && !(PCLS_TC_VSTREAM && prm.vstream)) ? 2 : 0;
   PCLS_CHECK_CUDA(launch_pdl(tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0, prm.act == PCLS_ACT_LEAKY ? 1 : 0, prm.ksteps, rtma),
                              dim3(grid), dim3(tc_threads(prm.res0 || prm.res1)), plan->smem_bytes, s,
                              plan->map_a, plan->map_b, plan->map_c, plan->map_r, plan->map_b2, plan->map_c2, prm, num_tiles));
