@@ -17,8 +17,10 @@ CSRC = os.path.join(HERE, "csrc")
 _SUFFIX = os.environ.get("PCLS_LIB_SUFFIX", "")
 LIB = os.path.join(HERE, "libpclseg%s.so" % _SUFFIX)
 OBJ_DIR = os.path.join(HERE, "build%s" % _SUFFIX)
-SOURCES = ["error.cu", "projection.cu", "head.cu", "input_stage.cu", "confusion.cu", "validation.cu", "nn_kernels.cu", "conv_tc.cu",
-           "conv_head.cu", "pool_conv.cu", "squeeze_upconv.cu", "net.cu"]
+# conv_tc.cu holds ~160 kernel instantiations: it is compiled once per part (-DPCLS_TC_PART=k, see the file) in parallel
+TC_PARTS = 13
+SOURCES = [("conv_tc.cu", k) for k in range(TC_PARTS)] + ["conv_head.cu", "net.cu", "nn_kernels.cu", "pool_conv.cu", "squeeze_upconv.cu",
+           "projection.cu", "head.cu", "input_stage.cu", "confusion.cu", "validation.cu", "error.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr"]
 # development builds, e.g. PCLS_NVCC_FLAGS="-DPCLS_TC_DEBUG=1" (wait-cycle counters) or "-DPCLS_TC_VSTREAM=1"
@@ -54,8 +56,14 @@ def build(force=False, verbose=False):
   nvcc = _nvcc()
 
   def compile_one(src):
-    obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-    cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    extra = []
+    if isinstance(src, tuple):
+      src, part = src
+      obj = os.path.join(OBJ_DIR, src.replace(".cu", "_p%d.o" % part))
+      extra = ["-DPCLS_TC_PART=%d" % part]
+    else:
+      obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
       raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -63,7 +71,7 @@ def build(force=False, verbose=False):
       print(r.stdout, r.stderr)
     return obj
 
-  with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+  with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 8, len(SOURCES))) as ex:
     objs = list(ex.map(compile_one, SOURCES))
   cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]
   r = subprocess.run(cmd, capture_output=True, text=True)

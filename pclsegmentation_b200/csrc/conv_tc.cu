@@ -925,8 +925,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 typedef void (*TcKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const int);
+
+// ---------------------------------------------------------------------------------------------------------------
+// Instantiations.  ~160 kernels: the build compiles this file once per PART (-DPCLS_TC_PART=k, pclsegmentation_b200/
+// build.py) so that they compile in parallel; part 0 also holds the host code.  Without the macro (a plain `nvcc -c`)
+// everything lands in one translation unit.
+//   parts 1-8   generic kernels (RM = 0) of one (type, RES, LEAKY) combination each
+//   parts 9-12  RM = 2: no residual, 16-bit outputs through the TMA-store epilogue (the float32 logits / fused-head path
+//               and the direct-store path compiled out), one (type, LEAKY) combination each
+//   part 0      RM = 1 (one TMA-loaded skip tensor, TMA store, ReLU: the FireDeconv expands) and the K-skip kernels
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef PCLS_TC_PART
+#define PCLS_TC_PART -1
+#endif
 template <typename T, bool RES, bool LEAKY>
-static TcKernelFn tc_kernel_for_t(int KC, int SUB, int G) {
+TcKernelFn tc_kernel_for_t(int KC, int SUB, int G) {
   if (G == 4) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 4, RES, LEAKY> : conv_tc_kernel<T, 64, 1, 4, RES, LEAKY>;
   if (G == 2) {
     if (KC == 64) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 2, RES, LEAKY> : conv_tc_kernel<T, 64, 1, 2, RES, LEAKY>;
@@ -935,36 +948,103 @@ static TcKernelFn tc_kernel_for_t(int KC, int SUB, int G) {
   if (SUB == 3) return KC == 64 ? conv_tc_kernel<T, 64, 3, 1, RES, LEAKY> : KC == 32 ? conv_tc_kernel<T, 32, 3, 1, RES, LEAKY> : conv_tc_kernel<T, 16, 3, 1, RES, LEAKY>;
   return KC == 64 ? conv_tc_kernel<T, 64, 1, 1, RES, LEAKY> : KC == 32 ? conv_tc_kernel<T, 32, 1, 1, RES, LEAKY> : conv_tc_kernel<T, 16, 1, 1, RES, LEAKY>;
 }
+// ks = UMMA K steps per chunk; the one shape with a zero-padded K tail (48 channels in a 64-channel chunk: 3x3 halo
+// kernel, ReLU, no residual) has its own instantiation, every other combination issues all KC / 16 steps (a run-time
+// bound or predicate in the issue loop cost the issue-bound N-split layers 30 %).
+template <typename T, bool LEAKY>
+TcKernelFn tc_ptma_kernel_for(int KC, int SUB, int G, int ks) {
+  if constexpr (!LEAKY) {
+    if (ks == 3 && KC == 64 && SUB == 3 && G == 1) return conv_tc_kernel<T, 64, 3, 1, false, false, 3, 2>;
+  }
+  if (G == 4) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 4, false, LEAKY, 4, 2> : conv_tc_kernel<T, 64, 1, 4, false, LEAKY, 4, 2>;
+  if (G == 2) {
+    if (KC == 64) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 2, false, LEAKY, 4, 2> : conv_tc_kernel<T, 64, 1, 2, false, LEAKY, 4, 2>;
+    return SUB == 3 ? conv_tc_kernel<T, 32, 3, 2, false, LEAKY, 2, 2> : conv_tc_kernel<T, 32, 1, 2, false, LEAKY, 2, 2>;
+  }
+  if (SUB == 3) return KC == 64 ? conv_tc_kernel<T, 64, 3, 1, false, LEAKY, 4, 2> : KC == 32 ? conv_tc_kernel<T, 32, 3, 1, false, LEAKY, 2, 2> : conv_tc_kernel<T, 16, 3, 1, false, LEAKY, 1, 2>;
+  return KC == 64 ? conv_tc_kernel<T, 64, 1, 1, false, LEAKY, 4, 2> : KC == 32 ? conv_tc_kernel<T, 32, 1, 1, false, LEAKY, 2, 2> : conv_tc_kernel<T, 16, 1, 1, false, LEAKY, 1, 2>;
+}
+#if PCLS_TC_PART >= 0
+#if PCLS_TC_PART == 1
+template TcKernelFn tc_kernel_for_t<__half, false, false>(int, int, int);
+#else
+extern template TcKernelFn tc_kernel_for_t<__half, false, false>(int, int, int);
+#endif
+#if PCLS_TC_PART == 2
+template TcKernelFn tc_kernel_for_t<__half, false, true>(int, int, int);
+#else
+extern template TcKernelFn tc_kernel_for_t<__half, false, true>(int, int, int);
+#endif
+#if PCLS_TC_PART == 3
+template TcKernelFn tc_kernel_for_t<__half, true, false>(int, int, int);
+#else
+extern template TcKernelFn tc_kernel_for_t<__half, true, false>(int, int, int);
+#endif
+#if PCLS_TC_PART == 4
+template TcKernelFn tc_kernel_for_t<__half, true, true>(int, int, int);
+#else
+extern template TcKernelFn tc_kernel_for_t<__half, true, true>(int, int, int);
+#endif
+#if PCLS_TC_PART == 5
+template TcKernelFn tc_kernel_for_t<__nv_bfloat16, false, false>(int, int, int);
+#else
+extern template TcKernelFn tc_kernel_for_t<__nv_bfloat16, false, false>(int, int, int);
+#endif
+#if PCLS_TC_PART == 6
+template TcKernelFn tc_kernel_for_t<__nv_bfloat16, false, true>(int, int, int);
+#else
+extern template TcKernelFn tc_kernel_for_t<__nv_bfloat16, false, true>(int, int, int);
+#endif
+#if PCLS_TC_PART == 7
+template TcKernelFn tc_kernel_for_t<__nv_bfloat16, true, false>(int, int, int);
+#else
+extern template TcKernelFn tc_kernel_for_t<__nv_bfloat16, true, false>(int, int, int);
+#endif
+#if PCLS_TC_PART == 8
+template TcKernelFn tc_kernel_for_t<__nv_bfloat16, true, true>(int, int, int);
+#else
+extern template TcKernelFn tc_kernel_for_t<__nv_bfloat16, true, true>(int, int, int);
+#endif
+#if PCLS_TC_PART == 9
+template TcKernelFn tc_ptma_kernel_for<__half, false>(int, int, int, int);
+#else
+extern template TcKernelFn tc_ptma_kernel_for<__half, false>(int, int, int, int);
+#endif
+#if PCLS_TC_PART == 10
+template TcKernelFn tc_ptma_kernel_for<__half, true>(int, int, int, int);
+#else
+extern template TcKernelFn tc_ptma_kernel_for<__half, true>(int, int, int, int);
+#endif
+#if PCLS_TC_PART == 11
+template TcKernelFn tc_ptma_kernel_for<__nv_bfloat16, false>(int, int, int, int);
+#else
+extern template TcKernelFn tc_ptma_kernel_for<__nv_bfloat16, false>(int, int, int, int);
+#endif
+#if PCLS_TC_PART == 12
+template TcKernelFn tc_ptma_kernel_for<__nv_bfloat16, true>(int, int, int, int);
+#else
+extern template TcKernelFn tc_ptma_kernel_for<__nv_bfloat16, true>(int, int, int, int);
+#endif
+#endif  // PCLS_TC_PART >= 0
+
+#if PCLS_TC_PART <= 0   // ---- host side + the special kernels: part 0 (or the single translation unit) ----
 template <typename T>
 static TcKernelFn tc_kernel_for_tt(int KC, int SUB, int G, int res, int leaky) {
   if (res) return leaky ? tc_kernel_for_t<T, true, true>(KC, SUB, G) : tc_kernel_for_t<T, true, false>(KC, SUB, G);
   return leaky ? tc_kernel_for_t<T, false, true>(KC, SUB, G) : tc_kernel_for_t<T, false, false>(KC, SUB, G);
 }
-// ks = UMMA K steps per chunk; the one shape with a zero-padded K tail (48 channels in a 64-channel chunk: 3x3 halo
-// kernel, ReLU, no residual) has its own instantiation, every other combination issues all KC / 16 steps (a run-time
-// bound or predicate in the issue loop cost the issue-bound N-split layers 30 %).
 static bool tc_kskip_kernel(int KC, int SUB, int G, int res, int leaky, int ks) {
   return ks == 3 && KC == 64 && SUB == 3 && G == 1 && !res && !leaky;
 }
 // the compile-time specialised residual kernel (RM = 1) exists for the shapes of SqueezeSegV2's FireDeconv expands
 static bool tc_rtma_kernel(int KC, int SUB, int G, int res, int leaky, int rtma) {
-  return rtma && res && !leaky && KC == 64 && SUB == 3 && (G == 1 || G == 2 || G == 4);
-}
-// RM = 2: kernels without residuals whose 16-bit outputs leave through the TMA-store epilogue (every SqueezeSegV2 layer
-// of that kind): the float32 logits / fused-head path and the direct-store path are compiled out
-template <typename T>
-static TcKernelFn tc_ptma_kernel_for(int KC, int SUB, int G, int ks) {
-  if (ks == 3 && KC == 64 && SUB == 3 && G == 1) return conv_tc_kernel<T, 64, 3, 1, false, false, 3, 2>;
-  if (G == 4) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 4, false, false, 4, 2> : conv_tc_kernel<T, 64, 1, 4, false, false, 4, 2>;
-  if (G == 2) {
-    if (KC == 64) return SUB == 3 ? conv_tc_kernel<T, 64, 3, 2, false, false, 4, 2> : conv_tc_kernel<T, 64, 1, 2, false, false, 4, 2>;
-    return SUB == 3 ? conv_tc_kernel<T, 32, 3, 2, false, false, 2, 2> : conv_tc_kernel<T, 32, 1, 2, false, false, 2, 2>;
-  }
-  if (SUB == 3) return KC == 64 ? conv_tc_kernel<T, 64, 3, 1, false, false, 4, 2> : KC == 32 ? conv_tc_kernel<T, 32, 3, 1, false, false, 2, 2> : conv_tc_kernel<T, 16, 3, 1, false, false, 1, 2>;
-  return KC == 64 ? conv_tc_kernel<T, 64, 1, 1, false, false, 4, 2> : KC == 32 ? conv_tc_kernel<T, 32, 1, 1, false, false, 2, 2> : conv_tc_kernel<T, 16, 1, 1, false, false, 1, 2>;
+  return rtma == 1 && res && !leaky && KC == 64 && SUB == 3 && (G == 1 || G == 2 || G == 4);
 }
 static TcKernelFn tc_kernel_for(int KC, int SUB, int G, int is_bf16, int res, int leaky, int ks = 0, int rtma = 0) {
-  if (rtma == 2 && !res && !leaky && !is_bf16) return tc_ptma_kernel_for<__half>(KC, SUB, G, ks);
+  if (rtma == 2 && !res) {
+    if (is_bf16) return leaky ? tc_ptma_kernel_for<__nv_bfloat16, true>(KC, SUB, G, ks) : tc_ptma_kernel_for<__nv_bfloat16, false>(KC, SUB, G, ks);
+    return leaky ? tc_ptma_kernel_for<__half, true>(KC, SUB, G, ks) : tc_ptma_kernel_for<__half, false>(KC, SUB, G, ks);
+  }
   if (tc_rtma_kernel(KC, SUB, G, res, leaky, rtma)) {
     if (G == 4) return is_bf16 ? conv_tc_kernel<__nv_bfloat16, 64, 3, 4, true, false, 4, 1> : conv_tc_kernel<__half, 64, 3, 4, true, false, 4, 1>;
     if (G == 2) return is_bf16 ? conv_tc_kernel<__nv_bfloat16, 64, 3, 2, true, false, 4, 1> : conv_tc_kernel<__half, 64, 3, 2, true, false, 4, 1>;
@@ -1397,7 +1477,8 @@ int Net::tc_prepare() {
         for (int sub = 1; sub <= 3; sub += 2)
           for (int g = 1; g <= 4; g *= 2) {
             if ((g == 2 && kc < 32) || (g == 4 && kc < 64)) continue;
-            PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(kc, sub, g, bf, 0, 0, 0, 2), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+            for (int lk = 0; lk < 2; ++lk)
+              PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(kc, sub, g, bf, 0, lk, 0, 2), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
           }
       PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(64, 3, 1, bf, 0, 0, 3, 2), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     }
@@ -1442,5 +1523,7 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
 void Net::tc_release() {
   for (auto& L : convs) { delete L.tc; L.tc = nullptr; L.tc_ok = false; head_release(L); }
 }
+
+#endif  // PCLS_TC_PART <= 0
 
 }  // namespace pcls
