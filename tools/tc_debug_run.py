@@ -10,7 +10,8 @@ import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__
 import bench
 from pclsegmentation_b200 import _lib
 from pclsegmentation_b200.utils.args_loader import model_map
-name, mc, B = bench.make_config("squeezesegv2_kitti_64x2048_b32")
+name, mc, B = bench.make_config(sys.argv[1] if len(sys.argv) > 1 else "squeezesegv2_kitti_64x2048_b32")
+if len(sys.argv) > 2: B = int(sys.argv[2])
 model = model_map[name](mc); model.randomize_batch_norm(1)
 model.set_option("tc_debug", 1); model.set_option("use_graph", 0)
 raw = torch.from_numpy(bench.synth_raw(1, B, 64, 2048)).cuda()
