@@ -152,33 +152,42 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ===================== epilogue: two groups of four warps, alternate tiles =====================
     const int ew = warp - 2, grp = ew >> 2, q = warp & 3;   // q = TMEM lane quarter this warp may read
     const int r = q * 32 + lane;                            // accumulator row = input pixel w0 - 1 + r
-    const uint32_t n_acc = (uint32_t)p.n_acc;
+    const uint32_t n_acc = (uint32_t)p.n_acc, acc_shift = 31u - (uint32_t)__clz(p.n_acc);   // (a power of two)
     const int cout = p.cout;
     const float slope = p.slope;
     float* const stg = reinterpret_cast<float*>(smem_raw + (stg_base - smem0)) + ew * p.stg_warp_floats;
     float* const xch = reinterpret_cast<float*>(smem_raw + (xch_base - smem0)) + grp * (2 * 4 * 2 * CS);
     uint32_t cnt = 0;
-    // this thread's output pixel of the group's tile number tl (r = 0 and r = 127 are halo rows, not outputs)
-    auto locate = [&](uint32_t tl, int64_t& pix, bool& valid) -> bool {
-      const long long tile_ll = (long long)blockIdx.x + (long long)tl * gridDim.x;
-      if (tile_ll >= num_tiles) { pix = 0; valid = false; return false; }
-      const int tile = (int)tile_ll;
-      const int wt = tile % n_wt, h = (tile / n_wt) % H, b = tile / (n_wt * H);
-      const int w = wt * HD_TILE - 1 + r;
+    // this thread's output pixel of the group's next tile (r = 0 and r = 127 are halo rows, not outputs).  The group's tiles
+    // advance by a constant stride (HD_NG * gridDim.x): the (column tile, row, frame) coordinates are kept incrementally -
+    // three integer divisions per tile were ~100 of the ~820 instructions an epilogue warp spends per tile.
+    const long long stride_ll = (long long)HD_NG * gridDim.x;
+    const int s_wt = (int)(stride_ll % n_wt), s_h = (int)((stride_ll / n_wt) % H), s_b = (int)(stride_ll / ((long long)n_wt * H));
+    long long t_ll = (long long)blockIdx.x + (long long)grp * gridDim.x;
+    int c_wt = (int)(t_ll % n_wt), c_h = (int)((t_ll / n_wt) % H), c_b = (int)(t_ll / ((long long)n_wt * H));
+    auto locate = [&](int64_t& pix, bool& valid) -> bool {
+      if (t_ll >= num_tiles) { pix = 0; valid = false; return false; }
+      const int w = c_wt * HD_TILE - 1 + r;
       valid = r >= 1 && r <= HD_TILE && w < W;
-      pix = ((int64_t)b * H + h) * W + w;
+      pix = ((int64_t)c_b * H + c_h) * W + w;
+      t_ll += stride_ll;
+      c_wt += s_wt;
+      if (c_wt >= n_wt) { c_wt -= n_wt; ++c_h; }
+      c_h += s_h;
+      if (c_h >= H) { c_h -= H; ++c_b; }
+      c_b += s_b;
       return true;
     };
     int64_t pix, pix_n;
     bool valid, valid_n;
     uint32_t tl = (uint32_t)grp;
-    bool have = locate(tl, pix, valid);
+    bool have = locate(pix, valid);
     uint32_t head_mask = (have && p.head && valid) ? p.mask[pix] : 1u;
     while (have) {
       // the NEXT tile's mask byte travels during this tile's work (its latency was 10 % of the kernel's stall samples)
-      const bool have_n = locate(tl + HD_NG, pix_n, valid_n);
+      const bool have_n = locate(pix_n, valid_n);
       const uint32_t head_mask_n = (have_n && p.head && valid_n) ? p.mask[pix_n] : 1u;
-      const uint32_t acc = tl & (n_acc - 1u), acc_parity = (tl / n_acc) & 1u;
+      const uint32_t acc = tl & (n_acc - 1u), acc_parity = (tl >> acc_shift) & 1u;
       mbar_wait(TFULL_BAR(acc), acc_parity);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N;
@@ -214,28 +223,32 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                                                              __uint_as_float(V(2 * CS + c + 2)), __uint_as_float(V(2 * CS + c + 3)));
       }
       group_barrier(1 + grp);   // (also orders the reuse of this exchange buffer two tiles later)
-      float lg[CS];
-#pragma unroll
-      for (int c = 0; c < CS; ++c) {
-        float left = __shfl_up_sync(0xffffffffu, __uint_as_float(V(c)), 1);              // T0 of row r-1
-        float right = __shfl_down_sync(0xffffffffu, __uint_as_float(V(2 * CS + c)), 1);  // T2 of row r+1
-        if (lane == 0) left = 0.0f;      // (shfl_up / shfl_down hand the edge lanes their own value back)
-        if (lane == 31) right = 0.0f;
-        lg[c] = __uint_as_float(V(CS + c)) + left + right;
-      }
-      if (lane == 0 && q > 0) {          // row r-1 is lane 31 of the previous quarter (r = 0 is not an output pixel)
+      // Lane 31's own T0 row has no reader inside the warp (it went to the next quarter through smem) and neither has
+      // lane 0's T2 row: they are REPLACED by the neighbouring quarter's rows, and a rotation by one lane then hands every
+      // lane - the boundary lanes included - the right neighbour value: no edge selects, no fix-up adds (-80 of ~820
+      // instructions per warp and tile).  Quarter 0 / lane 0 and quarter 3 / lane 31 are the halo rows r = 0 / 127: not outputs.
+      if (lane == 31 && q > 0) {
 #pragma unroll
         for (int c = 0; c < CS; c += 4) {
           const float4 t = *reinterpret_cast<const float4*>(xb + (q - 1) * 2 * CS + c);
-          lg[c] += t.x; lg[c + 1] += t.y; lg[c + 2] += t.z; lg[c + 3] += t.w;
+          V(c) = __float_as_uint(t.x); V(c + 1) = __float_as_uint(t.y); V(c + 2) = __float_as_uint(t.z); V(c + 3) = __float_as_uint(t.w);
         }
       }
-      if (lane == 31 && q < 3) {         // row r+1 is lane 0 of the next quarter (r = 127 is not an output pixel)
+      if (lane == 0 && q < 3) {
 #pragma unroll
         for (int c = 0; c < CS; c += 4) {
           const float4 t = *reinterpret_cast<const float4*>(xb + (q + 1) * 2 * CS + CS + c);
-          lg[c] += t.x; lg[c + 1] += t.y; lg[c + 2] += t.z; lg[c + 3] += t.w;
+          V(2 * CS + c) = __float_as_uint(t.x); V(2 * CS + c + 1) = __float_as_uint(t.y);
+          V(2 * CS + c + 2) = __float_as_uint(t.z); V(2 * CS + c + 3) = __float_as_uint(t.w);
         }
+      }
+      const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
+      float lg[CS];
+#pragma unroll
+      for (int c = 0; c < CS; ++c) {
+        const float left = __shfl_sync(0xffffffffu, __uint_as_float(V(c)), lane_l);             // T0 of row r-1
+        const float right = __shfl_sync(0xffffffffu, __uint_as_float(V(2 * CS + c)), lane_r);  // T2 of row r+1
+        lg[c] = __uint_as_float(V(CS + c)) + left + right;
       }
       // bias (-inf for the padding classes), activation (none for conv14 / head: slope 1)
 #pragma unroll

@@ -232,7 +232,7 @@ __device__ __forceinline__ int4 epilogue_vec8(const uint32_t* acc, const float* 
 }
 
 // RM = 1: the residual kernel specialised at compile time for ONE skip tensor that is TMA-loaded into the output staging
-// buffers, TMA-store epilogue, ReLU (the FireDeconv expands of SqueezeSegV2).  The generic residual kernel carries the
+// buffers, TMA-store epilogue, ReLU or LeakyReLU (the FireDeconv expands of SqueezeSegV2, Darknet's enc1 / enc2 blocks).  The generic residual kernel carries the
 // code of every residual mode (cp.async staging, per-chunk LDG, second residual) behind run-time flags that are tested per
 // 8 outputs; the epilogue's instruction chain is what bounds these layers.
 template <typename T, int KC, int SUB, int G, bool RES, bool LEAKY, int KS = KC / 16, int RM = 0>
@@ -1038,7 +1038,13 @@ static bool tc_kskip_kernel(int KC, int SUB, int G, int res, int leaky, int ks) 
 }
 // the compile-time specialised residual kernel (RM = 1) exists for the shapes of SqueezeSegV2's FireDeconv expands
 static bool tc_rtma_kernel(int KC, int SUB, int G, int res, int leaky, int rtma) {
-  return rtma == 1 && res && !leaky && KC == 64 && SUB == 3 && (G == 1 || G == 2 || G == 4);
+  return rtma == 1 && res && KC == 64 && SUB == 3 && (G == 1 || G == 2 || G == 4);
+}
+template <typename T, bool LEAKY>
+static TcKernelFn tc_rtma_kernel_for(int G) {
+  if (G == 4) return conv_tc_kernel<T, 64, 3, 4, true, LEAKY, 4, 1>;
+  if (G == 2) return conv_tc_kernel<T, 64, 3, 2, true, LEAKY, 4, 1>;
+  return conv_tc_kernel<T, 64, 3, 1, true, LEAKY, 4, 1>;
 }
 static TcKernelFn tc_kernel_for(int KC, int SUB, int G, int is_bf16, int res, int leaky, int ks = 0, int rtma = 0) {
   if (rtma == 2 && !res) {
@@ -1046,9 +1052,8 @@ static TcKernelFn tc_kernel_for(int KC, int SUB, int G, int is_bf16, int res, in
     return leaky ? tc_ptma_kernel_for<__half, true>(KC, SUB, G, ks) : tc_ptma_kernel_for<__half, false>(KC, SUB, G, ks);
   }
   if (tc_rtma_kernel(KC, SUB, G, res, leaky, rtma)) {
-    if (G == 4) return is_bf16 ? conv_tc_kernel<__nv_bfloat16, 64, 3, 4, true, false, 4, 1> : conv_tc_kernel<__half, 64, 3, 4, true, false, 4, 1>;
-    if (G == 2) return is_bf16 ? conv_tc_kernel<__nv_bfloat16, 64, 3, 2, true, false, 4, 1> : conv_tc_kernel<__half, 64, 3, 2, true, false, 4, 1>;
-    return is_bf16 ? conv_tc_kernel<__nv_bfloat16, 64, 3, 1, true, false, 4, 1> : conv_tc_kernel<__half, 64, 3, 1, true, false, 4, 1>;
+    if (is_bf16) return leaky ? tc_rtma_kernel_for<__nv_bfloat16, true>(G) : tc_rtma_kernel_for<__nv_bfloat16, false>(G);
+    return leaky ? tc_rtma_kernel_for<__half, true>(G) : tc_rtma_kernel_for<__half, false>(G);
   }
   if (tc_kskip_kernel(KC, SUB, G, res, leaky, ks))
     return is_bf16 ? conv_tc_kernel<__nv_bfloat16, 64, 3, 1, false, false, 3> : conv_tc_kernel<__half, 64, 3, 1, false, false, 3>;
@@ -1472,7 +1477,8 @@ int Net::tc_prepare() {
     for (int bf = 0; bf < 2; ++bf) {
       PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(64, 3, 1, bf, 0, 0, 3), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
       for (int g = 1; g <= 4; g *= 2)
-        PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(64, 3, g, bf, 1, 0, 0, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        for (int lk = 0; lk < 2; ++lk)
+          PCLS_CHECK_CUDA(cudaFuncSetAttribute(tc_kernel_for(64, 3, g, bf, 1, lk, 0, 1), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
       for (int kc = 16; kc <= 64; kc *= 2)
         for (int sub = 1; sub <= 3; sub += 2)
           for (int g = 1; g <= 4; g *= 2) {
@@ -1511,8 +1517,8 @@ int Net::tc_launch(ConvLayer& L, const ConvParams& p, int nb, cudaStream_t s) {
   int grid = work < sm_count() ? work : sm_count();
   if (prm.nsplit) grid -= grid % prm.n_nt;   // every CTA sees one N tile only (tile % n_nt == blockIdx.x % n_nt)
   // one skip tensor, TMA-loaded into the staging buffers, TMA-store epilogue, ReLU: the specialised residual kernel
-  const int rtma = (tc_rtma_mode && prm.res_tma && prm.res0 && !prm.res1 && prm.tma_store && !prm.out_f32 && prm.act == PCLS_ACT_RELU &&
-                    !(PCLS_TC_VSTREAM && prm.vstream)) ? 1
+  const int rtma = (tc_rtma_mode && prm.res_tma && prm.res0 && !prm.res1 && prm.tma_store && !prm.out_f32 &&
+                    (prm.act == PCLS_ACT_RELU || prm.act == PCLS_ACT_LEAKY) && !(PCLS_TC_VSTREAM && prm.vstream)) ? 1
                  : ((tc_rtma_mode & 2) && !prm.res0 && !prm.res1 && prm.tma_store && !prm.out_f32 && !(PCLS_TC_VSTREAM && prm.vstream)) ? 2 : 0;
   PCLS_CHECK_CUDA(launch_pdl(tc_kernel_for(prm.KC, prm.sub, prm.G, prm.is_bf16, (prm.res0 || prm.res1) ? 1 : 0, prm.act == PCLS_ACT_LEAKY ? 1 : 0, prm.ksteps, rtma),
                              dim3(grid), dim3(tc_threads(prm.res0 || prm.res1)), plan->smem_bytes, s,

@@ -14,6 +14,7 @@
 namespace pcls {
 
 int pad48_mode = 1;   // A/B switch (pcls_net_set_option "pad48", before the ops are added)
+int pair_s2_mode = 1; // A/B switch "pair_s2": stride-2 convs with Cin = 32 run on the pixel-pair view (build_pair_view)
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -189,6 +190,31 @@ void Net::build_deconv_row3(ConvLayer& L) {
 void Net::build_pair_view(ConvLayer& L) {
   const ConvParams& p = L.p;
   if (p.mode == MODE_DECONV) { build_deconv_row3(L); return; }
+  // 3x3 s[1,2] deeper in the net (Darknet's enc1.down 32 -> 64 and enc2.down 64 -> 128): as a strided convolution every tap
+  // is its own TMA box of 128 rows x Cin channels taken from every other pixel (64-byte rows for Cin = 32) - nine loads per
+  // tile, and the wait-cycle counters show the MMA issuer waiting for data 54 % of the kernel at 0.24 of the HBM peak.  On
+  // the pixel-pair view [B,H,W/2,2 Cin] the layer is a 3x3 stride-1 convolution whose dw = -1 taps are zero: three
+  // 130-pair halo tiles with 128-byte rows per tile: enc1.down 0.328 -> 0.202 ms at batch 32.  A third of the MMAs multiply
+  // zeros and the zero taps' weights are loaded like any others: for Cin = 64 (enc2.down, 295 KB of pair-view weights
+  // streamed per tile) the same change measured 0.219 -> 0.343 ms, so Cin = 32 only.
+  if (L.in != 0 && pair_s2_mode && p.mode == MODE_3x3_S2 && p.pad_left == 0 && p.Win % 2 == 0 && !p.out_f32 && L.res0 < 0 &&
+      L.res1 < 0 && p.cin == p.cin_pad && p.in_channels == p.cin_pad && p.cin_pad == 32 && p.Wout == p.Win / 2) {
+    ConvParams q = p;
+    const int cp2 = 2 * p.cin_pad;
+    q.Win = p.Win / 2; q.in_channels = cp2; q.cin = cp2; q.cin_pad = cp2; q.pad_left = 0;
+    q.mode = MODE_3x3_S1; q.ntaps = 9;
+    L.w_tc.assign((size_t)9 * q.cout_pad * cp2, 0.0f);
+    for (int dh = 0; dh < 3; ++dh)
+      for (int kx = 0; kx < 3; ++kx)
+        for (int co = 0; co < p.cout; ++co)
+          for (int ci = 0; ci < p.cin; ++ci)
+            L.w_tc[((size_t)(dh * 3 + 1 + (kx >> 1)) * q.cout_pad + co) * cp2 + (kx & 1) * p.cin_pad + ci] =
+                L.w_f32[((size_t)(dh * 3 + kx) * p.cout_pad + co) * p.cin_pad + ci];
+    L.bias_tc = L.bias_f32;
+    L.ptc = q;
+    L.pair_view = true;
+    return;
+  }
   if (L.in != 0 || W % 2 != 0 || p.out_f32 || L.res0 >= 0 || L.res1 >= 0) return;
   if (p.mode == MODE_3x3_S2 && p.pad_left != 0) return;
   if (p.mode == MODE_DECONV) return;
@@ -907,11 +933,15 @@ extern "C" int pcls_net_set_option(pcls_net* net, const char* name, int value) {
     n->keep_tensors = value != 0; return PCLS_OK;
   }
   if (!strcmp(name, "tc_head")) { tc_head_mode = value; return PCLS_OK; }
-  if (!strcmp(name, "cam_px")) { PCLS_REQUIRE(value >= 0 && value <= 2, "cam_px must be 0 (default), 1 or 2"); n->cam_px = value; n->drop_graphs(); return PCLS_OK; }
+  if (!strcmp(name, "cam_px")) { PCLS_REQUIRE(value >= 0 && value <= 3, "cam_px must be 0 (default), 1, 2 or 3 (2 without the persistent grid)"); n->cam_px = value; n->drop_graphs(); return PCLS_OK; }
   if (!strcmp(name, "tc_nsplit")) { tc_nsplit_mode = value; return PCLS_OK; }
   if (!strcmp(name, "pad48")) {
     PCLS_REQUIRE(n->convs.empty(), "pad48 must be set before the first pcls_net_conv");
     pad48_mode = value; return PCLS_OK;
+  }
+  if (!strcmp(name, "pair_s2")) {
+    PCLS_REQUIRE(n->convs.empty(), "pair_s2 must be set before the first pcls_net_conv");
+    pair_s2_mode = value; return PCLS_OK;
   }
   if (!strcmp(name, "tc_halo")) { tc_halo_mode = value; return PCLS_OK; }
   if (!strcmp(name, "tc_rtma")) { tc_rtma_mode = value; n->drop_graphs(); return PCLS_OK; }
