@@ -933,7 +933,7 @@ extern "C" int pcls_net_set_option(pcls_net* net, const char* name, int value) {
     n->keep_tensors = value != 0; return PCLS_OK;
   }
   if (!strcmp(name, "tc_head")) { tc_head_mode = value; return PCLS_OK; }
-  if (!strcmp(name, "cam_px")) { PCLS_REQUIRE(value >= 0 && value <= 3, "cam_px must be 0 (default), 1, 2 or 3 (2 without the persistent grid)"); n->cam_px = value; n->drop_graphs(); return PCLS_OK; }
+  if (!strcmp(name, "cam_px")) { PCLS_REQUIRE(value >= 0 && value <= 2, "cam_px must be 0 (default), 1 or 2"); n->cam_px = value; n->drop_graphs(); return PCLS_OK; }
   if (!strcmp(name, "tc_nsplit")) { tc_nsplit_mode = value; return PCLS_OK; }
   if (!strcmp(name, "pad48")) {
     PCLS_REQUIRE(n->convs.empty(), "pad48 must be set before the first pcls_net_conv");

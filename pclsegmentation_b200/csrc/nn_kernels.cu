@@ -543,8 +543,7 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
 // three 128-thread CTAs per SM.
 template <typename T, int C>
 __global__ void __launch_bounds__(128, 3)
-cam2_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int H, int W, int rows_per_seg, int n_ws,
-            long long total_units, int unit_rows) {
+cam2_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int H, int W, int rows_per_seg) {
   using G = CamGeom<C, 2>;
   constexpr int CV = G::CV, TW = G::TW, PITCH = G::PITCH, ROWB = G::ROWB, NB = G::NB, DIST = G::DIST;
   constexpr int R = C / 16;
@@ -556,9 +555,11 @@ cam2_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, in
   unsigned char* const ring = reinterpret_cast<unsigned char*>(cam_smem);
   unsigned char* const St = ring + NB * ROWB;
 
+  const int w0 = blockIdx.x * TW;
+  const int64_t b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int cvg = warp % CVG, pg = warp / CVG;
-  const int cv = cvg * 4 + t;      // this thread's channel vector; its pixels are c0, c0 + 1 of the strip (c0 = 16 pg + 2 g)
+  const int c0 = pg * 16 + 2 * g, cv = cvg * 4 + t;      // this thread's pixels c0, c0 + 1 (columns of the strip) and channel vector
   const int4 NEG = neg_inf8<T>();
   const int64_t rowv = (int64_t)W * CV;
 
@@ -586,36 +587,10 @@ cam2_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, in
   }
   const uint32_t one2 = pack2<T>(1.0f, 1.0f);
 
-  const float b1x = 2 * t < R ? p.b1[2 * t] : 0.0f, b1y = 2 * t + 1 < R ? p.b1[2 * t + 1] : 0.0f;
-  pdl_trigger(p.pdl_early);   // PDL (common.cuh): the weight fragments above are independent of the producing layer
-  pdl_wait();
-  const unsigned soff = (unsigned)__cvta_generic_to_shared(ring) + (threadIdx.x / CV) * PITCH + (threadIdx.x % CV) * 16;
-  const unsigned a_off = (pg * 16 + 2 * g) * PITCH + cv * 16;   // ring: pixel c0 - 3 (+ d * PITCH), this vector
-  const unsigned s_off = ((pg * 8 + g) * 4 + t) * 16;     // squeeze tile [pixel pair][t]: {c0: columns 2t, 2t+1 | c0 + 1: same} = one
-                                                          // conflict-free 16-byte access per lane
-  // Work = the rows of all (frame, column strip) pairs laid end to end, split EVENLY over a grid of one wave (persistent
-  // CTAs): a CTA walks rows [R0, R1) and restarts the row pipeline (7 iterations of halo / drain) where it enters a new
-  // strip - 2-4 restarts per CTA instead of one per 32-row segment plus the idle slots of a partial last wave (batch 32:
-  // 5 waves x 39 iterations -> ~171).  rows_per_seg > 0 keeps the one-segment-per-CTA grid (small batches: the row
-  // segments are what fills the machine there).
-  long long R0, R1;
-  if (rows_per_seg > 0) {
-    R0 = ((long long)blockIdx.y * n_ws + blockIdx.x) * H + (long long)blockIdx.z * rows_per_seg;
-    R1 = R0 + min(rows_per_seg, H - (int)blockIdx.z * rows_per_seg);
-  } else {
-    R0 = total_units * blockIdx.x / gridDim.x * unit_rows;
-    R1 = total_units * (blockIdx.x + 1) / gridDim.x * unit_rows;
-  }
-  for (long long Rc = R0; Rc < R1;) {
-  const int strip = (int)(Rc / H), h0 = (int)(Rc - (long long)strip * H);
-  const int h1 = (int)min((long long)H, (long long)h0 + (R1 - Rc));
-  Rc += h1 - h0;
-  const int w0 = (strip % n_ws) * TW;
-  const int64_t b = strip / n_ws;
-  const int c0 = pg * 16 + 2 * g;
   const int4* const fin = in + b * H * rowv;
   int4* const fout = out + b * H * rowv;
   unsigned sptr = (unsigned)((w0 - 3 + (int)threadIdx.x / CV) * CV + threadIdx.x % CV);
+  const unsigned soff = (unsigned)__cvta_generic_to_shared(ring) + (threadIdx.x / CV) * PITCH + (threadIdx.x % CV) * 16;
   bool sok[LPT];
 #pragma unroll
   for (int k = 0; k < LPT; ++k) {
@@ -625,6 +600,10 @@ cam2_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, in
     if (i < NSTG && !sok[k])
       for (int sl = 0; sl < NB; ++sl) *reinterpret_cast<int4*>(ring + sl * ROWB + (i / CV) * PITCH + (i % CV) * 16) = NEG;
   }
+  const float b1x = 2 * t < R ? p.b1[2 * t] : 0.0f, b1y = 2 * t + 1 < R ? p.b1[2 * t + 1] : 0.0f;
+  pdl_trigger(p.pdl_early);   // PDL (common.cuh): the weight fragments above are independent of the producing layer
+  pdl_wait();
+  const int h0 = blockIdx.z * rows_per_seg, h1 = min(H, h0 + rows_per_seg);
   const int a0 = h0 - 3 < 0 ? 0 : h0 - 3;
   sptr += (unsigned)a0 * (unsigned)rowv;
   auto stage_row = [&](int r, int slot) {
@@ -638,6 +617,10 @@ cam2_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, in
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+
+  const unsigned a_off = c0 * PITCH + cv * 16;            // ring: pixel c0 - 3 (+ d * PITCH), this vector
+  const unsigned s_off = ((pg * 8 + g) * 4 + t) * 16;     // squeeze tile [pixel pair][t]: {c0: columns 2t, 2t+1 | c0 + 1: same} = one
+                                                          // conflict-free 16-byte access per lane
   const bool ok0 = (w0 + c0) < W, ok1 = (w0 + c0 + 1) < W;
   unsigned optr = (unsigned)((w0 + c0) * CV + cv) + (unsigned)h0 * (unsigned)rowv;
 
@@ -714,13 +697,9 @@ cam2_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, in
       sc = sc + 1 == NB ? 0 : sc + 1;
     }
   }
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncthreads();   // the ring is re-initialised by the next piece
-  }
 }
 
-// px: pixels per thread (pcls_net_set_option "cam_px"): 1 = cam_kernel, 2 = cam2_kernel, 3 = cam2_kernel without the
-// persistent grid (A/B), 0 = default = 2 (measured at batch 32:
+// px: pixels per thread (pcls_net_set_option "cam_px"): 1 = cam_kernel, 2 = cam2_kernel, 0 = default = 2 (measured at batch 32:
 // C = 64 0.138 vs 0.185 ms, C = 128 0.143 vs 0.189 ms)
 template <typename T>
 int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, int px, cudaStream_t s) {
@@ -738,46 +717,24 @@ int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, int
     const int64_t cost = ceil_div(strips * sgs, slots) * (ceil_div(H, sgs) + 7);
     if (best < 0 || cost < best) { best = cost; segs = sgs; }
   }
-  int rows_per_seg = (int)ceil_div(H, segs);
+  const int rows_per_seg = (int)ceil_div(H, segs);
   segs = (int)ceil_div(H, rows_per_seg);
   dim3 grid((unsigned)ceil_div(W, TW), (unsigned)B, (unsigned)segs);
-  // two-pixel kernel, more than one wave of segments: one wave of persistent CTAs over the evenly split row list instead
-  // (cam2_kernel).  Cost model: rows per CTA + 7 iterations per strip it touches.
-  const int n_ws = (int)ceil_div(W, TW);
-  const int unit_rows = H % 4 == 0 ? 4 : 1;
-  const long long total_units = strips * H / unit_rows;
-  if (two && px != 3) {
-    const int64_t g1 = std::min<int64_t>(slots, total_units);
-    const int64_t rows_cta = ceil_div(strips * H, g1);
-    const int64_t cost_p = rows_cta + 7 * (ceil_div(rows_cta, H) + 1);
-    if (cost_p < best) { grid = dim3((unsigned)g1, 1, 1); rows_per_seg = 0; }
-  }
   const int smem = two ? (p.C == 64 ? CamGeom<64, 2>::SMEM : CamGeom<128, 2>::SMEM)
                        : (p.C == 64 ? CamGeom<64>::SMEM : CamGeom<128>::SMEM);   // ring + squeeze tiles, see cam_kernel
+  auto kern = two ? (p.C == 64 ? cam2_kernel<T, 64> : cam2_kernel<T, 128>) : (p.C == 64 ? cam_kernel<T, 64> : cam_kernel<T, 128>);
   static bool configured[64][2][2] = {};   // function attributes are per device
   int dev = 0;
   cudaGetDevice(&dev);
+  if (!configured[dev & 63][two][p.C == 128]) {
+    PCLS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PCLS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    configured[dev & 63][two][p.C == 128] = true;
+  }
   CamParams q = p;
   q.pdl_early = pdl_early_now;
-  if (two) {
-    auto kern = p.C == 64 ? cam2_kernel<T, 64> : cam2_kernel<T, 128>;
-    if (!configured[dev & 63][1][p.C == 128]) {
-      PCLS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      PCLS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      configured[dev & 63][1][p.C == 128] = true;
-    }
-    PCLS_CHECK_CUDA(launch_pdl(kern, grid, dim3(128), (size_t)smem, s, reinterpret_cast<const int4*>(in),
-                               reinterpret_cast<int4*>(out), q, H, W, rows_per_seg, n_ws, total_units, unit_rows));
-  } else {
-    auto kern = p.C == 64 ? cam_kernel<T, 64> : cam_kernel<T, 128>;
-    if (!configured[dev & 63][0][p.C == 128]) {
-      PCLS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      PCLS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      configured[dev & 63][0][p.C == 128] = true;
-    }
-    PCLS_CHECK_CUDA(launch_pdl(kern, grid, dim3(256), (size_t)smem, s, reinterpret_cast<const int4*>(in),
-                               reinterpret_cast<int4*>(out), q, H, W, rows_per_seg));
-  }
+  PCLS_CHECK_CUDA(launch_pdl(kern, grid, dim3(two ? 128 : 256), (size_t)smem, s, reinterpret_cast<const int4*>(in),
+                             reinterpret_cast<int4*>(out), q, H, W, rows_per_seg));
   return check_launch("cam_kernel");
 }
 template int launch_cam<__half>(const __half*, __half*, const CamParams&, int, int, int, int, cudaStream_t);
