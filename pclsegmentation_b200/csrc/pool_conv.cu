@@ -205,7 +205,9 @@ pool_conv1x1_kernel(const PoolConvParams p) {
         *reinterpret_cast<float2*>(dst + g * S + 8 * j + 2 * t) = make_float2(acc[j][0], acc[j][1]);
         *reinterpret_cast<float2*>(dst + (g + 8) * S + 8 * j + 2 * t) = make_float2(acc[j][2], acc[j][3]);
       }
-      __syncthreads();   // (every warp of the CTA runs the same number of rows: r_lo / r_hi are CTA-uniform)
+      // only the SLABS warps of this pixel group exchange partial sums: a named barrier per group lets the PG groups of the
+      // CTA drift apart (their load latencies overlap instead of lining up behind one CTA-wide barrier per row)
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + pg), "r"(SLABS * 32) : "memory");
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         if (j % SLABS != slab) continue;
