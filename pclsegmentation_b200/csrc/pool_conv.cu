@@ -6,7 +6,7 @@
 // pixel never leaves the registers:
 //
 //   * a warp owns 16 consecutive output pixels x one 64-channel slab; lane (g, t) holds channels [16 t, 16 t + 16) of
-//     pixels g and g + 8 (two 16-byte vectors each).  Walking down the rows of its segment it takes, per input row, the
+//     pixels 2 g and 2 g + 1 (two 16-byte vectors each).  Walking down the rows of its segment it takes, per input row, the
 //     horizontal 3-max (columns 2 wo - pad .. + 2: six 128-bit loads per pixel) and keeps the last two row maxima in
 //     registers; the vertical 3-max is the pooled pixel (-inf padding never wins, TF SAME semantics).
 //   * those registers ARE the A fragments of mma.sync.m16n8k16 (the K order is a free permutation of the channels, chosen
@@ -107,29 +107,25 @@ pool_conv1x1_kernel(const PoolConvParams p) {
   auto hrow = [&](int h, int4 (&m)[2][2]) {
     const bool hv = h >= 0 && h < p.H;
     const int4* row = img + (int64_t)min(max(h, 0), p.H - 1) * p.Win * CV;
-    int4 v[2][3][2];
-    bool ok[2][3];
+    // the lane's two pixels are ADJACENT (wo, wo + 1): their windows share the middle one of five input columns - ten
+    // 128-bit loads per row instead of twelve (ncu: the kernel's busiest unit is L1 / LSU at 70 %)
+    const int wi0 = 2 * min(wo0 + 2 * g, p.Wout - 1) - p.pad_left;   // (columns right of the image: computed, never stored)
+    int4 v[5][2];
+    bool ok[5];
 #pragma unroll
-    for (int px = 0; px < 2; ++px) {
-      const int wo = min(wo0 + g + 8 * px, p.Wout - 1);     // (columns right of the image: computed, never stored)
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int wi = 2 * wo - p.pad_left + dx;
-        ok[px][dx] = hv && wi >= 0 && wi < p.Win;
-        const int4* src = row + (int64_t)min(max(wi, 0), p.Win - 1) * CV;
-        v[px][dx][0] = __ldg(src);
-        v[px][dx][1] = __ldg(src + 1);
-      }
+    for (int dx = 0; dx < 5; ++dx) {
+      const int wi = wi0 + dx;
+      ok[dx] = hv && wi >= 0 && wi < p.Win;
+      const int4* src = row + (int64_t)min(max(wi, 0), p.Win - 1) * CV;
+      v[dx][0] = __ldg(src);
+      v[dx][1] = __ldg(src + 1);
     }
 #pragma unroll
-    for (int px = 0; px < 2; ++px)
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        int4 mm = ok[px][0] ? v[px][0][k] : NEG;
-        mm = max8pc<T>(mm, ok[px][1] ? v[px][1][k] : NEG);
-        mm = max8pc<T>(mm, ok[px][2] ? v[px][2][k] : NEG);
-        m[px][k] = mm;
-      }
+    for (int k = 0; k < 2; ++k) {
+      const int4 mid = ok[2] ? v[2][k] : NEG;
+      m[0][k] = max8pc<T>(max8pc<T>(ok[0] ? v[0][k] : NEG, ok[1] ? v[1][k] : NEG), mid);
+      m[1][k] = max8pc<T>(max8pc<T>(ok[3] ? v[3][k] : NEG, ok[4] ? v[4][k] : NEG), mid);
+    }
   };
   for (long long r = r_lo; r < r_hi; ++r) {
     const int st = (int)(r / p.H), h = (int)(r % p.H);
@@ -174,7 +170,7 @@ pool_conv1x1_kernel(const PoolConvParams p) {
     auto finish = [&](int j, float (&a4)[4]) {
 #pragma unroll
       for (int px = 0; px < 2; ++px) {
-        const int wo = wo0 + g + 8 * px;
+        const int wo = wo0 + 2 * g + px;
         if (wo < p.Wout) {
           float v0 = a4[2 * px] + __ldg(p.bias + 8 * j + 2 * t), v1 = a4[2 * px + 1] + __ldg(p.bias + 8 * j + 2 * t + 1);
           v0 = leaky ? fmaxf(v0, 0.1f * v0) : fmaxf(v0, lo);
@@ -188,7 +184,7 @@ pool_conv1x1_kernel(const PoolConvParams p) {
     if (p.zero_to > S && slab == 0) {   // padded output tensor (48 -> 64 channels): the pad channels are written as zeros
 #pragma unroll
       for (int px = 0; px < 2; ++px) {
-        const int wo = wo0 + g + 8 * px;
+        const int wo = wo0 + 2 * g + px;
         for (int c = S + 2 * t; c < p.zero_to && wo < p.Wout; c += 8)
           *reinterpret_cast<uint32_t*>(outp + ((bframe * p.H + h) * p.Wout + wo) * p.out_channels + c) = 0u;
       }
