@@ -541,8 +541,11 @@ cam_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int
 // columns, so the pair needs 8 loads instead of 14, and the squeeze / excitation MMAs (m16n8k16) carry the second pixel in
 // fragment rows 8-15 that were idle: half the MMAs, address arithmetic and loop overhead per pixel.  Needs ~150 registers:
 // three 128-thread CTAs per SM.
+#ifndef PCLS_CAM2_CTAS
+#define PCLS_CAM2_CTAS 3   // resident CTAs per SM the two-pixel kernel's register allocation targets
+#endif
 template <typename T, int C>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, PCLS_CAM2_CTAS)
 cam2_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, int H, int W, int rows_per_seg) {
   using G = CamGeom<C, 2>;
   constexpr int CV = G::CV, TW = G::TW, PITCH = G::PITCH, ROWB = G::ROWB, NB = G::NB, DIST = G::DIST;
@@ -710,7 +713,7 @@ int launch_cam(const T* in, T* out, const CamParams& p, int B, int H, int W, int
   // row segments (>= 8 rows each): minimise  waves x iterations per CTA  with two CTAs resident per SM; a segment of n
   // rows runs n + 7 iterations (three rows of halo above / below and the pipeline drain)
   const bool two = px != 1;
-  const int64_t strips = ceil_div(W, TW) * (int64_t)B, slots = (int64_t)sm_count() * (two ? 3 : PCLS_CAM_CTAS);
+  const int64_t strips = ceil_div(W, TW) * (int64_t)B, slots = (int64_t)sm_count() * (two ? PCLS_CAM2_CTAS : PCLS_CAM_CTAS);
   int segs = 1;
   int64_t best = -1;
   for (int sgs = 1; sgs <= (H >= 8 ? H / 8 : 1); ++sgs) {
