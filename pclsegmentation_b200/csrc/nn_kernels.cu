@@ -344,6 +344,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// PCLS_CAM_TANH=1: sigmoid(e) = 0.5 + 0.5 tanh(e / 2) with ONE SFU op (tanh.approx.f32, max relative error 2^-11) instead
+// of ex2 + rcp; the factor 1/2 is folded into W2 / b2.  x * sigmoid = fma(x/2, t, x/2).
+#ifndef PCLS_CAM_TANH
+#define PCLS_CAM_TANH 1
+#endif
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -574,7 +584,7 @@ cam2_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, in
     w1f[u][0] = pack2<T>(w1(0), w1(1));
     w1f[u][1] = pack2<T>(w1(2), w1(3));
   }
-  constexpr float NL2E = -1.4426950408889634f;
+  constexpr float NL2E = PCLS_CAM_TANH ? 0.5f : -1.4426950408889634f;   // (PCLS_CAM_TANH: the tanh form's 1/2)
   uint32_t w2f[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -690,8 +700,14 @@ cam2_kernel(const int4* __restrict__ in, int4* __restrict__ out, CamParams p, in
           sa[3] = sa[2];
           mma16816<T>(e, sa, bq);
           const float2 x0 = unpack2<T>(xw0[q]), x1 = unpack2<T>(xw1[q]);
+          if constexpr (PCLS_CAM_TANH) {
+            const float h0 = 0.5f * x0.x, h1 = 0.5f * x0.y, h2 = 0.5f * x1.x, h3 = 0.5f * x1.y;
+            o0[q] = pack2<T>(fmaf(h0, tanh_approx(e[0]), h0), fmaf(h1, tanh_approx(e[1]), h1));
+            o1[q] = pack2<T>(fmaf(h2, tanh_approx(e[2]), h2), fmaf(h3, tanh_approx(e[3]), h3));
+          } else {
           o0[q] = pack2<T>(x0.x * rcp_approx(1.0f + ex2_approx(e[0])), x0.y * rcp_approx(1.0f + ex2_approx(e[1])));
           o1[q] = pack2<T>(x1.x * rcp_approx(1.0f + ex2_approx(e[2])), x1.y * rcp_approx(1.0f + ex2_approx(e[3])));
+          }
         }
         if (ok0) fout[optr] = make_int4((int)o0[0], (int)o0[1], (int)o0[2], (int)o0[3]);
         if (ok1) fout[optr + CV] = make_int4((int)o1[0], (int)o1[1], (int)o1[2], (int)o1[3]);
