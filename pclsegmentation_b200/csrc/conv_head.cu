@@ -134,13 +134,11 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(FULL_BAR(stage), phase);
         tc_fence_after();
         const uint32_t a_addr = smem_base + (uint32_t)stage * a_bytes;
-        const uint64_t a_desc = ((uint64_t)desc_hi << 32) | (uint64_t)(((a_addr >> 4) & 0x3FFFu) | 0x10000u);
-        const uint64_t b_desc = ((uint64_t)desc_hi << 32) | (uint64_t)(((b_addr >> 4) & 0x3FFFu) | 0x10000u);
-#pragma unroll
-        for (int j = 0; j < KC / 16; ++j) {
-          umma_f16_elect(d_tmem, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j), idesc, accumulate);
-          accumulate = 1u;
-        }
+        // the KC / 16 K steps of this chunk behind one elect (tc_ptx.cuh): the issuing warp's instruction stream, ~22
+        // instructions per MMA in the per-MMA form, is what bounds this kernel (N = 64 MMAs execute faster than they issue)
+        umma_f16_ksteps_elect<KC / 16>(d_tmem, ((a_addr >> 4) & 0x3FFFu) | 0x10000u, desc_hi, ((b_addr >> 4) & 0x3FFFu) | 0x10000u,
+                                       desc_hi, idesc, accumulate);
+        accumulate = 1u;
         b_addr += b_tile_bytes;
         umma_commit_elect(EMPTY_BAR(stage));
         if (++stage == S) { stage = 0; phase ^= 1u; }

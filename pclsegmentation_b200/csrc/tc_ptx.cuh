@@ -108,6 +108,39 @@ __device__ __forceinline__ void umma_f16_elect(uint32_t d_tmem, uint64_t a_desc,
       "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// KS consecutive K = 16 steps of one operand pair behind ONE elect: the descriptors differ in their low words only (+2 per
+// step = 32 bytes along K inside the swizzle atom), the high words, the accumulator address and the instruction
+// descriptor are shared - so the issuing warp moves 2 values per MMA into uniform registers instead of 6 and runs one
+// elect / vote per K chunk instead of one per MMA.  (SASS of the per-MMA form: ~22 instructions per UTCHMMA, i.e. ~130
+// cycles of the single issuing warp per MMA - more than an N <= 128 MMA takes to execute.)
+#define PCLS_UMMA_HEAD                                                                                   \
+  "{\n\t"                                                                                                \
+  ".reg .pred p, pe, pt;\n\t"                                                                            \
+  ".reg .b64 da, db;\n\t"                                                                                \
+  ".reg .b32 ta, tb;\n\t"                                                                                \
+  "elect.sync _|pe, 0xffffffff;\n\t"                                                                     \
+  "setp.ne.b32 p, %6, 0;\n\t"                                                                            \
+  "setp.eq.b32 pt, 0, 0;\n\t"                                                                            \
+  "mov.b64 da, {%1, %2};\n\t"                                                                            \
+  "mov.b64 db, {%3, %4};\n\t"                                                                            \
+  "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+#define PCLS_UMMA_STEP(off)                                                                              \
+  "add.u32 ta, %1, " #off ";\n\t"                                                                        \
+  "add.u32 tb, %3, " #off ";\n\t"                                                                        \
+  "mov.b64 da, {ta, %2};\n\t"                                                                            \
+  "mov.b64 db, {tb, %4};\n\t"                                                                            \
+  "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+#define PCLS_UMMA_ARGS \
+  ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory"
+template <int KS>
+__device__ __forceinline__ void umma_f16_ksteps_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                      uint32_t idesc, uint32_t accumulate) {
+  static_assert(KS >= 1 && KS <= 4, "1..4 K steps");
+  if constexpr (KS == 1) asm volatile(PCLS_UMMA_HEAD "}" PCLS_UMMA_ARGS);
+  if constexpr (KS == 2) asm volatile(PCLS_UMMA_HEAD PCLS_UMMA_STEP(2) "}" PCLS_UMMA_ARGS);
+  if constexpr (KS == 3) asm volatile(PCLS_UMMA_HEAD PCLS_UMMA_STEP(2) PCLS_UMMA_STEP(4) "}" PCLS_UMMA_ARGS);
+  if constexpr (KS == 4) asm volatile(PCLS_UMMA_HEAD PCLS_UMMA_STEP(2) PCLS_UMMA_STEP(4) PCLS_UMMA_STEP(6) "}" PCLS_UMMA_ARGS);
+}
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n\t"
