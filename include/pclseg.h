@@ -298,6 +298,13 @@ int64_t pcls_net_workspace_bytes(const pcls_net* net);
  *   "tc_halo" (one 130-pixel tile serves three horizontal taps), "tc_resident" (weights stay in smem), "tc_group"
  *   (pixel-group view for 16 / 32-channel inputs), "tc_tma_store" (TMA-store epilogue), "tc_res_tma" (residual blocks
  *   TMA-loaded into the output staging buffers), "tc_split" (outer taps skip the expand1x1 half of merged Fire expands)
+ *   "tc_nsplit" (N-split across CTAs with resident weight halves), "tc_head" (logits layer on its own kernel),
+ *   "pad48" / "pair_s2" (before the first pcls_net_conv: 48-channel tensors stored with a 64-channel stride; 3x3 stride-2
+ *   convolutions with 32 input channels on the pixel-pair view)
+ * launch-time switches (any time; cached CUDA graphs are dropped):
+ *   "tc_rtma"  bit 0: compile-time specialised residual kernel (one TMA-loaded skip tensor, TMA store, ReLU / LeakyReLU),
+ *              bit 1: specialised plain kernel (no residual, TMA store); default 3, 0 = the generic kernel everywhere
+ *   "cam_px"   pixels per thread of the CAM kernel: 0 = default (2), 1, 2
  * "tc_debug" (wait-cycle counters) needs a library built with PCLS_NVCC_FLAGS=-DPCLS_TC_DEBUG=1. */
 int pcls_net_set_option(pcls_net* net, const char* name, int value);
 
