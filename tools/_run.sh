@@ -1,6 +1,9 @@
-mkdir -p gpurun_out/n8
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 5 --no-extras --no-cpu-baseline > gpurun_out/n8/bench_n8.json 2> gpurun_out/n8/bench_n8.err; tail -3 gpurun_out/n8/bench_n8.err
+mkdir -p gpurun_out/s34
+timeout 200 python bench.py --steps 30 --warmup 5 --no-extras --no-cpu-baseline --no-eval --op-table gpurun_out/s34/optable.json > gpurun_out/s34/bench.json 2>gpurun_out/s34/bench.err; tail -3 gpurun_out/s34/bench.err
 python -c "
-import json
-d=json.loads([l for l in open('gpurun_out/n8/bench_n8.json') if l.startswith('{')][-1]); print('N=8', round(d['value']), d['ms_per_step'], 'e2e', round(d['e2e']['value']), d.get('eval'))"
-(timeout 400 python -m pytest tests/test_gpu_multi.py -m gpu -q) > gpurun_out/n8/pytest_multi.log 2>&1; tail -3 gpurun_out/n8/pytest_multi.log
+import json; d=json.load(open('gpurun_out/s34/bench.json')); print('ssv2', round(d['value']), round(d['ms_per_step'],4), d['p50_latency_ms'])
+t=json.load(open('gpurun_out/s34/optable.json'))
+for o in t['ops']:
+  if 'pool+' in o['op']: print('  ', o['op'], round(o['ms'],4), round(o['frac'],3))
+"
+(timeout 600 python -m pytest tests -m gpu -x -q) > gpurun_out/s34/pytest.log 2>&1; tail -4 gpurun_out/s34/pytest.log
