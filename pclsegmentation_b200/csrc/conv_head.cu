@@ -59,7 +59,8 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t smem_base = (smem0 + 1023u) & ~1023u;
   const int S = p.stages;
   const uint32_t a_bytes = (uint32_t)p.a_bytes, b_tile_bytes = (uint32_t)p.b_tile_bytes;
-  const uint32_t bres_base = smem_base + (uint32_t)S * a_bytes;            // resident weights [3][kchunks] tiles
+  const uint32_t stage_bytes = (uint32_t)(3 * p.kchunks) * a_bytes;   // one stage = the 3 x kchunks input tiles of an output tile
+  const uint32_t bres_base = smem_base + (uint32_t)S * stage_bytes;            // resident weights [3][kchunks] tiles
   const uint32_t stg_base = bres_base + (uint32_t)p.bres_bytes;            // [4 HD_NG warps][stg_warp_floats] f32 output staging
   const uint32_t xch_base = stg_base + (uint32_t)(4 * HD_NG * p.stg_warp_floats) * 4u;   // [groups][2 buffers][4 quarters][2 CS] f32
   const uint32_t bar_base = xch_base + (uint32_t)HD_NG * 2u * 4u * 2u * (uint32_t)CS * 4u;
@@ -106,17 +107,23 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     pdl_wait();
     int stage = 0;
     uint32_t phase = 0;
+    // One pipeline stage = ALL input tiles of an output tile (3 rows x kchunks, 16 KB each) behind ONE full / empty
+    // barrier pair: the MMA issuer pays two barrier waits and two commits per tile instead of four and four (its spin
+    // counters never show it waiting, the tensor pipe is 25 % busy and trimming its instruction stream changed nothing:
+    // what it spends its time on is the latency of the mbarrier / commit round trips themselves).
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int wt = tile % n_wt, h = (tile / n_wt) % H, b = tile / (n_wt * H);
       const int ww = wt * HD_TILE - 1;
+      mbar_wait(EMPTY_BAR(stage), phase ^ 1u);
+      const uint32_t fb = FULL_BAR(stage);
+      mbar_arrive_expect_tx_elect(fb, (uint32_t)(3 * kchunks) * 128u * KC * 2u);
+      uint32_t dst = smem_base + (uint32_t)stage * stage_bytes;
       for (int g = 0; g < 3; ++g)
         for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait(EMPTY_BAR(stage), phase ^ 1u);
-          const uint32_t fb = FULL_BAR(stage);
-          mbar_arrive_expect_tx_elect(fb, 128u * KC * 2u);
-          tma_load_4d_elect(smem_base + (uint32_t)stage * a_bytes, &map_a, fb, kc * KC, ww, h + g - 1, b);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
+          tma_load_4d_elect(dst, &map_a, fb, kc * KC, ww, h + g - 1, b);
+          dst += a_bytes;
         }
+      if (++stage == S) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -130,19 +137,19 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * N;
       uint32_t b_addr = bres_base, accumulate = 0u;
+      mbar_wait(FULL_BAR(stage), phase);
+      tc_fence_after();
+      uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
       for (int k = 0; k < k_iters; ++k) {
-        mbar_wait(FULL_BAR(stage), phase);
-        tc_fence_after();
-        const uint32_t a_addr = smem_base + (uint32_t)stage * a_bytes;
-        // the KC / 16 K steps of this chunk behind one elect (tc_ptx.cuh): the issuing warp's instruction stream, ~22
-        // instructions per MMA in the per-MMA form, is what bounds this kernel (N = 64 MMAs execute faster than they issue)
+        // the KC / 16 K steps of this chunk behind one elect (tc_ptx.cuh)
         umma_f16_ksteps_elect<KC / 16>(d_tmem, ((a_addr >> 4) & 0x3FFFu) | 0x10000u, desc_hi, ((b_addr >> 4) & 0x3FFFu) | 0x10000u,
                                        desc_hi, idesc, accumulate);
         accumulate = 1u;
+        a_addr += a_bytes;
         b_addr += b_tile_bytes;
-        umma_commit_elect(EMPTY_BAR(stage));
-        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
+      umma_commit_elect(EMPTY_BAR(stage));   // the stage is free once these MMAs have read it
+      if (++stage == S) { stage = 0; phase ^= 1u; }
       umma_commit_elect(TFULL_BAR(acc));
       if (++acc == n_acc) { acc = 0; acc_phase ^= 1u; }
     }
@@ -392,11 +399,12 @@ int Net::head_plan_layer(ConvLayer& L) {
   q.slope = cp.act == PCLS_ACT_RELU ? 0.0f : (cp.act == PCLS_ACT_LEAKY ? 0.1f : 1.0f);
   q.stg_warp_floats = (cp.cout % 4 == 0) ? 32 * cp.cout : 32 * 33;
   const int fixed = q.bres_bytes + 4 * HD_NG * q.stg_warp_floats * 4 + HD_NG * 2 * 4 * 2 * CS * 4 + 1024 /*alignment*/ + 512 /*barriers, slot, bias*/;
-  int stages = (227 * 1024 - fixed) / q.a_bytes;
-  if (stages > 12) stages = 12;
-  if (stages < 3) { delete plan; return PCLS_OK; }
+  const int stage_bytes = 3 * q.kchunks * q.a_bytes;   // a stage holds every input tile of one output tile
+  int stages = (227 * 1024 - fixed) / stage_bytes;
+  if (stages > 4) stages = 4;
+  if (stages < 2) { delete plan; return PCLS_OK; }
   q.stages = stages;
-  plan->smem_bytes = (size_t)stages * q.a_bytes + fixed;
+  plan->smem_bytes = (size_t)stages * stage_bytes + fixed;
 
   // weights: [kernel row dh][n = kx * CS + class][ci], K-major, 16-bit
   std::vector<uint16_t> packed((size_t)3 * q.N * cp.cin_pad, 0);
