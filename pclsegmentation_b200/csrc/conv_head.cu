@@ -35,7 +35,19 @@
 namespace pcls {
 
 constexpr int HD_NG = 4;                        // epilogue warp-groups (4 warps each); tiles are dealt round-robin
-constexpr int HD_THREADS = 64 + 128 * HD_NG;
+// -DPCLS_HEAD_ISSUERS=2 (experimental, NOT validated on hardware yet - DESIGN.md section 6, step 27): a second MMA-issuing
+// warp (the last warp of the CTA); the two take alternate tiles so that their barrier / commit round trips overlap.  The
+// stage ring is then forced to an EVEN length: tile sequence number s lives in stage s % S, so with S even issuer i only
+// ever touches stages = i (mod 2) and accumulators = i (mod 2) - it has consumed the previous round of every barrier it
+// waits on itself.  (With three stages the issuers shared stages, the faster one could reach a stage a full ring round
+// ahead of the slower one, the parity wait returned on the stale phase: launch failure at batch 32.)
+#ifndef PCLS_HEAD_ISSUERS
+#define PCLS_HEAD_ISSUERS 1
+#endif
+#if PCLS_HEAD_ISSUERS == 2
+constexpr int HD_ISSUER2 = 2 + 4 * HD_NG;
+#endif
+constexpr int HD_THREADS = 64 + 128 * HD_NG + 32 * (PCLS_HEAD_ISSUERS - 1);
 constexpr int HD_TILE = 126;   // output pixels per tile (128 input pixels incl. the one-pixel halo on both sides)
 
 struct HeadParams {
@@ -131,6 +143,37 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       if (++stage == S) { stage = 0; phase ^= 1u; }
     }
+#if PCLS_HEAD_ISSUERS == 2
+  } else if (warp == 1 || warp == HD_ISSUER2) {
+    // ===================== MMA issuers (two warps, alternate tiles; see PCLS_HEAD_ISSUERS above) =====================
+    const uint32_t desc_hi = p.desc_hi, idesc = p.idesc, n_acc = (uint32_t)p.n_acc, acc_shift2 = 31u - (uint32_t)__clz(p.n_acc);
+    const int k_iters = 3 * kchunks;
+    const uint32_t iw = warp == 1 ? 0u : 1u;
+    int stage = (int)iw;                 // S is even and >= 2
+    uint32_t phase = 0, seq = iw;
+    mbar_wait(BRES_BAR, 0u);
+    for (long long tile = (long long)blockIdx.x + (long long)iw * gridDim.x; tile < num_tiles; tile += 2LL * gridDim.x, seq += 2u) {
+      const uint32_t acc = seq & (n_acc - 1u), acc_phase = (seq >> acc_shift2) & 1u;
+      mbar_wait(TEMPTY_BAR(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * N;
+      uint32_t b_addr = bres_base, accumulate = 0u;
+      mbar_wait(FULL_BAR(stage), phase);
+      tc_fence_after();
+      uint32_t a_addr = smem_base + (uint32_t)stage * stage_bytes;
+      for (int k = 0; k < k_iters; ++k) {
+        umma_f16_ksteps_elect<KC / 16>(d_tmem, ((a_addr >> 4) & 0x3FFFu) | 0x10000u, desc_hi, ((b_addr >> 4) & 0x3FFFu) | 0x10000u,
+                                       desc_hi, idesc, accumulate);
+        accumulate = 1u;
+        a_addr += a_bytes;
+        b_addr += b_tile_bytes;
+      }
+      umma_commit_elect(EMPTY_BAR(stage));
+      stage += 2;
+      if (stage >= S) { stage -= S; phase ^= 1u; }
+      umma_commit_elect(TFULL_BAR(acc));
+    }
+#else
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t desc_hi = p.desc_hi, idesc = p.idesc, n_acc = (uint32_t)p.n_acc;
@@ -159,6 +202,7 @@ conv_head_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       umma_commit_elect(TFULL_BAR(acc));
       if (++acc == n_acc) { acc = 0; acc_phase ^= 1u; }
     }
+#endif
   } else {
     // ===================== epilogue: two groups of four warps, alternate tiles =====================
     const int ew = warp - 2, grp = ew >> 2, q = warp & 3;   // q = TMEM lane quarter this warp may read
@@ -408,6 +452,10 @@ int Net::head_plan_layer(ConvLayer& L) {
   const int stage_bytes = 3 * q.kchunks * q.a_bytes;   // a stage holds every input tile of one output tile
   int stages = (227 * 1024 - fixed) / stage_bytes;
   if (stages > 4) stages = 4;
+#if PCLS_HEAD_ISSUERS == 2
+  stages -= stages % 2;   // each issuer owns the stages of its parity
+  if (q.n_acc < 2) { delete plan; return PCLS_OK; }
+#endif
   if (stages < 2) { delete plan; return PCLS_OK; }
   q.stages = stages;
   plan->smem_bytes = (size_t)stages * stage_bytes + fixed;
